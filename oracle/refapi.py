@@ -36,14 +36,35 @@ def _up(a):
     return None if a is None else a.ctypes.data_as(_u64p)
 
 
+class _NS:
+    """maps lib.oref_xxx -> lib.<prefix>xxx so one front-end drives the reference hooks and the port"""
+
+    def __init__(self, lib, prefix):
+        object.__setattr__(self, "_lib", lib)
+        object.__setattr__(self, "_prefix", prefix)
+
+    def __getattr__(self, name):
+        assert name.startswith("oref_")
+        return getattr(self._lib, self._prefix + name[5:])
+
+
 class RefSession:
     """One source set + one target set run through the reference's own call sequence."""
 
-    def __init__(self, physics, nsrc, ntarg, block=128, order=4, eq_block=128, build="strict"):
-        self.lib = C.CDLL(ref_lib_path(physics, build))
-        L = self.lib
+    _prefix = "oref_"
+
+    def _open(self, physics, build):
+        return C.CDLL(ref_lib_path(physics, build))
+
+    def _create(self, L, physics, nsrc, ntarg, block, eq_block, order):
         L.oref_create.restype = C.c_void_p
         L.oref_create.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
+        return L.oref_create(nsrc, ntarg, block, eq_block, order)
+
+    def __init__(self, physics, nsrc, ntarg, block=128, order=4, eq_block=128, build="strict"):
+        self.rawlib = self._open(physics, build)
+        self.lib = _NS(self.rawlib, self._prefix)
+        L = self.lib
         L.oref_destroy.argtypes = [C.c_void_p]
         L.oref_init_driver.argtypes = [C.c_void_p, C.c_int]
         L.oref_set_sources.argtypes = [C.c_void_p, _f32p, _f32p, _f32p]
@@ -63,12 +84,15 @@ class RefSession:
         L.oref_get_parts.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _f32p, _u64p]
         L.oref_tree_shape.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.oref_get_tree.argtypes = [C.c_void_p, C.c_int] + [_f32p] * 6 + [_u64p] * 4
-        pd, sd, od, hf = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-        L.oref_dims(C.byref(pd), C.byref(sd), C.byref(od), C.byref(hf))
-        self.PD, self.SD, self.OD, self.has_fastsumm = pd.value, sd.value, od.value, bool(hf.value)
         self.physics = physics
         self.nsrc, self.ntarg = int(nsrc), int(ntarg)
-        self.h = L.oref_create(nsrc, ntarg, block, eq_block, order)
+        self.h = self._create(L, physics, nsrc, ntarg, block, eq_block, order)
+        pd, sd, od, hf = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._dims(L, pd, sd, od, hf)
+        self.PD, self.SD, self.OD, self.has_fastsumm = pd.value, sd.value, od.value, bool(hf.value)
+
+    def _dims(self, L, pd, sd, od, hf):
+        L.oref_dims(C.byref(pd), C.byref(sd), C.byref(od), C.byref(hf))
 
     def close(self):
         if self.h:
@@ -139,9 +163,55 @@ class RefSession:
         return out
 
 
+def port_lib_path():
+    return os.path.join(_HERE, "libonbody_oracle.so")
+
+
+class PortSession(RefSession):
+    """Same front-end over the CPU restatement oracle/port/oracle_port.cpp (libonbody_oracle.so)."""
+
+    _prefix = "oport_"
+
+    def _open(self, physics, build):
+        return C.CDLL(port_lib_path())
+
+    def _create(self, L, physics, nsrc, ntarg, block, eq_block, order):
+        L.oref_create.restype = C.c_void_p
+        L.oref_create.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
+        return L.oref_create(PHYSICS.index(physics), nsrc, ntarg, block, eq_block, order)
+
+    def _dims(self, L, pd, sd, od, hf):
+        L.oref_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        L.oref_dims(self.h, C.byref(pd), C.byref(sd), C.byref(od), C.byref(hf))
+
+    def stats(self):
+        """sltp sbtp | sltl sbtl sltb sbtb tlc lpc bpc of the last treecode / dual-tree call"""
+        out = (C.c_uint64 * 9)()
+        self.rawlib.oport_get_stats.argtypes = [C.c_void_p, C.c_uint64 * 9]
+        self.rawlib.oport_get_stats(self.h, out)
+        k = ("sltp", "sbtp", "sltl", "sbtl", "sltb", "sbtb", "tlc", "lpc", "bpc")
+        return dict(zip(k, [int(v) for v in out]))
+
+    def build_stats(self):
+        out = (C.c_uint64 * 4)()
+        self.rawlib.oport_get_build_stats.argtypes = [C.c_void_p, C.c_uint64 * 4]
+        self.rawlib.oport_get_build_stats(self.h, out)
+        return dict(zip(("selects", "passes", "stalls", "scanned"), [int(v) for v in out]))
+
+    def refine_tie_sorts(self):
+        self.rawlib.oport_refine_tie_sorts.restype = C.c_uint64
+        self.rawlib.oport_refine_tie_sorts.argtypes = [C.c_void_p]
+        return int(self.rawlib.oport_refine_tie_sorts(self.h))
+
+
 def fnv1a64(a):
     """FNV-1a-64 over the raw little-endian bytes (the hash SURVEY.md section 4 quotes)."""
     data = np.ascontiguousarray(a).view(np.uint8)
+    if os.path.exists(port_lib_path()):
+        lib = C.CDLL(port_lib_path())
+        lib.oport_fnv1a64.restype = C.c_uint64
+        lib.oport_fnv1a64.argtypes = [C.c_void_p, C.c_uint64]
+        return int(lib.oport_fnv1a64(data.ctypes.data, data.size))
     h = np.uint64(1469598103934665603)
     prime = np.uint64(1099511628211)
     # vectorising FNV is not possible (serial dependency): chunked pure-python loop is fine up to ~1e6 bytes,
