@@ -1,0 +1,143 @@
+/*
+ * onbody_b200.h - C ABI of the B200-native (sm_100a) summation hot path of onbody.
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types. The shared library
+ * (onbody_b200/libonbody_b200.so) links the CUDA runtime statically, so callers do not link CUDA.
+ * There is NO CPU fallback: every entry point fails with a non-zero code (and onb_error() says why)
+ * when no sm_100 device is usable.
+ *
+ * The entry points mirror, one for one, the free functions the reference's drivers call between
+ * "particles are initialised" and "results are compared" (reference src/ongrav3d.cpp:600-908):
+ *
+ *   onb_make_tree     <- makeTree()                   barneshut.hpp:814-854  (splitNode :594, finishTree :717)
+ *   onb_refine        <- refineTree()                 barneshut.hpp:901-936
+ *   onb_upward        <- calcBarycentricLagrange()    BarycentricLagrange.hpp:255-417 (+ eq*.resize, ongrav3d.cpp:645,696)
+ *   onb_naive         <- nbody_naive()                barneshut.hpp:46-53
+ *   onb_treecode1     <- nbody_treecode1()            barneshut.hpp:107-132
+ *   onb_treecode2     <- nbody_treecode2()            barneshut.hpp:189-222  (pointwise)
+ *   onb_treecode3     <- nbody_treecode3()            barneshut.hpp:299-337  (boxwise)
+ *   onb_fastsumm      <- nbody_fastsumm()             ongrav3d.cpp:206-452   (dual-tree, incl. calcBarycentricDownward)
+ *   onb_zero_vels     <- Parts::zero_vels()           Parts.hpp:179-183
+ *
+ * The drop-in Fortran-style entry points external_vel_solver_f_ / external_vel_direct_f_ live in two
+ * separate shim libraries (same symbol names, different arity - exactly as in the reference):
+ * include/onbody_bh2dvort.h and include/onbody_bh3dvortgrads.h.
+ *
+ * "which" arguments: 0 = sources, 1 = targets, 2 = equivalent sources, 3 = equivalent targets.
+ * All array arguments are HOST pointers; planar layout: x is [PD][n], s is [SD][n], u is [OD][n].
+ */
+#ifndef ONBODY_B200_H
+#define ONBODY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONB_API __attribute__((visibility("default")))
+
+typedef struct onb_context onb_context;
+
+/* physics of the pair kernel = which reference driver is being replaced */
+enum {
+    ONB_GRAV3D     = 0,  /* ongrav3d.cpp:44-58       PD 3 SD 1 OD 3   19 flop/pair */
+    ONB_VORT3D     = 1,  /* onvort3d.cpp:44-59       PD 3 SD 3 OD 3   28 flop/pair */
+    ONB_VORTGRAD3D = 2,  /* onvortgrad3d.cpp:45-76   PD 3 SD 3 OD 12  64 flop/pair */
+    ONB_VORT2D     = 3,  /* interface2dvort.cpp:39-50  PD 2 SD 1 OD 2 13 flop/pair */
+    ONB_VORT2DTR   = 4   /* onvort2d.cpp:44-55 (+target radius) PD 2 SD 1 OD 2 15 flop/pair */
+};
+
+/* arithmetic of the pair / interpolation kernels */
+enum {
+    ONB_ARITH_FAST   = 0, /* rsqrt + FMA: the product path */
+    ONB_ARITH_STRICT = 1  /* the reference's IEEE operation sequence, for bit-exact verification */
+};
+
+/* error codes */
+enum {
+    ONB_OK = 0,
+    ONB_ERR_CUDA = 1,       /* a CUDA call failed (no device, OOM, launch failure) */
+    ONB_ERR_ARG = 2,        /* invalid argument or call order */
+    ONB_ERR_CAPACITY = 3,   /* an internal work queue overflowed */
+    ONB_ERR_UNSUPPORTED = 4 /* a path the GPU build does not implement (e.g. order < 1) */
+};
+
+/* lifetime ----------------------------------------------------------------------------------- */
+/* creates a context on CUDA device `device`; returns NULL (see onb_last_create_error) if there is none */
+ONB_API onb_context* onb_create(int physics, int device);
+ONB_API void         onb_destroy(onb_context* c);
+ONB_API const char*  onb_error(const onb_context* c);
+ONB_API const char*  onb_last_create_error(void);
+
+/* block size (-b, default 128), barycentric order (-o, >=1) and arithmetic; call before set_sources */
+ONB_API int onb_set_params(onb_context* c, int block_size, int order, int arith);
+ONB_API void onb_dims(const onb_context* c, int* pd, int* sd, int* od, int* has_fastsumm);
+
+/* inputs (host -> device copies) ------------------------------------------------------------- */
+ONB_API int onb_set_sources(onb_context* c, uint64_t n, const float* x, const float* r, const float* s);
+ONB_API int onb_set_targets(onb_context* c, uint64_t n, const float* x, const float* r);
+/* the drivers' own synthetic initialisation (std::mt19937(12345), Parts.hpp:99-109,169-176), done on the
+ * host into caller buffers: x [PD][n], r [n], s [SD][n] (s may be NULL for targets). strength_mode 1 = wave_strengths */
+ONB_API int onb_driver_inputs(int physics, uint64_t n, int strength_mode, float* x, float* r, float* s);
+
+/* phases ------------------------------------------------------------------------------------- */
+ONB_API int onb_make_tree(onb_context* c, int which);
+ONB_API int onb_refine(onb_context* c, int which);
+ONB_API int onb_upward(onb_context* c, int which);
+ONB_API int onb_zero_vels(onb_context* c);
+ONB_API int onb_naive(onb_context* c, uint64_t tskip, float* flops);
+ONB_API int onb_treecode1(onb_context* c, float theta, float* flops);
+ONB_API int onb_treecode2(onb_context* c, float theta, float* flops);
+ONB_API int onb_treecode3(onb_context* c, float theta, float* flops);
+ONB_API int onb_fastsumm(onb_context* c, float theta);
+
+/* target sharding for multi-GPU runs: this context evaluates only the targets of shard `rank` of `nranks`
+ * (contiguous tree-order ranges of target leaves); the trees themselves are built in full. */
+ONB_API int onb_set_shard(onb_context* c, int rank, int nranks);
+
+/* outputs (device -> host copies) ------------------------------------------------------------ */
+ONB_API uint64_t onb_count(const onb_context* c, int which);
+ONB_API int onb_get_parts(onb_context* c, int which, float* x, float* r, float* s, float* u, uint64_t* gidx);
+/* results scattered back to the caller's original target order and ADDED to u (the reference's
+ * external_vel_solver_f_ semantics, interface3dvortgrads.cpp:384-395); u is [OD][n] */
+ONB_API int onb_add_results_original_order(onb_context* c, float* u);
+ONB_API int onb_tree_shape(const onb_context* c, int which, int* levels, int* numnodes);
+ONB_API int onb_get_tree(onb_context* c, int which, float* x, float* nc, float* ns, float* nr, float* pr, float* s,
+                 uint64_t* ioffset, uint64_t* num, uint64_t* epoffset, uint64_t* epnum);
+
+/* counters of the last treecode / dual-tree call: sltp sbtp | sltl sbtl sltb sbtb tlc lpc bpc
+ * (the reference's treecode_stats barneshut.hpp:58-60 and fastsumm_stats ongrav3d.cpp:193-196) */
+ONB_API int onb_get_stats(const onb_context* c, uint64_t out[9]);
+
+/* measurement ------------------------------------------------------------------------------- */
+/* device time (CUDA events on the context's stream) of the named phase of the last call that ran it, in ms;
+ * names: "tree", "refine", "upward", "lists", "p2p", "downward", "eval". Returns <0 if never run. */
+ONB_API double   onb_phase_ms(const onb_context* c, const char* name);
+/* exact number of source-target pairs the pair kernels evaluated in the last evaluation call */
+ONB_API uint64_t onb_last_pairs(const onb_context* c);
+/* number of kernel launches issued by this context since creation */
+ONB_API uint64_t onb_launch_count(const onb_context* c);
+/* FP32 FMA issue-rate microbenchmark on this device: returns measured TFLOP/s (2 flop per FMA lane) */
+ONB_API double   onb_measure_fp32_peak(onb_context* c);
+/* raw device pointers for zero-copy plumbing (e.g. an NCCL all-gather issued from the host language):
+ * field: 0..2 x[d], 3 r, 4..6 s[d]; returns NULL if absent */
+ONB_API void*    onb_device_ptr(onb_context* c, int which, int field);
+
+/* diagnostics of the last onb_make_tree / onb_refine: selects, partition passes, stall exits, elements scanned, and the
+ * number of in-leaf sorts that met equal keys (where libstdc++'s introsort order had to be reproduced) */
+ONB_API int onb_get_build_stats(onb_context* c, uint64_t out[5]);
+/* pivot arithmetic of the partial select: 0 (default) = the reference source evaluated in IEEE order (matches the
+ * reference built with -O2 -ffp-contract=off); 1 = with the contractions g++ -O3 -ffast-math applies to
+ * barneshut.hpp:538-540 (matches that build's intra-leaf source order as well). Process-wide. */
+ONB_API void onb_set_pivot_mode(int mode);
+
+/* test support: install an already-built tree + already-ordered particles (lets each phase be parity-
+ * tested in isolation against the oracle). Arrays as in onb_get_tree. */
+ONB_API int onb_load_tree(onb_context* c, int which, int levels, const float* x, const float* nc, const float* ns,
+                  const float* nr, const float* pr, const float* s, const uint64_t* ioffset, const uint64_t* num);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONBODY_B200_H */

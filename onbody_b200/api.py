@@ -1,0 +1,248 @@
+"""ctypes mirror of include/onbody_b200.h.
+
+``GpuSession`` exposes the same phase methods, in the same order and with the same meaning, as the reference
+drivers call them (make_tree / refine / upward / naive / treecode1,2,3 / fastsumm); tests drive it side by side
+with the oracle's session objects. Nothing here computes: every method is one call through the C ABI.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PHYSICS = ("grav3d", "vort3d", "vortgrad3d", "vort2d", "vort2dtr")
+_WAVE = {"grav3d": 0, "vort3d": 1, "vortgrad3d": 1, "vort2d": 0, "vort2dtr": 0}
+_DIMS = {"grav3d": (3, 1, 3), "vort3d": (3, 3, 3), "vortgrad3d": (3, 3, 12), "vort2d": (2, 1, 2), "vort2dtr": (2, 1, 2)}
+
+ARITH_FAST, ARITH_STRICT = 0, 1
+
+_f32p = C.POINTER(C.c_float)
+_u64p = C.POINTER(C.c_uint64)
+
+
+class OnbodyError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libonbody_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Loads the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise OnbodyError("%s is missing: run `python -m onbody_b200.build` (nvcc, sm_100a). "
+                          "There is no CPU fallback." % p)
+    L = C.CDLL(p)
+    L.onb_create.restype = C.c_void_p
+    L.onb_create.argtypes = [C.c_int, C.c_int]
+    L.onb_destroy.argtypes = [C.c_void_p]
+    L.onb_error.restype = C.c_char_p
+    L.onb_error.argtypes = [C.c_void_p]
+    L.onb_last_create_error.restype = C.c_char_p
+    L.onb_set_params.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.onb_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+    L.onb_set_sources.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.onb_set_targets.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.onb_driver_inputs.argtypes = [C.c_int, C.c_uint64, C.c_int, _f32p, _f32p, _f32p]
+    for fn in ("onb_make_tree", "onb_refine", "onb_upward"):
+        getattr(L, fn).argtypes = [C.c_void_p, C.c_int]
+    L.onb_zero_vels.argtypes = [C.c_void_p]
+    L.onb_naive.argtypes = [C.c_void_p, C.c_uint64, _f32p]
+    for fn in ("onb_treecode1", "onb_treecode2", "onb_treecode3"):
+        getattr(L, fn).argtypes = [C.c_void_p, C.c_float, _f32p]
+    L.onb_fastsumm.argtypes = [C.c_void_p, C.c_float]
+    L.onb_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.onb_count.restype = C.c_uint64
+    L.onb_count.argtypes = [C.c_void_p, C.c_int]
+    L.onb_get_parts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.onb_add_results_original_order.argtypes = [C.c_void_p, C.c_void_p]
+    L.onb_tree_shape.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.onb_get_tree.argtypes = [C.c_void_p, C.c_int] + [_f32p] * 6 + [_u64p] * 4
+    L.onb_get_stats.argtypes = [C.c_void_p, C.c_uint64 * 9]
+    L.onb_phase_ms.restype = C.c_double
+    L.onb_phase_ms.argtypes = [C.c_void_p, C.c_char_p]
+    L.onb_last_pairs.restype = C.c_uint64
+    L.onb_last_pairs.argtypes = [C.c_void_p]
+    L.onb_launch_count.restype = C.c_uint64
+    L.onb_launch_count.argtypes = [C.c_void_p]
+    L.onb_measure_fp32_peak.restype = C.c_double
+    L.onb_measure_fp32_peak.argtypes = [C.c_void_p]
+    L.onb_load_tree.argtypes = [C.c_void_p, C.c_int, C.c_int] + [_f32p] * 6 + [_u64p] * 2
+    L.onb_get_build_stats.argtypes = [C.c_void_p, C.c_uint64 * 5]
+    _lib = L
+    return L
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(_f32p)
+
+
+def _up(a):
+    return None if a is None else a.ctypes.data_as(_u64p)
+
+
+def driver_inputs(physics, n, sources=True):
+    """The reference drivers' synthetic inputs (mt19937(12345), Parts.hpp:99-109, wave_strengths :169-176),
+    generated on the host by the product library. Returns x [PD,n], r [n], s [SD,n] (s None for targets)."""
+    L = load_library()
+    PD, SD, _ = _DIMS[physics]
+    x = np.empty((PD, n), np.float32); r = np.empty(n, np.float32)
+    s = np.empty((SD, n), np.float32) if sources else None
+    rc = L.onb_driver_inputs(PHYSICS.index(physics), n, _WAVE[physics], _fp(x), _fp(r), _fp(s))
+    if rc != 0:
+        raise OnbodyError("onb_driver_inputs failed (%d)" % rc)
+    return x, r, s
+
+
+class GpuSession:
+    """One source set + one target set on one B200, phase by phase."""
+
+    def __init__(self, physics, nsrc=None, ntarg=None, block=128, order=4, arith=ARITH_FAST, device=0, **_ignored):
+        self.lib = load_library()
+        self.physics = physics
+        self.PD, self.SD, self.OD = _DIMS[physics]
+        self.has_fastsumm = physics != "vortgrad3d"
+        self.nsrc, self.ntarg = nsrc, ntarg
+        self.h = self.lib.onb_create(PHYSICS.index(physics), device)
+        if not self.h:
+            raise OnbodyError("onb_create failed: %s" % self.lib.onb_last_create_error().decode())
+        self._chk(self.lib.onb_set_params(self.h, block, order, arith))
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise OnbodyError("onbody_b200 error %d: %s" % (rc, self.lib.onb_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.onb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs (host arrays; may be pinned torch tensors' numpy views or raw pointers)
+    def init_driver(self):
+        n = self.nsrc
+        x, r, s = driver_inputs(self.physics, n, True)
+        self.set_sources(x, r, s)
+        if self.ntarg == n:
+            self.set_targets(x, r)          # the drivers copy the engine: targets == sources (ongrav3d.cpp:574-594)
+        else:
+            tx, tr, _ = driver_inputs(self.physics, self.ntarg, False)
+            self.set_targets(tx, tr)
+
+    def set_sources(self, x, r, s):
+        x = np.ascontiguousarray(x, np.float32); r = np.ascontiguousarray(r, np.float32); s = np.ascontiguousarray(s, np.float32)
+        n = r.shape[0]
+        assert x.shape == (self.PD, n) and s.shape == (self.SD, n)
+        self.nsrc = n
+        self._chk(self.lib.onb_set_sources(self.h, n, x.ctypes.data, r.ctypes.data, s.ctypes.data))
+
+    def set_targets(self, x, r):
+        x = np.ascontiguousarray(x, np.float32); r = np.ascontiguousarray(r, np.float32)
+        n = r.shape[0]
+        assert x.shape == (self.PD, n)
+        self.ntarg = n
+        self._chk(self.lib.onb_set_targets(self.h, n, x.ctypes.data, r.ctypes.data))
+
+    def set_sources_ptr(self, n, x_ptr, r_ptr, s_ptr):
+        self.nsrc = n
+        self._chk(self.lib.onb_set_sources(self.h, n, x_ptr, r_ptr, s_ptr))
+
+    def set_targets_ptr(self, n, x_ptr, r_ptr):
+        self.ntarg = n
+        self._chk(self.lib.onb_set_targets(self.h, n, x_ptr, r_ptr))
+
+    def set_shard(self, rank, nranks):
+        self._chk(self.lib.onb_set_shard(self.h, rank, nranks))
+
+    # ---- phases
+    def make_tree(self, which): self._chk(self.lib.onb_make_tree(self.h, which))
+    def refine(self, which): self._chk(self.lib.onb_refine(self.h, which))
+    def upward(self, which): self._chk(self.lib.onb_upward(self.h, which))
+    def zero_vels(self): self._chk(self.lib.onb_zero_vels(self.h))
+
+    def naive(self, tskip=1):
+        f = C.c_float(); self._chk(self.lib.onb_naive(self.h, tskip, C.byref(f))); return f.value
+
+    def treecode1(self, theta):
+        f = C.c_float(); self._chk(self.lib.onb_treecode1(self.h, theta, C.byref(f))); return f.value
+
+    def treecode2(self, theta):
+        f = C.c_float(); self._chk(self.lib.onb_treecode2(self.h, theta, C.byref(f))); return f.value
+
+    def treecode3(self, theta):
+        f = C.c_float(); self._chk(self.lib.onb_treecode3(self.h, theta, C.byref(f))); return f.value
+
+    def fastsumm(self, theta, parallel=False):
+        self._chk(self.lib.onb_fastsumm(self.h, theta))
+
+    # ---- outputs
+    def parts(self, which, want=("x", "r", "s", "u", "gidx")):
+        n = int(self.lib.onb_count(self.h, which))
+        src = which in (0, 2)
+        x = np.zeros((self.PD, n), np.float32) if "x" in want else None
+        r = np.zeros(n, np.float32) if "r" in want else None
+        s = np.zeros((self.SD, n), np.float32) if (src and "s" in want) else None
+        u = np.zeros((self.OD, n), np.float32) if (not src and "u" in want) else None
+        g = np.full(n, np.iinfo(np.uint64).max, np.uint64) if (which == 1 and "gidx" in want) else None
+        ptr = lambda a: None if a is None else a.ctypes.data
+        self._chk(self.lib.onb_get_parts(self.h, which, ptr(x), ptr(r), ptr(s), ptr(u), ptr(g)))
+        return {"n": n, "x": x, "r": r, "s": s, "u": u, "gidx": g}
+
+    def results_into(self, u_ptr):
+        """device -> host copy of the target outputs [OD][n] (tree order) into caller memory"""
+        self._chk(self.lib.onb_get_parts(self.h, 1, None, None, None, u_ptr, None))
+
+    def add_results_original_order(self, u):
+        assert u.dtype == np.float32 and u.shape == (self.OD, self.ntarg) and u.flags.c_contiguous
+        self._chk(self.lib.onb_add_results_original_order(self.h, u.ctypes.data))
+
+    def tree(self, which):
+        lev, nn = C.c_int(), C.c_int()
+        self._chk(self.lib.onb_tree_shape(self.h, which, C.byref(lev), C.byref(nn)))
+        n = nn.value
+        out = {"levels": lev.value, "numnodes": n,
+               "x": np.zeros((self.PD, n), np.float32), "nc": np.zeros((self.PD, n), np.float32),
+               "ns": np.zeros((self.PD, n), np.float32), "nr": np.zeros(n, np.float32),
+               "pr": np.zeros(n, np.float32), "s": np.zeros((self.SD, n), np.float32),
+               "ioffset": np.zeros(n, np.uint64), "num": np.zeros(n, np.uint64),
+               "epoffset": np.zeros(n, np.uint64), "epnum": np.zeros(n, np.uint64)}
+        self._chk(self.lib.onb_get_tree(self.h, which, _fp(out["x"]), _fp(out["nc"]), _fp(out["ns"]), _fp(out["nr"]),
+                                        _fp(out["pr"]), _fp(out["s"]), _up(out["ioffset"]), _up(out["num"]),
+                                        _up(out["epoffset"]), _up(out["epnum"])))
+        return out
+
+    def load_tree(self, which, t):
+        """test support: install an oracle-built tree (particles must already be set in tree order)"""
+        c = lambda a, dt: np.ascontiguousarray(a, dt)
+        self._chk(self.lib.onb_load_tree(self.h, which, int(t["levels"]), _fp(c(t["x"], np.float32)), _fp(c(t["nc"], np.float32)),
+                                         _fp(c(t["ns"], np.float32)), _fp(c(t["nr"], np.float32)), _fp(c(t["pr"], np.float32)),
+                                         _fp(c(t["s"], np.float32)), _up(c(t["ioffset"], np.uint64)), _up(c(t["num"], np.uint64))))
+
+    def stats(self):
+        out = (C.c_uint64 * 9)()
+        self.lib.onb_get_stats(self.h, out)
+        k = ("sltp", "sbtp", "sltl", "sbtl", "sltb", "sbtb", "tlc", "lpc", "bpc")
+        return dict(zip(k, [int(v) for v in out]))
+
+    def build_stats(self):
+        out = (C.c_uint64 * 5)()
+        self._chk(self.lib.onb_get_build_stats(self.h, out))
+        return dict(zip(("selects", "passes", "stalls", "scanned", "tie_sorts"), [int(v) for v in out]))
+
+    def phase_ms(self, name): return float(self.lib.onb_phase_ms(self.h, name.encode()))
+    def last_pairs(self): return int(self.lib.onb_last_pairs(self.h))
+    def launch_count(self): return int(self.lib.onb_launch_count(self.h))
+    def measure_fp32_peak(self): return float(self.lib.onb_measure_fp32_peak(self.h))

@@ -1,0 +1,189 @@
+/*
+ * bary.cu - barycentric Lagrange equivalent particles: upward pass (anterpolation of strengths onto the
+ * (order+1)^PD Chebyshev points of every non-leaf node) and downward pass (interpolation of the parent's
+ * equivalent-target values onto a child's points, fused with the zero-fill the dual-tree traversal does at node entry).
+ *
+ * Replaces reference src/BarycentricLagrange.hpp: set_sk/set_wk :28-48, calcBarycentricLagrange :255-417,
+ * calcBarycentricUpward :175-248, calcBarycentricDownward :62-166 (called from ongrav3d.cpp:232,257,270,296).
+ *
+ * One CTA per tree node, one level per launch (children before parents going up, parents before children going
+ * down). Phase A: one thread per contributing point builds its PD x (order+1) one-dimensional weights and the
+ * normalising denominator in shared memory. Phase B: one thread per equivalent point walks the contributors in
+ * the reference's order (child 2i first, then 2i+1; points in index order) and accumulates. The arithmetic is the
+ * reference's IEEE sequence (true divisions, no FMA contraction): these passes move O(N) data once and are
+ * HBM-bound, so exact arithmetic costs nothing measurable and makes equivalent strengths bit-comparable.
+ */
+#include "onb_internal.h"
+#include <cmath>
+
+namespace {
+
+constexpr int AM_STRIDE = 23;     // >= PD*(order+1) for every supported (PD, order), odd -> conflict-free rows
+
+struct Cheb { float sk[ONB_MAX_ORDER + 1]; float wk[ONB_MAX_ORDER + 1]; };
+
+struct UpArgs {
+    PartsView p, ep; TreeView t; Cheb ch;
+    uint32_t block, ebs; int level, PD, SD, ncp, numEqps, are_sources;
+};
+
+// 1-D weights of one point against the node's Chebyshev coordinates lsk[d*ncp+k]; row = PD*ncp floats.
+// Returns 1/prod_d(sum_k a_dk)   (BarycentricLagrange.hpp:193-225 == :105-137)
+__device__ __forceinline__ float bary_row(int PD, int ncp, const float* wk, const float* px, const float* lsk, float* row) {
+    float denom = 1.0f;
+    for (int d = 0; d < PD; ++d) {
+        int flag = -1; float sum = 0.0f;
+        for (int k = 0; k < ncp; ++k) {
+            row[d * ncp + k] = 0.0f;
+            const float dist = __fsub_rn(px[d], lsk[d * ncp + k]);
+            if ((double)fabsf(dist) < 1.e-10) flag = k;                                   // CLOSE_THRESH :16
+            else { const float am = __fdiv_rn(wk[k], dist); row[d * ncp + k] = am; sum = __fadd_rn(sum, am); }
+        }
+        if (flag > -1) { sum = 1.0f; for (int k = 0; k < ncp; ++k) row[d * ncp + k] = 0.0f; row[d * ncp + flag] = 1.0f; }
+        denom = __fmul_rn(denom, sum);
+    }
+    return __fdiv_rn(1.0f, denom);
+}
+
+__global__ void __launch_bounds__(128) k_upward(const UpArgs a) {
+    const uint32_t node = (1u << a.level) + blockIdx.x;
+    if (a.t.num[node] <= a.block) return;                                                 // :266 leaves have no equivalents
+    const int tid = threadIdx.x, PD = a.PD, SD = a.SD, ncp = a.ncp, numEqps = a.numEqps;
+    __shared__ float lsk[3 * (ONB_MAX_ORDER + 1)];
+    __shared__ float s_am[128 * AM_STRIDE];
+    __shared__ float s_den[128];
+    __shared__ float s_str[3][128];
+    const uint32_t e0 = node * a.ebs;                                                     // :289
+    if (tid < PD * ncp) {
+        const int d = tid / ncp, k = tid % ncp;
+        lsk[tid] = __fadd_rn(a.t.nc[d][node], __fmul_rn(__fmul_rn(0.5f, a.ch.sk[k]), a.t.ns[d][node]));   // :305
+    }
+    // my equivalent point's Chebyshev indices
+    int kd[3] = {0, 0, 0};
+    { int q = tid; for (int d = 0; d < PD; ++d) { kd[d] = q % ncp; q /= ncp; } }
+    __syncthreads();
+    if ((uint32_t)tid < a.ebs) {
+        const float rr = a.p.r[a.t.ioffset[node]];                                        // :353
+        for (int d = 0; d < PD; ++d)
+            a.ep.x[d][e0 + tid] = tid < numEqps ? lsk[d * ncp + kd[d]] : a.t.nc[d][node]; // :330, :336
+        a.ep.r[e0 + tid] = rr;
+    }
+    if (!a.are_sources) return;                                                           // target trees: positions only (:378,:400)
+
+    float acc[3] = {0.0f, 0.0f, 0.0f};                                                    // :343-347
+    for (uint32_t child = 2 * node; child < 2 * node + 2; ++child) {                      // :360
+        const uint32_t cn = a.t.num[child];
+        const bool leaf = cn <= a.block;
+        const PartsView& sp = leaf ? a.p : a.ep;
+        const uint32_t is = leaf ? a.t.ioffset[child] : child * a.ebs;
+        const int cnt = leaf ? (int)cn : numEqps;
+        if (tid < cnt) {
+            float px[3];
+            for (int d = 0; d < PD; ++d) px[d] = sp.x[d][is + tid];
+            s_den[tid] = bary_row(PD, ncp, a.ch.wk, px, lsk, &s_am[tid * AM_STRIDE]);
+            for (int d = 0; d < SD; ++d) s_str[d][tid] = sp.s[d][is + tid];
+        }
+        __syncthreads();
+        if (tid < numEqps) {
+            for (int j = 0; j < cnt; ++j) {                                               // :190, :228-241
+                const float* row = &s_am[j * AM_STRIDE];
+                float wgt = s_den[j];
+                for (int d = 0; d < PD; ++d) wgt = __fmul_rn(wgt, row[d * ncp + kd[d]]);
+                for (int d = 0; d < SD; ++d) acc[d] = __fadd_rn(acc[d], __fmul_rn(wgt, s_str[d][j]));
+            }
+        }
+        __syncthreads();
+    }
+    if ((uint32_t)tid < a.ebs) for (int d = 0; d < SD; ++d) a.ep.s[d][e0 + tid] = tid < numEqps ? acc[d] : 0.0f;
+}
+
+// ---- downward: zero-fill + interpolation from the parent, one CTA per target node of this level ----
+struct DownArgs {
+    PartsView tl, tb; TreeView t; Cheb ch;
+    uint32_t block, ebs, shard_lo, shard_hi; int level, PD, OD, ncp, numEqps;
+};
+
+__global__ void __launch_bounds__(128) k_downward(const DownArgs a) {
+    const uint32_t T = (1u << a.level) + blockIdx.x;
+    const uint32_t tn = a.t.num[T];
+    if (tn < 1) return;                                                                   // ongrav3d.cpp:221
+    const uint32_t tio = a.t.ioffset[T];
+    if (!(tio < a.shard_hi && tio + tn > a.shard_lo)) return;                             // not needed by this shard
+    const int tid = threadIdx.x, PD = a.PD, OD = a.OD, ncp = a.ncp, numEqps = a.numEqps;
+    const bool leaf = tn <= a.block;
+    const PartsView& tp = leaf ? a.tl : a.tb;
+    const uint32_t p0 = leaf ? tio : T * a.ebs;
+    const int cnt = leaf ? (int)tn : numEqps;
+    __shared__ float lsk[3 * (ONB_MAX_ORDER + 1)];
+    __shared__ float s_am[128 * AM_STRIDE];
+    __shared__ float s_pu[3][128];
+    float acc[3] = {0.0f, 0.0f, 0.0f};                                                    // :232 / :270 zero fill
+    if (T > 1) {
+        const uint32_t pe0 = (T >> 1) * a.ebs;                                            // parent's equivalent points
+        if (tid < PD * ncp) {                                                             // BarycentricLagrange.hpp:78-89
+            const int d = tid / ncp, k = tid % ncp;
+            int stride = 1; for (int q = 0; q < d; ++q) stride *= ncp;
+            lsk[tid] = a.tb.x[d][pe0 + stride * k];
+        }
+        if (tid < numEqps) for (int d = 0; d < OD; ++d) s_pu[d][tid] = a.tb.u[d][pe0 + tid];
+        __syncthreads();
+        if (tid < cnt) {
+            float px[3];
+            for (int d = 0; d < PD; ++d) px[d] = tp.x[d][p0 + tid];
+            float* row = &s_am[tid * AM_STRIDE];
+            const float denom = bary_row(PD, ncp, a.ch.wk, px, lsk, row);
+            int k0 = 0, k1 = 0, k2 = 0;
+            for (int i = 0; i < numEqps; ++i) {                                           // :140-156
+                float wgt = __fmul_rn(denom, row[k0]);
+                if (PD > 1) wgt = __fmul_rn(wgt, row[ncp + k1]);
+                if (PD > 2) wgt = __fmul_rn(wgt, row[2 * ncp + k2]);
+                for (int d = 0; d < OD; ++d) acc[d] = __fadd_rn(acc[d], __fmul_rn(wgt, s_pu[d][i]));
+                if (++k0 == ncp) { k0 = 0; if (++k1 == ncp) { k1 = 0; ++k2; } }
+            }
+        }
+    }
+    if (tid < cnt) for (int d = 0; d < OD; ++d) tp.u[d][p0 + tid] = acc[d];
+}
+
+Cheb make_cheb(int order) {                                                               // set_sk / set_wk :28-48
+    Cheb c;
+    for (int k = 0; k <= ONB_MAX_ORDER; ++k) { c.sk[k] = 0.f; c.wk[k] = 0.f; }
+    for (int k = 0; k <= order; ++k) c.sk[k] = (float)(-std::cos(k * M_PI / order));
+    c.wk[0] = 0.5f;
+    for (int k = 1; k < order; ++k) c.wk[k] = (k % 2) ? -1.0f : 1.0f;
+    c.wk[order] = 0.5f * ((order % 2) ? -1.0f : 1.0f);
+    return c;
+}
+
+}  // namespace
+
+int onb_bary_upward(onb_context* c, DParts& p, DParts& ep, DTree& t) {
+    if (!t.built) { c->err = "upward: tree not built"; return ONB_ERR_ARG; }
+    const uint32_t need = (uint32_t)(t.numnodes / 2) * (uint32_t)c->ebs;                  // ongrav3d.cpp:645,696
+    if (ep.n != need) {
+        onb_free_parts(ep);
+        int rc = onb_alloc_parts(c, ep, need, p.are_sources);
+        if (rc) return rc;
+    }
+    UpArgs a; a.p = view_of(p); a.ep = view_of(ep); a.t = view_of(t); a.ch = make_cheb(c->order);
+    a.block = c->block; a.ebs = c->ebs; a.PD = c->PD; a.SD = c->SD; a.ncp = c->ncp; a.numEqps = c->num_eqps;
+    a.are_sources = p.are_sources ? 1 : 0;
+    for (int lev = t.levels - 2; lev >= 0; --lev) {      // the last level holds only leaves
+        a.level = lev;
+        k_upward<<<1u << lev, 128, 0, c->stream>>>(a); ONB_LAUNCH(c);
+    }
+    ONB_CUDA(cudaGetLastError());
+    ep.packed_valid = false;
+    return ONB_OK;
+}
+
+int onb_bary_downward_level(onb_context* c, int level) {
+    DTree& t = c->trees[1];
+    DownArgs a; a.tl = view_of(c->parts[1]); a.tb = view_of(c->parts[3]); a.t = view_of(t); a.ch = make_cheb(c->order);
+    a.block = c->block; a.ebs = c->ebs; a.level = level; a.PD = c->PD; a.OD = c->OD; a.ncp = c->ncp; a.numEqps = c->num_eqps;
+    // shard range in particle indices (contiguous target leaves)
+    onb_shard_range(c, &a.shard_lo, &a.shard_hi);
+    k_downward<<<1u << level, 128, 0, c->stream>>>(a); ONB_LAUNCH(c);
+    ONB_CUDA(cudaGetLastError());
+    return ONB_OK;
+}

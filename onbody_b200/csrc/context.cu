@@ -1,0 +1,408 @@
+/*
+ * context.cu - the C ABI (include/onbody_b200.h): device context, host<->device copies, and the phase
+ * sequence of the reference drivers (ongrav3d.cpp:600-908) expressed as calls into the CUDA kernels.
+ * Host-side C++ only orchestrates; there is no CPU compute path and every entry point fails loudly when the
+ * device is missing.
+ */
+#include "onb_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <random>
+
+static std::string g_create_error;
+
+// ---------------------------------------------------------------------------------------------
+// memory
+// ---------------------------------------------------------------------------------------------
+int onb_alloc_parts(onb_context* c, DParts& p, uint32_t n, bool are_sources) {
+    p = DParts();
+    p.n = n; p.cap = ((n + 63u) & ~31u) + 32u; p.PD = c->PD; p.SD = c->SD; p.OD = c->OD; p.are_sources = are_sources;
+    const size_t bytes = (size_t)p.cap * sizeof(float);
+    for (int d = 0; d < c->PD; ++d) { ONB_CUDA(cudaMalloc(&p.x[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.x[d], 0, bytes, c->stream)); }
+    ONB_CUDA(cudaMalloc(&p.r, bytes)); ONB_CUDA(cudaMemsetAsync(p.r, 0, bytes, c->stream));
+    if (are_sources) {
+        for (int d = 0; d < c->SD; ++d) { ONB_CUDA(cudaMalloc(&p.s[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.s[d], 0, bytes, c->stream)); }
+        ONB_CUDA(cudaMalloc(&p.pk0, (size_t)p.cap * sizeof(float4)));
+        const bool nf2 = c->physics == ONB_VORT3D || c->physics == ONB_VORTGRAD3D;
+        if (nf2) ONB_CUDA(cudaMalloc(&p.pk1, (size_t)p.cap * sizeof(float4)));
+        if (c->physics == ONB_GRAV3D) ONB_CUDA(cudaMalloc(&p.pk2, bytes));
+    } else {
+        for (int d = 0; d < c->OD; ++d) { ONB_CUDA(cudaMalloc(&p.u[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.u[d], 0, bytes, c->stream)); }
+    }
+    return ONB_OK;
+}
+void onb_free_parts(DParts& p) {
+    for (int d = 0; d < ONB_MAX_PD; ++d) if (p.x[d]) cudaFree(p.x[d]);
+    if (p.r) cudaFree(p.r);
+    for (int d = 0; d < ONB_MAX_SD; ++d) if (p.s[d]) cudaFree(p.s[d]);
+    for (int d = 0; d < ONB_MAX_OD; ++d) if (p.u[d]) cudaFree(p.u[d]);
+    if (p.gidx) cudaFree(p.gidx);
+    if (p.pk0) cudaFree(p.pk0); if (p.pk1) cudaFree(p.pk1); if (p.pk2) cudaFree(p.pk2);
+    p = DParts();
+}
+static inline uint32_t host_log2(uint32_t x) { return x == 0 ? 0 : 31 - __builtin_clz(x); }
+
+int onb_alloc_tree(onb_context* c, DTree& t, uint32_t n, int block) {
+    onb_free_tree(t);
+    const uint32_t numLeaf = 1 + (n - 1) / block;                                         // Tree.hpp:83-87
+    t.levels = 1 + host_log2(2 * numLeaf - 1);
+    t.numnodes = 1 << t.levels;
+    const size_t fb = (size_t)t.numnodes * sizeof(float), ub = (size_t)t.numnodes * sizeof(uint32_t);
+    for (int d = 0; d < c->PD; ++d) {
+        ONB_CUDA(cudaMalloc(&t.x[d], fb)); ONB_CUDA(cudaMalloc(&t.nc[d], fb)); ONB_CUDA(cudaMalloc(&t.ns[d], fb));
+        ONB_CUDA(cudaMemsetAsync(t.x[d], 0, fb, c->stream)); ONB_CUDA(cudaMemsetAsync(t.nc[d], 0, fb, c->stream)); ONB_CUDA(cudaMemsetAsync(t.ns[d], 0, fb, c->stream));
+    }
+    ONB_CUDA(cudaMalloc(&t.nr, fb)); ONB_CUDA(cudaMalloc(&t.pr, fb));
+    ONB_CUDA(cudaMemsetAsync(t.nr, 0, fb, c->stream)); ONB_CUDA(cudaMemsetAsync(t.pr, 0, fb, c->stream));
+    for (int d = 0; d < c->SD; ++d) { ONB_CUDA(cudaMalloc(&t.s[d], fb)); ONB_CUDA(cudaMemsetAsync(t.s[d], 0, fb, c->stream)); }
+    ONB_CUDA(cudaMalloc(&t.ioffset, ub)); ONB_CUDA(cudaMalloc(&t.num, ub));
+    ONB_CUDA(cudaMemsetAsync(t.ioffset, 0, ub, c->stream)); ONB_CUDA(cudaMemsetAsync(t.num, 0, ub, c->stream));
+    return ONB_OK;
+}
+void onb_free_tree(DTree& t) {
+    for (int d = 0; d < ONB_MAX_PD; ++d) { if (t.x[d]) cudaFree(t.x[d]); if (t.nc[d]) cudaFree(t.nc[d]); if (t.ns[d]) cudaFree(t.ns[d]); }
+    if (t.nr) cudaFree(t.nr); if (t.pr) cudaFree(t.pr);
+    for (int d = 0; d < ONB_MAX_SD; ++d) if (t.s[d]) cudaFree(t.s[d]);
+    if (t.ioffset) cudaFree(t.ioffset); if (t.num) cudaFree(t.num);
+    t = DTree();
+}
+int onb_check_flag(onb_context* c, const char* what) {
+    ONB_CUDA(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    const int f = *c->h_flag;
+    if (f != 0) {
+        c->err = std::string(what);
+        ONB_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+        return f;
+    }
+    return ONB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* onb_last_create_error(void) { return g_create_error.c_str(); }
+
+onb_context* onb_create(int physics, int device) {
+    if (physics < 0 || physics > 4) { g_create_error = "unknown physics id"; return nullptr; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this library has no CPU fallback)";
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return nullptr; }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return nullptr;
+    }
+    if (prop.major < 10) { g_create_error = "device is not sm_100 class (kernels are built for sm_100a only)"; return nullptr; }
+    onb_context* c = new onb_context();
+    static const int PDs[5] = {3, 3, 3, 2, 2}, SDs[5] = {1, 3, 3, 1, 1}, ODs[5] = {3, 3, 12, 2, 2}, FL[5] = {19, 28, 64, 13, 15};
+    c->physics = physics; c->device = device; c->PD = PDs[physics]; c->SD = SDs[physics]; c->OD = ODs[physics];
+    c->flops_per_pair = FL[physics]; c->has_tr = physics == ONB_VORT2DTR; c->has_fastsumm = physics != ONB_VORTGRAD3D;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&c->d_flag, sizeof(int)) != cudaSuccess || cudaMallocHost(&c->h_flag, sizeof(int)) != cudaSuccess) {
+        g_create_error = "context allocation failed"; delete c; return nullptr;
+    }
+    cudaMemset(c->d_flag, 0, sizeof(int));
+    onb_set_params(c, 128, 4, ONB_ARITH_FAST);
+    return c;
+}
+
+void onb_destroy(onb_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < 4; ++i) onb_free_parts(c->parts[i]);
+    for (int i = 0; i < 2; ++i) onb_free_tree(c->trees[i]);
+    if (c->d_flag) cudaFree(c->d_flag);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* onb_error(const onb_context* c) { return c ? c->err.c_str() : "null context"; }
+
+int onb_set_params(onb_context* c, int block_size, int order, int arith) {
+    if (!c) return ONB_ERR_ARG;
+    if (block_size < 2) { c->err = "block size must be >= 2"; return ONB_ERR_ARG; }
+    block_size = 2 * ((block_size + 1) / 2);            // the reference rounds -b up to even (ongrav3d.cpp:522, minBlkSz 2)
+    if (block_size > 128) { c->err = "block sizes above 128 are not supported by the GPU build"; return ONB_ERR_UNSUPPORTED; }
+    if (order < 1) { c->err = "order < 1 (the legacy pair-merge equivalents, -o omitted) is not implemented on the GPU"; return ONB_ERR_UNSUPPORTED; }
+    if (order > ONB_MAX_ORDER) { c->err = "order above 20"; return ONB_ERR_ARG; }
+    int ne = 1; for (int d = 0; d < c->PD; ++d) ne *= (order + 1);
+    if (ne > 128) { c->err = "(order+1)^PD exceeds the 128-slot equivalent block of the GPU build"; return ONB_ERR_UNSUPPORTED; }
+    c->block = block_size; c->order = order; c->arith = arith; c->ncp = order + 1; c->num_eqps = ne; c->ebs = 128;
+    return ONB_OK;
+}
+
+void onb_dims(const onb_context* c, int* pd, int* sd, int* od, int* hf) { *pd = c->PD; *sd = c->SD; *od = c->OD; *hf = c->has_fastsumm; }
+
+int onb_set_shard(onb_context* c, int rank, int nranks) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) { c->err = "bad shard"; return ONB_ERR_ARG; }
+    c->shard_rank = rank; c->shard_n = nranks; return ONB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// inputs
+// ---------------------------------------------------------------------------------------------
+static int set_parts(onb_context* c, int which, uint64_t n, const float* x, const float* r, const float* s) {
+    if (n == 0 || n >= 0xfffff000ull) { c->err = "particle count out of range for one GPU"; return ONB_ERR_ARG; }
+    ONB_CUDA(cudaSetDevice(c->device));
+    DParts& p = c->parts[which];
+    if (p.n != n) { onb_free_parts(p); int rc = onb_alloc_parts(c, p, (uint32_t)n, which == 0); if (rc) return rc; }
+    if (p.gidx) { cudaFree(p.gidx); p.gidx = nullptr; }
+    const size_t bytes = (size_t)n * sizeof(float);
+    for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(p.x[d], x + (size_t)d * n, bytes, cudaMemcpyHostToDevice, c->stream));
+    ONB_CUDA(cudaMemcpyAsync(p.r, r, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (which == 0) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(p.s[d], s + (size_t)d * n, bytes, cudaMemcpyHostToDevice, c->stream));
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    p.packed_valid = false;
+    c->trees[which].built = false;
+    return ONB_OK;
+}
+int onb_set_sources(onb_context* c, uint64_t n, const float* x, const float* r, const float* s) { return set_parts(c, 0, n, x, r, s); }
+int onb_set_targets(onb_context* c, uint64_t n, const float* x, const float* r) { return set_parts(c, 1, n, x, r, nullptr); }
+
+// Parts::random_in_cube(std::mt19937) Parts.hpp:99-109 and wave_strengths :169-176, on the host like the reference
+int onb_driver_inputs(int physics, uint64_t n, int strength_mode, float* x, float* r, float* s) {
+    if (physics < 0 || physics > 4 || n == 0) return ONB_ERR_ARG;
+    static const int PDs[5] = {3, 3, 3, 2, 2}, SDs[5] = {1, 3, 3, 1, 1};
+    const int PD = PDs[physics], SD = SDs[physics];
+    std::mt19937 eng(12345);
+    std::uniform_real_distribution<float> dist(-1.0, 1.0);
+    for (int d = 0; d < PD; ++d) for (uint64_t i = 0; i < n; ++i) x[(size_t)d * n + i] = dist(eng);
+    const float factor = (float)(1.0 / (float)n);
+    if (s) for (int d = 0; d < SD; ++d) for (uint64_t i = 0; i < n; ++i) s[(size_t)d * n + i] = dist(eng) * factor;
+    const float rad = (float)std::pow((float)n, -1.0 / (float)PD);
+    for (uint64_t i = 0; i < n; ++i) r[i] = rad;
+    if (s && strength_mode == 1)
+        for (uint64_t i = 0; i < n; ++i) for (int d = 0; d < SD; ++d)
+            s[(size_t)d * n + i] = (float)((double)factor * std::cos((d + 0.7) * 10.0 * (double)x[(size_t)d * n + i]));
+    return ONB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phases
+// ---------------------------------------------------------------------------------------------
+int onb_make_tree(onb_context* c, int which) {
+    if (which < 0 || which > 1 || c->parts[which].n == 0) { c->err = "make_tree: set the particles first"; return ONB_ERR_ARG; }
+    ONB_CUDA(cudaSetDevice(c->device));
+    int rc = onb_alloc_tree(c, c->trees[which], c->parts[which].n, c->block);
+    if (rc) return rc;
+    PhaseTimer tm(c, "tree");
+    rc = onb_tree_build(c, c->parts[which], c->trees[which]);
+    tm.stop();
+    return rc;
+}
+int onb_refine(onb_context* c, int which) {
+    if (which < 0 || which > 1) return ONB_ERR_ARG;
+    ONB_CUDA(cudaSetDevice(c->device));
+    PhaseTimer tm(c, "refine");
+    int rc = onb_tree_refine(c, c->parts[which], c->trees[which]);
+    tm.stop();
+    return rc;
+}
+int onb_upward(onb_context* c, int which) {
+    if (which < 0 || which > 1) return ONB_ERR_ARG;
+    ONB_CUDA(cudaSetDevice(c->device));
+    PhaseTimer tm(c, "upward");
+    int rc = onb_bary_upward(c, c->parts[which], c->parts[which + 2], c->trees[which]);
+    if (rc == ONB_OK && which == 0) rc = onb_pack_sources(c, c->parts[2]);
+    if (rc == ONB_OK && which == 0 && !c->parts[0].packed_valid) rc = onb_pack_sources(c, c->parts[0]);
+    tm.stop();
+    return rc;
+}
+int onb_zero_vels(onb_context* c) {
+    DParts& t = c->parts[1];
+    for (int d = 0; d < c->OD; ++d) if (t.u[d]) ONB_CUDA(cudaMemsetAsync(t.u[d], 0, (size_t)t.cap * sizeof(float), c->stream));
+    return ONB_OK;
+}
+int onb_naive(onb_context* c, uint64_t tskip, float* flops) {
+    ONB_CUDA(cudaSetDevice(c->device));
+    if (c->parts[0].n == 0 || c->parts[1].n == 0) { c->err = "naive: set sources and targets first"; return ONB_ERR_ARG; }
+    if (tskip < 1) tskip = 1;
+    PhaseTimer tm(c, "eval");
+    int rc = onb_p2p_direct(c, tskip);
+    tm.stop();
+    c->phase_ms["p2p"] = c->phase_ms["eval"];
+    if (flops) *flops = (float)(c->parts[1].n / tskip) * (float)c->parts[0].n * (float)c->flops_per_pair;   // barneshut.hpp:52
+    return rc;
+}
+static int need_trees(onb_context* c, bool target_tree, bool eq_targets) {
+    if (!c->trees[0].built || c->parts[2].n == 0) { c->err = "build the source tree and run the upward pass first"; return ONB_ERR_ARG; }
+    if (target_tree && !c->trees[1].built) { c->err = "build the target tree first"; return ONB_ERR_ARG; }
+    if (eq_targets && c->parts[3].n == 0) { c->err = "run the target upward pass first"; return ONB_ERR_ARG; }
+    return ONB_OK;
+}
+int onb_treecode3(onb_context* c, float theta, float* flops) {
+    ONB_CUDA(cudaSetDevice(c->device));
+    int rc = need_trees(c, true, false); if (rc) return rc;
+    PhaseTimer te(c, "eval");
+    WorkList wl;
+    { PhaseTimer tl(c, "lists"); rc = onb_lists_boxwise(c, theta, wl); tl.stop(); }
+    if (rc == ONB_OK) { PhaseTimer tp(c, "p2p"); rc = onb_p2p_lists(c, wl, 1, 1, true); tp.stop(); }
+    onb_free_worklist(wl);
+    te.stop();
+    if (flops) *flops = (float)c->flops_per_pair * (float)c->block *
+                        ((float)c->stats[0] * (float)c->block + (float)c->stats[1] * (float)c->num_eqps);        // :335-336
+    return rc;
+}
+int onb_fastsumm(onb_context* c, float theta) {
+    ONB_CUDA(cudaSetDevice(c->device));
+    if (!c->has_fastsumm) { c->err = "this physics has no dual-tree method in the reference (onvortgrad3d.cpp:264)"; return ONB_ERR_UNSUPPORTED; }
+    int rc = need_trees(c, true, true); if (rc) return rc;
+    PhaseTimer te(c, "eval");
+    rc = onb_run_fastsumm(c, theta);
+    te.stop();
+    return rc;
+}
+int onb_treecode2(onb_context* c, float theta, float* flops) {
+    ONB_CUDA(cudaSetDevice(c->device));
+    int rc = need_trees(c, false, false); if (rc) return rc;
+    PhaseTimer te(c, "eval");
+    rc = onb_run_treecode2(c, theta, 2);
+    te.stop();
+    if (flops) *flops = (float)c->flops_per_pair * ((float)c->stats[0] * (float)c->block + (float)c->stats[1] * (float)c->num_eqps);   // :220-221
+    return rc;
+}
+int onb_treecode1(onb_context* c, float theta, float* flops) {
+    ONB_CUDA(cudaSetDevice(c->device));
+    if (!c->trees[0].built) { c->err = "build the source tree first"; return ONB_ERR_ARG; }
+    PhaseTimer te(c, "eval");
+    int rc = onb_run_treecode2(c, theta, 1);
+    te.stop();
+    if (flops) *flops = (float)c->flops_per_pair * ((float)c->stats[1] + (float)c->stats[0] * (float)c->block);   // :131
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// outputs
+// ---------------------------------------------------------------------------------------------
+uint64_t onb_count(const onb_context* c, int which) { return (which >= 0 && which < 4) ? c->parts[which].n : 0; }
+
+int onb_get_parts(onb_context* c, int which, float* x, float* r, float* s, float* u, uint64_t* gidx) {
+    if (which < 0 || which > 3) return ONB_ERR_ARG;
+    ONB_CUDA(cudaSetDevice(c->device));
+    DParts& p = c->parts[which];
+    const size_t n = p.n, bytes = n * sizeof(float);
+    if (n == 0) return ONB_OK;
+    if (x) for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(x + d * n, p.x[d], bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (r) ONB_CUDA(cudaMemcpyAsync(r, p.r, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (s && p.are_sources) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(s + d * n, p.s[d], bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (u && !p.are_sources) for (int d = 0; d < c->OD; ++d) ONB_CUDA(cudaMemcpyAsync(u + d * n, p.u[d], bytes, cudaMemcpyDeviceToHost, c->stream));
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    if (gidx && p.gidx) {
+        std::vector<uint32_t> tmp(n);
+        ONB_CUDA(cudaMemcpy(tmp.data(), p.gidx, n * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) gidx[i] = tmp[i];
+    }
+    return ONB_OK;
+}
+
+int onb_add_results_original_order(onb_context* c, float* u) {
+    ONB_CUDA(cudaSetDevice(c->device));
+    DParts& p = c->parts[1];
+    const size_t n = p.n;
+    if (!p.gidx) { c->err = "targets have no tree order yet"; return ONB_ERR_ARG; }
+    std::vector<uint32_t> g(n); std::vector<float> tmp(n);
+    ONB_CUDA(cudaMemcpy(g.data(), p.gidx, n * 4, cudaMemcpyDeviceToHost));
+    for (int d = 0; d < c->OD; ++d) {
+        ONB_CUDA(cudaMemcpy(tmp.data(), p.u[d], n * 4, cudaMemcpyDeviceToHost));
+        float* ud = u + (size_t)d * n;
+        for (size_t i = 0; i < n; ++i) ud[g[i]] += tmp[i];                                // interface3dvortgrads.cpp:384-395
+    }
+    return ONB_OK;
+}
+
+int onb_tree_shape(const onb_context* c, int which, int* levels, int* numnodes) {
+    if (which < 0 || which > 1) return ONB_ERR_ARG;
+    *levels = c->trees[which].levels; *numnodes = c->trees[which].numnodes; return ONB_OK;
+}
+
+int onb_get_tree(onb_context* c, int which, float* x, float* nc, float* ns, float* nr, float* pr, float* s,
+                 uint64_t* ioffset, uint64_t* num, uint64_t* epoffset, uint64_t* epnum) {
+    if (which < 0 || which > 1) return ONB_ERR_ARG;
+    ONB_CUDA(cudaSetDevice(c->device));
+    DTree& t = c->trees[which];
+    const size_t n = t.numnodes, fb = n * sizeof(float);
+    if (n == 0) return ONB_OK;
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int d = 0; d < c->PD; ++d) {
+        if (x)  ONB_CUDA(cudaMemcpy(x + d * n,  t.x[d],  fb, cudaMemcpyDeviceToHost));
+        if (nc) ONB_CUDA(cudaMemcpy(nc + d * n, t.nc[d], fb, cudaMemcpyDeviceToHost));
+        if (ns) ONB_CUDA(cudaMemcpy(ns + d * n, t.ns[d], fb, cudaMemcpyDeviceToHost));
+    }
+    if (nr) ONB_CUDA(cudaMemcpy(nr, t.nr, fb, cudaMemcpyDeviceToHost));
+    if (pr) ONB_CUDA(cudaMemcpy(pr, t.pr, fb, cudaMemcpyDeviceToHost));
+    if (s) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpy(s + d * n, t.s[d], fb, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> io(n), nm(n);
+    ONB_CUDA(cudaMemcpy(io.data(), t.ioffset, n * 4, cudaMemcpyDeviceToHost));
+    ONB_CUDA(cudaMemcpy(nm.data(), t.num, n * 4, cudaMemcpyDeviceToHost));
+    const bool have_eq = c->parts[which + 2].n > 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (ioffset) ioffset[i] = io[i];
+        if (num) num[i] = nm[i];
+        const bool nonleaf = have_eq && nm[i] > (uint32_t)c->block;
+        if (epoffset) epoffset[i] = nonleaf ? (uint64_t)i * c->ebs : 0;                   // BarycentricLagrange.hpp:289
+        if (epnum) epnum[i] = nonleaf ? c->num_eqps : 0;
+    }
+    return ONB_OK;
+}
+
+int onb_get_stats(const onb_context* c, uint64_t out[9]) { for (int i = 0; i < 9; ++i) out[i] = c->stats[i]; return ONB_OK; }
+
+double onb_phase_ms(const onb_context* c, const char* name) {
+    auto it = c->phase_ms.find(name);
+    return it == c->phase_ms.end() ? -1.0 : it->second;
+}
+uint64_t onb_last_pairs(const onb_context* c) { return c->last_pairs; }
+uint64_t onb_launch_count(const onb_context* c) { return c->launches; }
+
+void* onb_device_ptr(onb_context* c, int which, int field) {
+    if (which < 0 || which > 3) return nullptr;
+    DParts& p = c->parts[which];
+    if (field >= 0 && field < 3) return p.x[field];
+    if (field == 3) return p.r;
+    if (field >= 4 && field < 7) return p.s[field - 4];
+    return nullptr;
+}
+
+int onb_load_tree(onb_context* c, int which, int levels, const float* x, const float* nc, const float* ns,
+                  const float* nr, const float* pr, const float* s, const uint64_t* ioffset, const uint64_t* num) {
+    if (which < 0 || which > 1 || c->parts[which].n == 0) { c->err = "load_tree: set the particles first"; return ONB_ERR_ARG; }
+    ONB_CUDA(cudaSetDevice(c->device));
+    DTree& t = c->trees[which];
+    int rc = onb_alloc_tree(c, t, c->parts[which].n, c->block);
+    if (rc) return rc;
+    if (t.levels != levels) { c->err = "load_tree: level count does not match Tree.hpp sizing"; return ONB_ERR_ARG; }
+    const size_t n = t.numnodes, fb = n * sizeof(float);
+    for (int d = 0; d < c->PD; ++d) {
+        ONB_CUDA(cudaMemcpy(t.x[d], x + d * n, fb, cudaMemcpyHostToDevice));
+        ONB_CUDA(cudaMemcpy(t.nc[d], nc + d * n, fb, cudaMemcpyHostToDevice));
+        ONB_CUDA(cudaMemcpy(t.ns[d], ns + d * n, fb, cudaMemcpyHostToDevice));
+    }
+    ONB_CUDA(cudaMemcpy(t.nr, nr, fb, cudaMemcpyHostToDevice));
+    ONB_CUDA(cudaMemcpy(t.pr, pr, fb, cudaMemcpyHostToDevice));
+    if (s) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpy(t.s[d], s + d * n, fb, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> io(n), nm(n);
+    for (size_t i = 0; i < n; ++i) { io[i] = (uint32_t)ioffset[i]; nm[i] = (uint32_t)num[i]; }
+    ONB_CUDA(cudaMemcpy(t.ioffset, io.data(), n * 4, cudaMemcpyHostToDevice));
+    ONB_CUDA(cudaMemcpy(t.num, nm.data(), n * 4, cudaMemcpyHostToDevice));
+    if (which == 1) {   // targets loaded in tree order: original index = position
+        DParts& p = c->parts[1];
+        if (!p.gidx) ONB_CUDA(cudaMalloc(&p.gidx, (size_t)p.n * 4));
+        std::vector<uint32_t> id(p.n); for (uint32_t i = 0; i < p.n; ++i) id[i] = i;
+        ONB_CUDA(cudaMemcpy(p.gidx, id.data(), (size_t)p.n * 4, cudaMemcpyHostToDevice));
+    }
+    t.built = true;
+    return ONB_OK;
+}
+
+}  // extern "C"

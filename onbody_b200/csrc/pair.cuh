@@ -1,0 +1,129 @@
+/*
+ * pair.cuh - the physics policies and the one-source-on-one-target pair functions shared by p2p.cu (list driven
+ * block kernels) and pointwise.cu (fused traversal). See p2p.cu for the reference citations.
+ */
+#pragma once
+#include "onb_internal.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// physics policies
+// ---------------------------------------------------------------------------------------------
+template <int PHYS> struct Phys;
+template <> struct Phys<ONB_GRAV3D>     { static constexpr int PD = 3, SD = 1, OD = 3,  NF4 = 1; static constexpr bool F1 = true,  TR = false; };
+template <> struct Phys<ONB_VORT3D>     { static constexpr int PD = 3, SD = 3, OD = 3,  NF4 = 2; static constexpr bool F1 = false, TR = false; };
+template <> struct Phys<ONB_VORTGRAD3D> { static constexpr int PD = 3, SD = 3, OD = 12, NF4 = 2; static constexpr bool F1 = false, TR = false; };
+template <> struct Phys<ONB_VORT2D>     { static constexpr int PD = 2, SD = 1, OD = 2,  NF4 = 1; static constexpr bool F1 = false, TR = false; };
+template <> struct Phys<ONB_VORT2DTR>   { static constexpr int PD = 2, SD = 1, OD = 2,  NF4 = 1; static constexpr bool F1 = false, TR = true;  };
+
+struct Tgt { float x, y, z, r2; };
+
+// single-instruction SFU approximations (MUFU.RSQ / MUFU.RCP, ~1 ulp-level relative error 2^-22); the *_rn intrinsics
+// are the correctly-rounded (multi-instruction, branchy) versions and are used only by the STRICT instantiations
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x)   { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+   // r2 = target radius squared (vort2dtr only)
+
+// one source on one target. p0/p1/p2 are the packed planes' values for this source.
+template <int PHYS, bool STRICT>
+__device__ __forceinline__ void pair(const float4 p0, const float4 p1, const float p2, const Tgt& t, float* __restrict__ u) {
+    if (PHYS == ONB_GRAV3D) {
+        // p0 = (x,y,z,m)  p2 = r^2
+        if (!STRICT) {
+            const float dx = p0.x - t.x, dy = p0.y - t.y, dz = p0.z - t.z;
+            const float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, p2)));
+            const float ri = rsqrt_approx(r2);
+            const float r3 = (p0.w * ri) * (ri * ri);
+            u[0] = fmaf(r3, dx, u[0]); u[1] = fmaf(r3, dy, u[1]); u[2] = fmaf(r3, dz, u[2]);
+        } else {
+            const float dx = __fsub_rn(p0.x, t.x), dy = __fsub_rn(p0.y, t.y), dz = __fsub_rn(p0.z, t.z);
+            float r3 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)), p2);
+            r3 = __fdiv_rn(p0.w, __fmul_rn(r3, __fsqrt_rn(r3)));
+            u[0] = __fadd_rn(u[0], __fmul_rn(r3, dx)); u[1] = __fadd_rn(u[1], __fmul_rn(r3, dy)); u[2] = __fadd_rn(u[2], __fmul_rn(r3, dz));
+        }
+    } else if (PHYS == ONB_VORT3D) {
+        // p0 = (x,y,z,r^2)  p1 = (wx,wy,wz,-)
+        if (!STRICT) {
+            const float dx = p0.x - t.x, dy = p0.y - t.y, dz = p0.z - t.z;
+            const float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, p0.w)));
+            const float ri = rsqrt_approx(r2);
+            const float r3 = ri * (ri * ri);
+            const float dxxw = fmaf(dz, p1.y, -(dy * p1.z));
+            const float dyxw = fmaf(dx, p1.z, -(dz * p1.x));
+            const float dzxw = fmaf(dy, p1.x, -(dx * p1.y));
+            u[0] = fmaf(r3, dxxw, u[0]); u[1] = fmaf(r3, dyxw, u[1]); u[2] = fmaf(r3, dzxw, u[2]);
+        } else {
+            const float dx = __fsub_rn(p0.x, t.x), dy = __fsub_rn(p0.y, t.y), dz = __fsub_rn(p0.z, t.z);
+            const float dsq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            const float r2 = __fadd_rn(dsq, p0.w);
+            const float r3 = __fdiv_rn(1.0f, __fmul_rn(r2, __fsqrt_rn(r2)));
+            const float dxxw = __fsub_rn(__fmul_rn(dz, p1.y), __fmul_rn(dy, p1.z));
+            const float dyxw = __fsub_rn(__fmul_rn(dx, p1.z), __fmul_rn(dz, p1.x));
+            const float dzxw = __fsub_rn(__fmul_rn(dy, p1.x), __fmul_rn(dx, p1.y));
+            u[0] = __fadd_rn(u[0], __fmul_rn(r3, dxxw)); u[1] = __fadd_rn(u[1], __fmul_rn(r3, dyxw)); u[2] = __fadd_rn(u[2], __fmul_rn(r3, dzxw));
+        }
+    } else if (PHYS == ONB_VORTGRAD3D) {
+        // note the sign: d = target - source (onvortgrad3d.cpp:53-55)
+        if (!STRICT) {
+            const float dx = t.x - p0.x, dy = t.y - p0.y, dz = t.z - p0.z;
+            const float r2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, p0.w)));
+            const float ri = rsqrt_approx(r2);
+            const float ri2 = ri * ri;
+            const float r3 = ri * ri2;
+            const float bbb = (-3.0f * r3) * ri2;
+            float dxxw = fmaf(dz, p1.y, -(dy * p1.z));
+            float dyxw = fmaf(dx, p1.z, -(dz * p1.x));
+            float dzxw = fmaf(dy, p1.x, -(dx * p1.y));
+            u[0] = fmaf(r3, dxxw, u[0]); u[1] = fmaf(r3, dyxw, u[1]); u[2] = fmaf(r3, dzxw, u[2]);
+            dxxw *= bbb; dyxw *= bbb; dzxw *= bbb;
+            u[3]  = fmaf(dx, dxxw, u[3]);
+            u[4]  = fmaf(dx, dyxw, fmaf(p1.z, r3, u[4]));
+            u[5]  = fmaf(dx, dzxw, fmaf(-p1.y, r3, u[5]));
+            u[6]  = fmaf(dy, dxxw, fmaf(-p1.z, r3, u[6]));
+            u[7]  = fmaf(dy, dyxw, u[7]);
+            u[8]  = fmaf(dy, dzxw, fmaf(p1.x, r3, u[8]));
+            u[9]  = fmaf(dz, dxxw, fmaf(p1.y, r3, u[9]));
+            u[10] = fmaf(dz, dyxw, fmaf(-p1.x, r3, u[10]));
+            u[11] = fmaf(dz, dzxw, u[11]);
+        } else {
+            const float dx = __fsub_rn(t.x, p0.x), dy = __fsub_rn(t.y, p0.y), dz = __fsub_rn(t.z, p0.z);
+            const float dsq = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            const float r2 = __fadd_rn(dsq, p0.w);
+            const float r3 = __fdiv_rn(1.0f, __fmul_rn(r2, __fsqrt_rn(r2)));
+            const float bbb = __fmul_rn(__fmul_rn(-3.0f, r3), __fdiv_rn(1.0f, r2));
+            float dxxw = __fsub_rn(__fmul_rn(dz, p1.y), __fmul_rn(dy, p1.z));
+            float dyxw = __fsub_rn(__fmul_rn(dx, p1.z), __fmul_rn(dz, p1.x));
+            float dzxw = __fsub_rn(__fmul_rn(dy, p1.x), __fmul_rn(dx, p1.y));
+            u[0] = __fadd_rn(u[0], __fmul_rn(r3, dxxw)); u[1] = __fadd_rn(u[1], __fmul_rn(r3, dyxw)); u[2] = __fadd_rn(u[2], __fmul_rn(r3, dzxw));
+            dxxw = __fmul_rn(dxxw, bbb); dyxw = __fmul_rn(dyxw, bbb); dzxw = __fmul_rn(dzxw, bbb);
+            u[3]  = __fadd_rn(u[3],  __fmul_rn(dx, dxxw));
+            u[4]  = __fadd_rn(u[4],  __fadd_rn(__fmul_rn(dx, dyxw), __fmul_rn(p1.z, r3)));
+            u[5]  = __fadd_rn(u[5],  __fsub_rn(__fmul_rn(dx, dzxw), __fmul_rn(p1.y, r3)));
+            u[6]  = __fadd_rn(u[6],  __fsub_rn(__fmul_rn(dy, dxxw), __fmul_rn(p1.z, r3)));
+            u[7]  = __fadd_rn(u[7],  __fmul_rn(dy, dyxw));
+            u[8]  = __fadd_rn(u[8],  __fadd_rn(__fmul_rn(dy, dzxw), __fmul_rn(p1.x, r3)));
+            u[9]  = __fadd_rn(u[9],  __fadd_rn(__fmul_rn(dz, dxxw), __fmul_rn(p1.y, r3)));
+            u[10] = __fadd_rn(u[10], __fsub_rn(__fmul_rn(dz, dyxw), __fmul_rn(p1.x, r3)));
+            u[11] = __fadd_rn(u[11], __fmul_rn(dz, dzxw));
+        }
+    } else {
+        // 2D: p0 = (x, y, r^2, strength); d = target - source; optional target radius
+        if (!STRICT) {
+            const float dx = t.x - p0.x, dy = t.y - p0.y;
+            float r2c = fmaf(dx, dx, fmaf(dy, dy, p0.z));
+            if (Phys<PHYS>::TR) r2c += t.r2;
+            const float r2 = p0.w * rcp_approx(r2c);
+            u[0] = fmaf(-r2, dy, u[0]); u[1] = fmaf(r2, dx, u[1]);
+        } else {
+            const float dx = __fsub_rn(t.x, p0.x), dy = __fsub_rn(t.y, p0.y);
+            float r2c = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), p0.z);
+            if (Phys<PHYS>::TR) r2c = __fadd_rn(r2c, t.r2);
+            const float r2 = __fmul_rn(p0.w, __fdiv_rn(1.0f, r2c));
+            u[0] = __fsub_rn(u[0], __fmul_rn(r2, dy)); u[1] = __fadd_rn(u[1], __fmul_rn(r2, dx));
+        }
+    }
+}
+
+
+}  // namespace

@@ -1,0 +1,326 @@
+/*
+ * traverse.cu - GPU-side interaction-list generation under the reference's reciprocal multipole-acceptance
+ * criteria, and the drivers that pair the lists with the leaf-block kernels of p2p.cu.
+ *
+ * Replaces (reference): treecode3_block + nbody_treecode3 barneshut.hpp:228-337 (boxwise),
+ *                       nbody_fastsumm ongrav3d.cpp:206-452 == onvort3d.cpp:219-465 == onvort2d.cpp:193-439 (dual tree).
+ * (pointwise treecode2 / treecode1 live in pointwise.cu)
+ *
+ * The reference's lists are implicit in its recursion; here they are explicit CSR arrays so that the pair kernel
+ * gets one CTA per target block with a contiguous, ORDER-PRESERVING list (accumulation order == the reference's
+ * recursion order, which is what lets ARITH_STRICT reproduce its results bit for bit).
+ *
+ * Every acceptance test is evaluated in the reference's exact IEEE sequence, including the float->double->float
+ * round trips that std::pow(float,int) introduces (barneshut.hpp:255, ongrav3d.cpp:338): an accept/reject that
+ * flips changes the printed GFlop checksum and moves results at the 1e-4 level.
+ *
+ * Boxwise: one thread per target leaf walks the source tree depth first with a small stack (count pass, scan,
+ * fill pass). Dual tree: level-synchronous over the target tree; one warp per target node
+ * consumes its inherited list 32 entries at a time, ballot-compacting into (a) its interaction list, (b) the list its
+ * children inherit, (c) a FIFO of opened source nodes that is processed in the following rounds - exactly the
+ * "push_back onto the list being iterated" order of the reference.
+ */
+#include "onb_internal.h"
+
+namespace {
+
+__device__ __forceinline__ float dist_sq_step(float dist, float v) {
+    // dist += std::pow(v, 2) with float dist: promoted to double, rounded back to float each step
+    return __double2float_rn(__dadd_rn((double)dist, __dmul_rn((double)v, (double)v)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// boxwise (treecode3)
+// ---------------------------------------------------------------------------------------------
+struct BoxArgs {
+    TreeView st, tt;
+    const uint32_t* leaf_nodes;     // target leaf node ids of this shard, tree order
+    uint32_t nleaves;
+    uint32_t* counts;               // per leaf (count pass)
+    const uint32_t* start;          // per leaf (fill pass)
+    uint32_t* entries;
+    unsigned long long* stats;      // [0] sltp [1] sbtp [9] pairs
+    uint32_t block, num_eqps; int PD; float theta;
+};
+
+template <bool FILL>
+__global__ void k_boxwise(const BoxArgs a) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.nleaves) return;
+    const uint32_t T = a.leaf_nodes[w];
+    float tc[3]; for (int d = 0; d < a.PD; ++d) tc[d] = a.tt.nc[d][T];
+    const float tnr = a.tt.nr[T];
+    const uint32_t tcnt = a.tt.num[T];
+    uint32_t stack[64]; int sp = 0;
+    stack[sp++] = 1;
+    uint32_t n = 0, nl = 0, nb = 0; unsigned long long pairs = 0;
+    uint32_t* out = FILL ? a.entries + a.start[w] : nullptr;
+    while (sp > 0) {
+        const uint32_t S = stack[--sp];
+        const uint32_t sn = a.st.num[S];
+        if (sn <= a.block) {                                                              // barneshut.hpp:242 leaf first, no MAC
+            if (FILL) { out[n] = S; pairs += (unsigned long long)sn * tcnt; }
+            ++n; ++nl; continue;
+        }
+        float dist = 0.0f;
+        for (int d = 0; d < a.PD; ++d) dist = dist_sq_step(dist, __fsub_rn(a.st.nc[d][S], tc[d]));   // :255
+        dist = __fsqrt_rn(dist);
+        const float snr = a.st.nr[S];
+        const float testrad = __fadd_rn(fmaxf(snr, tnr), __fmul_rn(0.25f, fminf(snr, tnr)));          // :280
+        if (__fdiv_rn(dist, __fmul_rn(2.0f, testrad)) > a.theta) {                                     // :283
+            if (FILL) { out[n] = S | 0x80000000u; pairs += (unsigned long long)a.num_eqps * tcnt; }
+            ++n; ++nb;
+        } else {
+            if (sp + 2 > 64) { continue; }      // cannot happen: depth <= levels <= 32
+            stack[sp++] = 2 * S + 1;            // :291-292 left child is visited first
+            stack[sp++] = 2 * S;
+        }
+    }
+    if (!FILL) a.counts[w] = n;
+    else {
+        atomicAdd(&a.stats[0], (unsigned long long)nl); atomicAdd(&a.stats[1], (unsigned long long)nb);
+        atomicAdd(&a.stats[9], pairs);
+    }
+}
+
+// leaf table: leaf j of a tree = the node whose particles start at j*block
+__global__ void k_leaf_table(TreeView t, uint32_t block, uint32_t* leaf_nodes) {
+    const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node == 0 || node >= (uint32_t)t.numnodes) return;
+    const uint32_t n = t.num[node];
+    if (n > 0 && n <= block) leaf_nodes[t.ioffset[node] / block] = node;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dual tree (fastsumm)
+// ---------------------------------------------------------------------------------------------
+struct DttArgs {
+    TreeView st, tt;
+    int level; uint32_t nnodes;             // target nodes of this level: T = 2^level + local
+    // inherited lists = the parent's deferred list
+    const uint32_t* pc_start;               // per node of level-1 (+1); null at the root level
+    const uint32_t* pc_entries;
+    // outputs
+    uint32_t* icount; uint32_t* ccount;     // count pass, per node of this level
+    const uint32_t* istart; const uint32_t* cstart;   // fill pass
+    uint32_t* ientries; uint32_t* centries;
+    uint32_t* queue; uint32_t qcap;         // per-warp FIFO scratch: 2 x qcap entries per warp slot
+    unsigned long long* stats;              // [2] sltl [3] sbtl [4] sltb [5] sbtb [6] tlc [7] lpc [8] bpc [9] pairs
+    int* flag;
+    uint32_t block, num_eqps, shard_lo, shard_hi; int PD; float theta;
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_dtt(const DttArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t wslot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* q0 = a.queue + (size_t)wslot * 2 * a.qcap;
+    uint32_t* q1 = q0 + a.qcap;
+    unsigned long long st_sltl = 0, st_sbtl = 0, st_sltb = 0, st_sbtb = 0, st_pairs = 0, st_tlc = 0, st_lpc = 0, st_bpc = 0;
+
+    for (uint32_t local = wslot; local < a.nnodes; local += nwarps) {
+        const uint32_t T = (1u << a.level) + local;
+        const uint32_t tn = a.tt.num[T];
+        const uint32_t tio = a.tt.ioffset[T];
+        const bool needed = tn >= 1 && tio < a.shard_hi && tio + tn > a.shard_lo;         // ongrav3d.cpp:221 (+ sharding)
+        if (!needed) { if (!FILL && lane == 0) { a.icount[local] = 0; a.ccount[local] = 0; } continue; }
+        const bool tleaf = tn <= a.block;                                                 // :224
+        const uint32_t tcnt = tleaf ? tn : a.num_eqps;
+        float tx[3]; for (int d = 0; d < a.PD; ++d) tx[d] = a.tt.x[d][T];
+        const float tnr = a.tt.nr[T];
+        if (FILL && lane == 0) { if (tleaf) { ++st_tlc; if (T > 1) ++st_lpc; } else if (T > 1) ++st_bpc; }
+
+        const uint32_t* cur; uint32_t len;
+        uint32_t root_list = 1;
+        if (a.level == 0) { cur = nullptr; len = 1; }
+        else { const uint32_t pl = (T >> 1) - (1u << (a.level - 1)); cur = a.pc_entries + a.pc_start[pl]; len = a.pc_start[pl + 1] - a.pc_start[pl]; }
+        uint32_t nI = 0, nC = 0;
+        uint32_t* oI = FILL ? a.ientries + a.istart[local] : nullptr;
+        uint32_t* oC = FILL ? a.centries + a.cstart[local] : nullptr;
+        uint32_t* nxt = q0;
+        bool overflow = false;
+        while (len > 0 && !overflow) {
+            uint32_t nextlen = 0;
+            for (uint32_t base = 0; base < len; base += 32) {                             // :315 list order
+                const uint32_t i = base + lane;
+                const bool valid = i < len;
+                const uint32_t S = valid ? (a.level == 0 && cur == nullptr ? root_list : cur[i]) : 1u;
+                int outcome = 0;   // 0 skip, 1 emit real sources, 2 emit equivalent sources, 3 defer to children, 4 open source node
+                uint32_t sn = 0;
+                if (valid) {
+                    sn = a.st.num[S];
+                    if (sn >= 1) {                                                        // :319
+                        const bool sleaf = sn <= a.block;
+                        if (sleaf && tleaf) outcome = 1;                                  // :326 direct, no MAC
+                        else {
+                            float dist = 0.0f;
+                            for (int d = 0; d < a.PD; ++d) dist = dist_sq_step(dist, __fsub_rn(a.st.x[d][S], tx[d]));   // :338
+                            dist = __fsqrt_rn(dist);
+                            const float snr = a.st.nr[S];
+                            const float diag = __fadd_rn(snr, tnr);                       // :340
+                            if (__fdiv_rn(dist, diag) > a.theta) outcome = sleaf ? 1 : 2; // :344-365
+                            else if (tnr > snr) outcome = tleaf ? 4 : 3;                  // :367-382
+                            else outcome = sleaf ? 3 : 4;                                 // :384-399
+                        }
+                    }
+                }
+                const uint32_t bE = __ballot_sync(0xffffffffu, outcome == 1 || outcome == 2);
+                const uint32_t bC = __ballot_sync(0xffffffffu, outcome == 3);
+                const uint32_t bX = __ballot_sync(0xffffffffu, outcome == 4);
+                if (nextlen + 2u * __popc(bX) > a.qcap) { overflow = true; break; }
+                if (outcome == 4) { const uint32_t pos = nextlen + 2u * __popc(bX & lt_mask); nxt[pos] = 2 * S; nxt[pos + 1] = 2 * S + 1; }   // :374,:395
+                if (FILL) {
+                    if (outcome == 1 || outcome == 2) {
+                        oI[nI + __popc(bE & lt_mask)] = outcome == 2 ? (S | 0x80000000u) : S;
+                        st_pairs += (unsigned long long)(outcome == 2 ? a.num_eqps : sn) * tcnt;
+                        if (outcome == 1) { if (tleaf) ++st_sltl; else ++st_sltb; } else { if (tleaf) ++st_sbtl; else ++st_sbtb; }
+                    }
+                    if (outcome == 3) oC[nC + __popc(bC & lt_mask)] = S;
+                }
+                nI += __popc(bE); nC += __popc(bC); nextlen += 2u * __popc(bX);
+            }
+            __syncwarp();
+            cur = nxt; len = nextlen; nxt = (nxt == q0) ? q1 : q0;
+        }
+        if (overflow && lane == 0) atomicExch(a.flag, ONB_ERR_CAPACITY);
+        if (!FILL && lane == 0) { a.icount[local] = nI; a.ccount[local] = tleaf ? 0u : nC; }
+    }
+    if (FILL) {
+        // warp-reduce the statistics, one atomic per warp and counter
+        unsigned long long v[8] = { st_sltl, st_sbtl, st_sltb, st_sbtb, st_tlc, st_lpc, st_bpc, st_pairs };
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            unsigned long long x = v[k];
+            for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0 && x) atomicAdd(&a.stats[2 + k], x);
+        }
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------------------------
+void onb_shard_range(const onb_context* c, uint32_t* lo, uint32_t* hi) {
+    const DParts& t = c->parts[1];
+    const uint64_t nleaf = (t.n + c->block - 1) / c->block;
+    const uint64_t l0 = nleaf * (uint64_t)c->shard_rank / (uint64_t)c->shard_n;
+    const uint64_t l1 = nleaf * (uint64_t)(c->shard_rank + 1) / (uint64_t)c->shard_n;
+    *lo = (uint32_t)std::min<uint64_t>(l0 * c->block, t.n);
+    *hi = (uint32_t)std::min<uint64_t>(l1 * c->block, t.n);
+}
+
+static int fetch_stats(onb_context* c, unsigned long long* d_stats) {
+    unsigned long long h[10];
+    ONB_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 9; ++i) c->stats[i] = h[i];
+    c->last_pairs = h[9];
+    return ONB_OK;
+}
+
+int onb_lists_boxwise(onb_context* c, float theta, WorkList& wl) {
+    DTree& st = c->trees[0]; DTree& tt = c->trees[1];
+    const uint32_t nleaf_all = (c->parts[1].n + c->block - 1) / c->block;
+    uint32_t* leaf_all = nullptr;
+    ONB_CUDA(cudaMalloc(&leaf_all, (size_t)nleaf_all * 4));
+    k_leaf_table<<<(tt.numnodes + 255) / 256, 256, 0, c->stream>>>(view_of(tt), c->block, leaf_all); ONB_LAUNCH(c);
+    uint32_t lo, hi; onb_shard_range(c, &lo, &hi);
+    const uint32_t l0 = lo / c->block, l1 = (hi + c->block - 1) / c->block;
+    const uint32_t nl = l1 - l0;
+    unsigned long long* d_stats = nullptr;
+    ONB_CUDA(cudaMalloc(&d_stats, 10 * sizeof(unsigned long long)));
+    ONB_CUDA(cudaMemsetAsync(d_stats, 0, 10 * sizeof(unsigned long long), c->stream));
+    wl = WorkList(); wl.nitems = nl;
+    if (nl == 0) { cudaFree(leaf_all); cudaFree(d_stats); memset(c->stats, 0, sizeof(c->stats)); c->last_pairs = 0; return ONB_OK; }
+    ONB_CUDA(cudaMalloc(&wl.tgt_node, (size_t)nl * 4));
+    ONB_CUDA(cudaMemcpyAsync(wl.tgt_node, leaf_all + l0, (size_t)nl * 4, cudaMemcpyDeviceToDevice, c->stream));
+    ONB_CUDA(cudaMalloc(&wl.start, (size_t)(nl + 1) * 4));
+    BoxArgs a; a.st = view_of(st); a.tt = view_of(tt); a.leaf_nodes = wl.tgt_node; a.nleaves = nl;
+    a.counts = wl.start; a.start = wl.start; a.entries = nullptr; a.stats = d_stats;
+    a.block = c->block; a.num_eqps = c->num_eqps; a.PD = c->PD; a.theta = theta;
+    const int TB = 128;
+    k_boxwise<false><<<(nl + TB - 1) / TB, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
+    ONB_CUDA(cudaGetLastError());
+    ONB_CUDA(cudaMemsetAsync(wl.start + nl, 0, 4, c->stream));
+    uint64_t total = 0;
+    int rc = onb_exclusive_scan_u32(c, wl.start, wl.start, nl + 1, &total);
+    if (rc) return rc;
+    if (total >= 0xffffffffull) { c->err = "boxwise: interaction list exceeds 2^32 entries on one GPU"; return ONB_ERR_CAPACITY; }
+    wl.nentries = total;
+    ONB_CUDA(cudaMalloc(&wl.entries, std::max<size_t>(4, (size_t)total * 4)));
+    a.entries = wl.entries;
+    k_boxwise<true><<<(nl + TB - 1) / TB, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
+    ONB_CUDA(cudaGetLastError());
+    rc = fetch_stats(c, d_stats);
+    cudaFree(d_stats); cudaFree(leaf_all);
+    return rc;
+}
+
+int onb_run_fastsumm(onb_context* c, float theta) {
+    DTree& st = c->trees[0]; DTree& tt = c->trees[1];
+    uint32_t lo, hi; onb_shard_range(c, &lo, &hi);
+    unsigned long long* d_stats = nullptr;
+    ONB_CUDA(cudaMalloc(&d_stats, 10 * sizeof(unsigned long long)));
+    ONB_CUDA(cudaMemsetAsync(d_stats, 0, 10 * sizeof(unsigned long long), c->stream));
+    const int TB = 256, WPB = TB / 32;
+    const uint32_t max_blocks = (uint32_t)c->sm_count * 8u;
+    const uint32_t qcap = 8192;
+    uint32_t* queue = nullptr;
+    ONB_CUDA(cudaMalloc(&queue, (size_t)max_blocks * WPB * 2 * qcap * 4));
+
+    uint32_t *pc_start = nullptr, *pc_entries = nullptr;     // previous level's deferred lists
+    double ms_lists = 0.0, ms_p2p = 0.0, ms_down = 0.0;
+    cudaEvent_t ev[4]; for (int i = 0; i < 4; ++i) cudaEventCreate(&ev[i]);
+    int rc = ONB_OK;
+    for (int lev = 0; lev < tt.levels && rc == ONB_OK; ++lev) {
+        const uint32_t nn = 1u << lev;
+        cudaEventRecord(ev[0], c->stream);
+        uint32_t *istart = nullptr, *cstart = nullptr, *ientries = nullptr, *centries = nullptr;
+        ONB_CUDA(cudaMalloc(&istart, (size_t)(nn + 1) * 4)); ONB_CUDA(cudaMalloc(&cstart, (size_t)(nn + 1) * 4));
+        DttArgs a; a.st = view_of(st); a.tt = view_of(tt); a.level = lev; a.nnodes = nn;
+        a.pc_start = pc_start; a.pc_entries = pc_entries;
+        a.icount = istart; a.ccount = cstart; a.istart = istart; a.cstart = cstart; a.ientries = nullptr; a.centries = nullptr;
+        a.queue = queue; a.qcap = qcap; a.stats = d_stats; a.flag = c->d_flag;
+        a.block = c->block; a.num_eqps = c->num_eqps; a.shard_lo = lo; a.shard_hi = hi; a.PD = c->PD; a.theta = theta;
+        const uint32_t blocks = std::min<uint32_t>(max_blocks, (nn + WPB - 1) / WPB);
+        k_dtt<false><<<blocks, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
+        ONB_CUDA(cudaGetLastError());
+        ONB_CUDA(cudaMemsetAsync(istart + nn, 0, 4, c->stream)); ONB_CUDA(cudaMemsetAsync(cstart + nn, 0, 4, c->stream));
+        uint64_t itotal = 0, ctotal = 0;
+        if ((rc = onb_exclusive_scan_u32(c, istart, istart, nn + 1, &itotal))) break;
+        if ((rc = onb_exclusive_scan_u32(c, cstart, cstart, nn + 1, &ctotal))) break;
+        if ((rc = onb_check_flag(c, "dual-tree traversal: per-node source FIFO overflow"))) break;
+        if (itotal >= 0xffffffffull || ctotal >= 0xffffffffull) { c->err = "fastsumm: list exceeds 2^32 entries on one GPU"; rc = ONB_ERR_CAPACITY; break; }
+        ONB_CUDA(cudaMalloc(&ientries, std::max<size_t>(4, (size_t)itotal * 4)));
+        ONB_CUDA(cudaMalloc(&centries, std::max<size_t>(4, (size_t)ctotal * 4)));
+        a.ientries = ientries; a.centries = centries;
+        k_dtt<true><<<blocks, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
+        ONB_CUDA(cudaGetLastError());
+        cudaEventRecord(ev[1], c->stream);
+        // node entry: zero + interpolate from the parent (ongrav3d.cpp:232-304)
+        if ((rc = onb_bary_downward_level(c, lev))) break;
+        cudaEventRecord(ev[2], c->stream);
+        // then this level's interactions, in list order, on top of the interpolated values (:315-402)
+        WorkList wl; wl.nitems = nn; wl.tgt_node = nullptr; wl.node_base = nn; wl.start = istart; wl.entries = ientries; wl.nentries = itotal;
+        if (itotal > 0) if ((rc = onb_p2p_lists(c, wl, 1, 3, true))) break;
+        cudaEventRecord(ev[3], c->stream);
+        ONB_CUDA(cudaStreamSynchronize(c->stream));
+        float t01 = 0, t12 = 0, t23 = 0;
+        cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
+        ms_lists += t01; ms_down += t12; ms_p2p += t23;
+        cudaFree(istart); cudaFree(ientries);
+        if (pc_start) cudaFree(pc_start); if (pc_entries) cudaFree(pc_entries);
+        pc_start = cstart; pc_entries = centries;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+    if (pc_start) cudaFree(pc_start); if (pc_entries) cudaFree(pc_entries);
+    cudaFree(queue);
+    if (rc == ONB_OK) rc = fetch_stats(c, d_stats);
+    cudaFree(d_stats);
+    c->phase_ms["lists"] = ms_lists; c->phase_ms["downward"] = ms_down; c->phase_ms["p2p"] = ms_p2p;
+    return rc;
+}

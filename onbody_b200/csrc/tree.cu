@@ -1,0 +1,514 @@
+/*
+ * tree.cu - VAM-split k-d tree build, node summaries and in-leaf refinement on the GPU.
+ *
+ * Replaces (reference src/barneshut.hpp): makeTree :814-854, splitNode :594-712, partialSortIndexes :505-587,
+ * minMaxValue :423-454, reorder :475-500, Parts::reorder_idx Parts.hpp:188-196, finishTree :717-807,
+ * refineTree/refineLeaf :860-936.
+ *
+ * The reference builds the tree by recursive partial selection on the longest axis of the node's tight bounding
+ * box. There is no Morton key and no radix sort in it, and the particle order that comes out (which the parity
+ * contract requires bit-for-bit) is the composition of its Hoare partition passes. This file therefore runs the
+ * SAME passes, level-synchronously and in closed form (proven equal to the recursive
+ * two-pointer loop by oracle/port against the compiled reference):
+ *
+ *   pass:  m = #{v < pivot in window}; B = wf + m;
+ *          a_1 < a_2 < ...  positions in [wf,B) holding v >= pivot,   b_1 > b_2 > ...  positions in [B,wl] holding v < pivot
+ *          swap (v, idx) at a_j <-> b_j for all j                      (two ordered stream compactions + one scatter)
+ *
+ * One CTA owns one tree node per level: bounding box (block min/max), pivot arithmetic in the reference's exact IEEE
+ * sequence (double for the 9:1 blend), count / ordered-compaction / swap passes until the reference's own exit
+ * conditions (done, stall, window of one), then one element-parallel gather kernel per level permutes the remaining
+ * planes. All traffic is HBM/L2 streaming: the roofline for this file is memory bandwidth.
+ */
+#include "onb_internal.h"
+
+namespace {
+
+__device__ __forceinline__ float warp_min(float v) { for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ float warp_max(float v) { for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+
+__device__ __forceinline__ uint32_t log_2(uint32_t x) { return x == 0 ? 0u : 31u - __clz(x); }   // Tree.hpp:30-33
+
+struct SplitArgs {
+    float* x[3];            // current coordinate planes (the select permutes x[axis] in place)
+    TreeView t;
+    uint8_t* axis_of;       // per node: split axis
+    uint32_t* pmid;         // per node: first index of the right child
+    uint32_t* lidx;         // per particle: position before this level's select (barneshut.hpp:516)
+    uint32_t* scr;          // per particle scratch for the ordered compactions
+    unsigned long long* stats;   // selects, passes, stalls, scanned
+    uint32_t block;
+    int level, PD, pivot_mode;
+};
+
+constexpr int SPLIT_ROUNDS = 4;   // each warp handles 4 x 32 consecutive elements per chunk
+
+// ---- one CTA = one node of this level -----------------------------------------------------
+__global__ void __launch_bounds__(1024) k_node_split(const SplitArgs a) {
+    const uint32_t node = (1u << a.level) + blockIdx.x;
+    const uint32_t n = a.t.num[node];
+    if (n == 0) return;
+    const uint32_t pf = a.t.ioffset[node], pl = pf + n;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+
+    __shared__ float s_min[32], s_max[32];
+    __shared__ uint32_t s_cnt[32], s_cnt2[32];
+    __shared__ float s_lo[3], s_hi[3];
+
+    // bounding box :621-625 (exact, order independent)
+    for (int d = 0; d < a.PD; ++d) {
+        const float* xd = a.x[d];
+        float lo = INFINITY, hi = -INFINITY;
+        for (uint32_t i = pf + tid; i < pl; i += T) { const float v = xd[i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        lo = warp_min(lo); hi = warp_max(hi);
+        if (lane == 0) { s_min[warp] = lo; s_max[warp] = hi; }
+        __syncthreads();
+        if (warp == 0) {
+            lo = lane < W ? s_min[lane] : INFINITY; hi = lane < W ? s_max[lane] : -INFINITY;
+            lo = warp_min(lo); hi = warp_max(hi);
+            if (lane == 0) { s_lo[d] = lo; s_hi[d] = hi; }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        float bsss = 0.0f;
+        for (int d = 0; d < a.PD; ++d) {
+            const float ns = __fsub_rn(s_hi[d], s_lo[d]);
+            a.t.ns[d][node] = ns;
+            a.t.nc[d][node] = __fmul_rn(0.5f, __fadd_rn(s_hi[d], s_lo[d]));
+            bsss = __double2float_rn(__dadd_rn((double)bsss, __dmul_rn((double)ns, (double)ns)));   // std::pow(float,int) is double :638
+        }
+        a.t.nr[node] = __fmul_rn(0.5f, __fsqrt_rn(bsss));
+    }
+    if (n <= a.block) return;                                                            // :644 leaf
+
+    // longest axis :652-659 (first strict maximum)
+    int axis = 0; float axsz = -1.0f;
+    for (int d = 0; d < a.PD; ++d) { const float ns = __fsub_rn(s_hi[d], s_lo[d]); if (ns > axsz) { axsz = ns; axis = d; } }
+    const uint32_t nless = pf + a.block * (1u << log_2((n - 1) / a.block));              // :663
+    float* key = a.x[axis];
+    uint32_t* lidx = a.lidx;
+    uint32_t* scr = a.scr;
+
+    for (uint32_t i = pf + tid; i < pl; i += T) lidx[i] = i;                             // :516
+    __syncthreads();
+
+    // partial select :519-586; every thread tracks the (identical) window state in registers
+    uint32_t wf = pf, wl = pl - 1;
+    float lo = s_lo[axis], hi = s_hi[axis];
+    const float ideal = __fdiv_rn(__uint2float_rn(nless - pf), __uint2float_rn(pl - pf));     // :522
+    int iters = 0;
+    uint32_t n_pass = 0, n_stall = 0; unsigned long long n_scan = 0;
+    while (wl > wf && iters < 100) {
+        // :538-540
+        const float f0 = __fdiv_rn(__double2float_rn(__dsub_rn(__dsub_rn((double)nless, 0.5), (double)wf)), __uint2float_rn(wl - wf));
+        float frac, pivot;
+        if (a.pivot_mode == 0) {
+            frac = __double2float_rn(__ddiv_rn(__dadd_rn(__dmul_rn(9.0, (double)f0), __dmul_rn(1.0, (double)ideal)), 10.0));
+            pivot = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), frac));
+        } else {   // what g++ -O3 -ffast-math emits for the same two lines
+            frac = __double2float_rn(__dmul_rn(__fma_rn(9.0, (double)f0, (double)ideal), 0.1));
+            pivot = __fmaf_rn(__fsub_rn(hi, lo), frac, lo);
+        }
+        // pass 1: m = #{v < pivot}, and the min/max the two possible next windows will have
+        uint32_t cnt = 0; float mx_lt = -INFINITY, mn_ge = INFINITY;
+        for (uint32_t i = wf + tid; i <= wl; i += T) {
+            const float v = key[i];
+            if (v < pivot) { ++cnt; mx_lt = fmaxf(mx_lt, v); } else mn_ge = fminf(mn_ge, v);
+        }
+        cnt = warp_sum(cnt); mx_lt = warp_max(mx_lt); mn_ge = warp_min(mn_ge);
+        if (lane == 0) { s_cnt[warp] = cnt; s_max[warp] = mx_lt; s_min[warp] = mn_ge; }
+        __syncthreads();
+        {
+            uint32_t c2 = lane < W ? s_cnt[lane] : 0u; float a2 = lane < W ? s_max[lane] : -INFINITY; float b2 = lane < W ? s_min[lane] : INFINITY;
+            cnt = warp_sum(c2); mx_lt = warp_max(a2); mn_ge = warp_min(b2);
+        }
+        __syncthreads();
+        const uint32_t B = wf + cnt;
+
+        // pass 2: ordered compaction of the misplaced positions; a_j ascending from the front of scr[pf..],
+        // b ascending-rank jb stored at scr[pl-1-jb] so that b_j (descending rank j) sits at scr[pl-k+j]
+        uint32_t carryA = 0, carryB = 0;
+        const uint32_t chunk = (uint32_t)W * 32u * SPLIT_ROUNDS;
+        for (uint32_t base = wf; base <= wl; base += chunk) {
+            uint32_t ba[SPLIT_ROUNDS], bb[SPLIT_ROUNDS];
+            uint32_t totA = 0, totB = 0;
+            #pragma unroll
+            for (int r = 0; r < SPLIT_ROUNDS; ++r) {
+                const uint32_t i = base + (uint32_t)warp * 32u * SPLIT_ROUNDS + (uint32_t)r * 32u + lane;
+                const bool valid = i <= wl;
+                const float v = valid ? key[i] : 0.f;
+                const bool lt = v < pivot;
+                ba[r] = __ballot_sync(0xffffffffu, valid && i < B && !lt);
+                bb[r] = __ballot_sync(0xffffffffu, valid && i >= B && lt);
+                totA += __popc(ba[r]); totB += __popc(bb[r]);
+            }
+            if (lane == 0) { s_cnt[warp] = totA; s_cnt2[warp] = totB; }
+            __syncthreads();
+            uint32_t exA = 0, exB = 0, allA = 0, allB = 0;
+            for (int w = 0; w < W; ++w) { const uint32_t ca = s_cnt[w], cb = s_cnt2[w]; if (w < warp) { exA += ca; exB += cb; } allA += ca; allB += cb; }
+            uint32_t offA = carryA + exA, offB = carryB + exB;
+            const uint32_t lt_mask = (1u << lane) - 1u;
+            #pragma unroll
+            for (int r = 0; r < SPLIT_ROUNDS; ++r) {
+                const uint32_t i = base + (uint32_t)warp * 32u * SPLIT_ROUNDS + (uint32_t)r * 32u + lane;
+                if ((ba[r] >> lane) & 1u) scr[pf + offA + __popc(ba[r] & lt_mask)] = i;
+                if ((bb[r] >> lane) & 1u) scr[pl - 1u - (offB + __popc(bb[r] & lt_mask))] = i;
+                offA += __popc(ba[r]); offB += __popc(bb[r]);
+            }
+            carryA += allA; carryB += allB;
+            __syncthreads();
+        }
+        const uint32_t k = carryA;    // == carryB
+        // pass 3: the swaps :549-556
+        for (uint32_t j = tid; j < k; j += T) {
+            const uint32_t pa = scr[pf + j], pb = scr[pl - k + j];
+            const float va = key[pa], vb = key[pb]; key[pa] = vb; key[pb] = va;
+            const uint32_t ia = lidx[pa], ib = lidx[pb]; lidx[pa] = ib; lidx[pb] = ia;
+        }
+        __syncthreads();
+        ++n_pass; n_scan += (wl - wf + 1);
+        // :565-583
+        if (B == nless) break;
+        const uint32_t owf = wf, owl = wl;
+        if (B < nless) { wf = B; lo = mn_ge; } else { wl = B - 1; hi = mx_lt; }
+        if (wf == owf && wl == owl) { ++n_stall; break; }
+        ++iters;
+    }
+    if (tid == 0) {
+        a.axis_of[node] = (uint8_t)axis; a.pmid[node] = nless;
+        a.t.ioffset[2 * node] = pf;        a.t.num[2 * node] = nless - pf;               // :702-704
+        a.t.ioffset[2 * node + 1] = nless; a.t.num[2 * node + 1] = pl - nless;
+        atomicAdd(&a.stats[0], 1ull); atomicAdd(&a.stats[1], (unsigned long long)n_pass);
+        atomicAdd(&a.stats[2], (unsigned long long)n_stall); atomicAdd(&a.stats[3], n_scan);
+    }
+}
+
+// ---- per level: permute the other planes by lidx (reorder :475-485, reorder_idx Parts.hpp:188-196) ----
+struct GatherArgs {
+    float* sx[3]; float* sr; float* ss[3]; uint32_t* sg;     // current
+    float* dx[3]; float* dr; float* ds[3]; uint32_t* dg;     // destination
+    const uint32_t* lidx; uint32_t* owner;
+    const uint8_t* axis_of; const uint32_t* pmid; const uint32_t* num;
+    uint32_t n, block; int level, PD, SD;
+};
+__global__ void k_gather(const GatherArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const uint32_t node = a.owner[i];
+    const bool active = node >= (1u << a.level) && a.num[node] > a.block;
+    const uint32_t j = active ? a.lidx[i] : i;
+    const int ax = active ? (int)a.axis_of[node] : -1;
+    for (int d = 0; d < a.PD; ++d) a.dx[d][i] = a.sx[d][d == ax ? i : j];
+    a.dr[i] = a.sr[j];
+    for (int d = 0; d < a.SD; ++d) a.ds[d][i] = a.ss[d][j];
+    a.dg[i] = a.sg[j];
+    if (active) a.owner[i] = 2u * node + (i >= a.pmid[node] ? 1u : 0u);
+}
+
+__global__ void k_fill_u32(uint32_t* p, uint32_t n, uint32_t v, int iota) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = iota ? i : v;
+}
+
+// ---- finishTree leaves :753-806: one warp per node, one lane per summed quantity, sequential double sums ----
+struct FinishArgs { PartsView p; TreeView t; uint32_t block; int PD, SD, are_sources; };
+
+__global__ void k_finish_leaves(const FinishArgs a) {
+    const uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (node >= (uint32_t)a.t.numnodes || node == 0) return;
+    const uint32_t n = a.t.num[node];
+    if (n == 0 || n > a.block) return;
+    const uint32_t pf = a.t.ioffset[node], pl = pf + n;
+    const int PD = a.PD, SD = a.are_sources ? a.SD : 0;
+    // lane roles: [0,PD) weighted coordinate sums; PD weight sum; (PD, PD+SD] strength sums; PD+SD+1 radius sum
+    double acc = 0.0;
+    if (lane <= PD) {
+        for (uint32_t i = pf; i < pl; ++i) {
+            float w;
+            if (!a.are_sources) w = 1.0f;
+            else if (a.SD == 1) w = fabsf(a.p.s[0][i]);
+            else {
+                w = 0.0f;
+                for (int d = 0; d < a.SD; ++d) { const double sd = (double)a.p.s[d][i]; w = __double2float_rn(__dadd_rn((double)w, __dmul_rn(sd, sd))); }   // :775
+                w = __fsqrt_rn(w);
+            }
+            if (lane < PD) acc = __dadd_rn(acc, (double)__fmul_rn(a.p.x[lane][i], w));     // :790 float product, double sum
+            else           acc = __dadd_rn(acc, (double)w);                                // :786
+        }
+    } else if (lane <= PD + SD) {
+        const float* __restrict__ sd = a.p.s[lane - PD - 1];
+        for (uint32_t i = pf; i < pl; ++i) acc = __dadd_rn(acc, (double)sd[i]);            // :796
+    } else if (lane == PD + SD + 1) {
+        for (uint32_t i = pf; i < pl; ++i) acc = __dadd_rn(acc, (double)a.p.r[i]);         // :800
+    }
+    const double wsum = __shfl_sync(0xffffffffu, acc, PD);
+    if (lane < PD) {
+        const float ooass = __double2float_rn(__ddiv_rn(1.0, __dadd_rn(1.e-20, wsum)));
+        a.t.x[lane][node] = __double2float_rn(__dmul_rn((double)ooass, acc));
+    } else if (lane > PD && lane <= PD + SD) {
+        a.t.s[lane - PD - 1][node] = __double2float_rn(acc);
+    } else if (lane == PD + SD + 1) {
+        a.t.pr[node] = __fdiv_rn(__double2float_rn(acc), __uint2float_rn(n));              // :801
+    }
+}
+
+// ---- finishTree parents :721-746, one level per launch (children first) ----
+__global__ void k_finish_parents(const FinishArgs a, int level) {
+    const uint32_t node = (1u << level) + blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= (2u << level)) return;
+    const uint32_t n = a.t.num[node];
+    if (n <= a.block) return;
+    const uint32_t c1 = 2 * node, c2 = c1 + 1;
+    const float n1 = __uint2float_rn(a.t.num[c1]), n2 = __uint2float_rn(a.t.num[c2]);
+    const float oonp = __fdiv_rn(1.0f, __uint2float_rn(a.t.num[c1] + a.t.num[c2]));
+    for (int d = 0; d < a.PD; ++d)
+        a.t.x[d][node] = __fmul_rn(oonp, __fadd_rn(__fmul_rn(n1, a.t.x[d][c1]), __fmul_rn(n2, a.t.x[d][c2])));
+    for (int d = 0; d < a.SD; ++d) a.t.s[d][node] = __fadd_rn(a.t.s[d][c1], a.t.s[d][c2]);
+    a.t.pr[node] = __fmul_rn(oonp, __fadd_rn(__fmul_rn(n1, a.t.pr[c1]), __fmul_rn(n2, a.t.pr[c2])));
+}
+
+// ---------------------------------------------------------------------------------------------
+// refineLeaf :860-895. One CTA per leaf (leaf j = particles [j*b, min((j+1)*b, n)): the VAM split gives
+// every left child a perfect subtree, so all leaves but the last hold exactly b particles).
+// Each recursion level sorts every segment on its longest axis. Without equal keys any sort gives the
+// same order, so ranks are counted in parallel; a segment that does contain equal keys is re-sorted by
+// one thread with libstdc++ 13's introsort restated literally (std::sort is unstable; the reference's tie
+// order is whatever that algorithm leaves - bits/stl_algo.h: threshold 16, median-of-3 to first,
+// unguarded partition, final insertion sort).
+// ---------------------------------------------------------------------------------------------
+struct IdxKey { const float* v; __device__ bool lt(int a, int b) const { return v[a] < v[b]; } };
+
+__device__ void dev_insertion_unguarded(int* last, IdxKey K) {
+    const int val = *last; int* next = last - 1;
+    while (K.lt(val, *next)) { *last = *next; last = next; --next; }
+    *last = val;
+}
+__device__ void dev_insertion_sort(int* first, int* last, IdxKey K) {
+    if (first == last) return;
+    for (int* i = first + 1; i != last; ++i) {
+        if (K.lt(*i, *first)) { const int val = *i; for (int* q = i; q != first; --q) *q = *(q - 1); *first = val; }
+        else dev_insertion_unguarded(i, K);
+    }
+}
+__device__ bool dev_libstdcxx_sort(int* first, int* last, IdxKey K) {
+    const int n = (int)(last - first);
+    if (n == 0) return true;
+    // __introsort_loop with an explicit stack of pending right parts
+    int stk_f[40], stk_l[40], stk_d[40]; int sp = 0;
+    stk_f[0] = 0; stk_l[0] = n; stk_d[0] = 2 * (int)log_2((uint32_t)n); sp = 1;
+    bool ok = true;
+    while (sp > 0) {
+        --sp; int* f = first + stk_f[sp]; int* l = first + stk_l[sp]; int depth = stk_d[sp];
+        while (l - f > 16) {
+            if (depth == 0) { ok = false; break; }      // heapsort fallback of libstdc++: not restated (needs 2 log2 n bad splits)
+            --depth;
+            int* mid = f + (l - f) / 2;
+            int* a = f + 1; int* b = mid; int* c = l - 1;   // __move_median_to_first(f, f+1, mid, l-1)
+            int* med;
+            if (K.lt(*a, *b)) { if (K.lt(*b, *c)) med = b; else if (K.lt(*a, *c)) med = c; else med = a; }
+            else if (K.lt(*a, *c)) med = a; else if (K.lt(*b, *c)) med = c; else med = b;
+            { const int tmp = *f; *f = *med; *med = tmp; }
+            int* lo = f + 1; int* hi = l;                   // __unguarded_partition(f+1, l, f)
+            while (true) {
+                while (K.lt(*lo, *f)) ++lo;
+                --hi;
+                while (K.lt(*f, *hi)) --hi;
+                if (!(lo < hi)) break;
+                const int tmp = *lo; *lo = *hi; *hi = tmp;
+                ++lo;
+            }
+            if (sp < 40) { stk_f[sp] = (int)(lo - first); stk_l[sp] = (int)(l - first); stk_d[sp] = depth; ++sp; } else ok = false;
+            l = lo;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16) { dev_insertion_sort(first, first + 16, K); for (int* i = first + 16; i != last; ++i) dev_insertion_unguarded(i, K); }
+    else dev_insertion_sort(first, last, K);
+    return ok;
+}
+
+struct RefineArgs { PartsView p; uint32_t n, block; int PD, SD, OD, are_sources; int* flag; unsigned long long* tie_sorts; };
+
+__global__ void __launch_bounds__(128) k_refine(const RefineArgs a) {
+    const uint32_t pf = blockIdx.x * a.block;
+    const int n = (int)min(a.block, a.n - pf);
+    const int tid = threadIdx.x;
+    __shared__ float sx[3][128];
+    __shared__ int sidx[128];
+    __shared__ int perm[128];
+    __shared__ int segtie[128];
+    __shared__ float keys[128];
+    const bool act = tid < n;
+    if (act) { for (int d = 0; d < a.PD; ++d) sx[d][tid] = a.p.x[d][pf + tid]; perm[tid] = tid; }
+    int sa = 0, sb = n;             // my segment [sa, sb)
+    __syncthreads();
+    while (true) {
+        const bool work = act && (sb - sa) >= 3;                                          // :864
+        if (!__syncthreads_or(work ? 1 : 0)) break;
+        int axis = 0; int rank = 0; bool tie = false;
+        if (act) segtie[tid] = 0;
+        if (work) {
+            float bs[3];
+            for (int d = 0; d < a.PD; ++d) {
+                float lo = sx[d][sa], hi = lo;
+                for (int j = sa; j < sb; ++j) { const float v = sx[d][j]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+                bs[d] = __fsub_rn(hi, lo);
+            }
+            for (int d = 1; d < a.PD; ++d) if (bs[axis] < bs[d]) axis = d;                // std::max_element :878
+            const float key = sx[axis][tid];
+            for (int j = sa; j < sb; ++j) { const float v = sx[axis][j]; rank += (v < key); tie |= (v == key && j != tid); }
+            keys[tid] = key;
+        }
+        __syncthreads();
+        if (work && tie) segtie[sa] = 1;
+        __syncthreads();
+        if (work) {
+            if (!segtie[sa]) sidx[sa + rank] = tid;
+            else if (tid == sa) {
+                for (int j = sa; j < sb; ++j) sidx[j] = j;                                // :408
+                IdxKey K; K.v = keys;
+                if (!dev_libstdcxx_sort(sidx + sa, sidx + sb, K)) atomicExch(a.flag, ONB_ERR_UNSUPPORTED);
+                atomicAdd(a.tie_sorts, 1ull);
+            }
+        }
+        __syncthreads();
+        float nx[3]; int np = 0;
+        if (work) { const int src = sidx[tid]; for (int d = 0; d < a.PD; ++d) nx[d] = sx[d][src]; np = perm[src]; }
+        __syncthreads();
+        if (work) {
+            for (int d = 0; d < a.PD; ++d) sx[d][tid] = nx[d];
+            perm[tid] = np;
+            const int pm = sa + (1 << log_2((uint32_t)(sb - sa - 1)));                    // :890
+            if (tid < pm) sb = pm; else sa = pm;
+        }
+        __syncthreads();
+    }
+    // write back: coordinates from shared memory, the other planes through the composed permutation
+    float vr = 0.f, vs[3] = {0.f, 0.f, 0.f}; uint32_t vg = 0;
+    if (act) {
+        const uint32_t src = pf + perm[tid];
+        vr = a.p.r[src];
+        if (a.are_sources) for (int d = 0; d < a.SD; ++d) vs[d] = a.p.s[d][src];
+        if (a.p.gidx) vg = a.p.gidx[src];
+    }
+    __syncthreads();
+    if (act) {
+        for (int d = 0; d < a.PD; ++d) a.p.x[d][pf + tid] = sx[d][tid];
+        a.p.r[pf + tid] = vr;
+        if (a.are_sources) for (int d = 0; d < a.SD; ++d) a.p.s[d][pf + tid] = vs[d];
+        if (a.p.gidx) a.p.gidx[pf + tid] = vg;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static unsigned long long* g_build_stats_dev = nullptr;   // per-process scratch (selects, passes, stalls, scanned, tie sorts)
+
+extern "C" int onb_get_build_stats(onb_context* c, uint64_t out[5]) {
+    if (!g_build_stats_dev) { for (int i = 0; i < 5; ++i) out[i] = 0; return ONB_OK; }
+    unsigned long long h[5];
+    ONB_CUDA(cudaMemcpy(h, g_build_stats_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 5; ++i) out[i] = h[i];
+    return ONB_OK;
+}
+static int onb_pivot_mode = 0;   // 0 = the reference source evaluated in IEEE order; 1 = as g++ -O3 -ffast-math contracts it
+extern "C" void onb_set_pivot_mode(int mode) { onb_pivot_mode = mode ? 1 : 0; }
+
+int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
+    const uint32_t n = p.n;
+    const int PD = c->PD, SD = p.are_sources ? c->SD : 0;
+    if (n == 0) { c->err = "make_tree: no particles"; return ONB_ERR_ARG; }
+    if (!g_build_stats_dev) ONB_CUDA(cudaMalloc(&g_build_stats_dev, 5 * sizeof(unsigned long long)));
+    ONB_CUDA(cudaMemsetAsync(g_build_stats_dev, 0, 4 * sizeof(unsigned long long), c->stream));
+
+    // scratch: second copy of every plane (ping-pong), per-particle index planes, per-node split records
+    const size_t capf = (size_t)p.cap * sizeof(float);
+    float* alt_x[3] = {nullptr, nullptr, nullptr}; float* alt_r = nullptr; float* alt_s[3] = {nullptr, nullptr, nullptr};
+    uint32_t *alt_g = nullptr, *cur_g = nullptr, *lidx = nullptr, *scr = nullptr, *owner = nullptr, *pmid = nullptr; uint8_t* axis_of = nullptr;
+    for (int d = 0; d < PD; ++d) ONB_CUDA(cudaMalloc(&alt_x[d], capf));
+    ONB_CUDA(cudaMalloc(&alt_r, capf));
+    for (int d = 0; d < SD; ++d) ONB_CUDA(cudaMalloc(&alt_s[d], capf));
+    ONB_CUDA(cudaMalloc(&alt_g, (size_t)n * 4)); ONB_CUDA(cudaMalloc(&cur_g, (size_t)n * 4));
+    ONB_CUDA(cudaMalloc(&lidx, (size_t)n * 4)); ONB_CUDA(cudaMalloc(&scr, (size_t)n * 4)); ONB_CUDA(cudaMalloc(&owner, (size_t)n * 4));
+    ONB_CUDA(cudaMalloc(&pmid, (size_t)t.numnodes * 4)); ONB_CUDA(cudaMalloc(&axis_of, (size_t)t.numnodes));
+    for (int d = 0; d < PD; ++d) ONB_CUDA(cudaMemsetAsync(alt_x[d], 0, capf, c->stream));
+    ONB_CUDA(cudaMemsetAsync(alt_r, 0, capf, c->stream));
+    for (int d = 0; d < SD; ++d) ONB_CUDA(cudaMemsetAsync(alt_s[d], 0, capf, c->stream));
+
+    const int TB = 256; const uint32_t GB = (n + TB - 1) / TB;
+    k_fill_u32<<<GB, TB, 0, c->stream>>>(cur_g, n, 0, 1); ONB_LAUNCH(c);                 // gidx = iota :823
+    k_fill_u32<<<GB, TB, 0, c->stream>>>(owner, n, 1, 0); ONB_LAUNCH(c);
+    ONB_CUDA(cudaMemsetAsync(t.num, 0, (size_t)t.numnodes * 4, c->stream));
+    ONB_CUDA(cudaMemsetAsync(t.ioffset, 0, (size_t)t.numnodes * 4, c->stream));
+    { const uint32_t root[1] = { n }; ONB_CUDA(cudaMemcpyAsync(t.num + 1, root, 4, cudaMemcpyHostToDevice, c->stream)); }
+
+    float* cx[3] = { p.x[0], p.x[1], p.x[2] }; float* cr = p.r; float* cs[3] = { p.s[0], p.s[1], p.s[2] }; uint32_t* cg = cur_g;
+    float* ax[3] = { alt_x[0], alt_x[1], alt_x[2] }; float* ar = alt_r; float* as[3] = { alt_s[0], alt_s[1], alt_s[2] }; uint32_t* ag = alt_g;
+
+    uint32_t leftmost = n;     // the leftmost node of a level is its largest
+    for (int lev = 0; lev < t.levels; ++lev) {
+        SplitArgs sa;
+        for (int d = 0; d < 3; ++d) sa.x[d] = cx[d];
+        sa.t = view_of(t); sa.axis_of = axis_of; sa.pmid = pmid; sa.lidx = lidx; sa.scr = scr; sa.stats = g_build_stats_dev;
+        sa.block = c->block; sa.level = lev; sa.PD = PD; sa.pivot_mode = onb_pivot_mode;
+        int threads = 1024;
+        while (threads > 128 && (uint32_t)threads * 2 > leftmost) threads >>= 1;
+        k_node_split<<<1u << lev, threads, 0, c->stream>>>(sa); ONB_LAUNCH(c);
+        ONB_CUDA(cudaGetLastError());
+        if (leftmost <= (uint32_t)c->block) break;     // every node of this level is a leaf: nothing below
+        GatherArgs ga;
+        for (int d = 0; d < 3; ++d) { ga.sx[d] = cx[d]; ga.dx[d] = ax[d]; ga.ss[d] = cs[d]; ga.ds[d] = as[d]; }
+        ga.sr = cr; ga.dr = ar; ga.sg = cg; ga.dg = ag;
+        ga.lidx = lidx; ga.owner = owner; ga.axis_of = axis_of; ga.pmid = pmid; ga.num = t.num;
+        ga.n = n; ga.block = c->block; ga.level = lev; ga.PD = PD; ga.SD = SD;
+        k_gather<<<GB, TB, 0, c->stream>>>(ga); ONB_LAUNCH(c);
+        ONB_CUDA(cudaGetLastError());
+        for (int d = 0; d < 3; ++d) { std::swap(cx[d], ax[d]); std::swap(cs[d], as[d]); }
+        std::swap(cr, ar); std::swap(cg, ag);
+        leftmost = (uint32_t)c->block * (1u << (31 - __builtin_clz((leftmost - 1) / c->block)));
+    }
+    // the particle set now owns whichever buffers hold the final order
+    for (int d = 0; d < PD; ++d) p.x[d] = cx[d];
+    p.r = cr;
+    for (int d = 0; d < SD; ++d) p.s[d] = cs[d];
+    if (!p.are_sources) { if (p.gidx) cudaFree(p.gidx); p.gidx = cg; cg = nullptr; }
+    p.packed_valid = false;
+
+    // finishTree
+    FinishArgs fa; fa.p = view_of(p); fa.t = view_of(t); fa.block = c->block; fa.PD = PD; fa.SD = c->SD; fa.are_sources = p.are_sources ? 1 : 0;
+    k_finish_leaves<<<((size_t)t.numnodes * 32 + 255) / 256, 256, 0, c->stream>>>(fa); ONB_LAUNCH(c);
+    ONB_CUDA(cudaGetLastError());
+    for (int lev = t.levels - 2; lev >= 0; --lev) {
+        const uint32_t nn = 1u << lev;
+        k_finish_parents<<<(nn + 127) / 128, 128, 0, c->stream>>>(fa, lev); ONB_LAUNCH(c);
+    }
+    ONB_CUDA(cudaGetLastError());
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int d = 0; d < PD; ++d) cudaFree(ax[d]);
+    cudaFree(ar);
+    for (int d = 0; d < SD; ++d) cudaFree(as[d]);
+    cudaFree(ag); if (cg) cudaFree(cg);
+    cudaFree(lidx); cudaFree(scr); cudaFree(owner); cudaFree(pmid); cudaFree(axis_of);
+    t.built = true;
+    return ONB_OK;
+}
+
+int onb_tree_refine(onb_context* c, DParts& p, DTree& t) {
+    if (!t.built) { c->err = "refine: tree not built"; return ONB_ERR_ARG; }
+    if (c->block > 128) { c->err = "refine: block size > 128 not supported by the GPU build"; return ONB_ERR_UNSUPPORTED; }
+    if (!g_build_stats_dev) ONB_CUDA(cudaMalloc(&g_build_stats_dev, 5 * sizeof(unsigned long long)));
+    ONB_CUDA(cudaMemsetAsync(g_build_stats_dev + 4, 0, sizeof(unsigned long long), c->stream));
+    RefineArgs ra; ra.p = view_of(p); ra.n = p.n; ra.block = c->block; ra.PD = c->PD; ra.SD = c->SD; ra.OD = c->OD;
+    ra.are_sources = p.are_sources ? 1 : 0; ra.flag = c->d_flag; ra.tie_sorts = g_build_stats_dev + 4;
+    const uint32_t nleaf = (p.n + c->block - 1) / c->block;
+    k_refine<<<nleaf, 128, 0, c->stream>>>(ra); ONB_LAUNCH(c);
+    ONB_CUDA(cudaGetLastError());
+    p.packed_valid = false;
+    return onb_check_flag(c, "refine (introsort depth limit: libstdc++ heapsort fallback is not restated)");
+}
