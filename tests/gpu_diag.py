@@ -101,6 +101,11 @@ def main():
     g.upward(1); o.upward(1)
     cmp_parts("eqtargs", g.parts(3), o.parts(3), out, ("x", "r"))
 
+    if os.environ.get("DIAG_TREE_ONLY"):
+        print("   upward %.2f ms" % g.phase_ms("upward"))
+        bad = [l for l in out if not l.startswith("OK")]
+        print("SUMMARY (tree only) %s N=%d: %d checks, %d not OK" % (physics, N, len(out), len(bad)))
+        return
     # ---- evaluations, strict arithmetic: bit-exact expected
     tsk = max(1, N // 400)
     res = {}
