@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py - the hot path of ongrav3d (dual-tree, -t=1.4 -o=4 -b=128, charges) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n PARTICLES]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic input (the drivers' own mt19937(12345) cloud):
+source tree build -> barycentric upward pass -> target tree build -> in-leaf refinement -> target equivalent
+points -> dual-tree evaluation (interaction lists + leaf-block P2P + downward interpolation), i.e. what the
+reference prints as "[fast total]". metric = pair interactions per second: the exact number of source-target pairs
+the dual-tree lists contain (the same lists as the reference's, proven bit-for-bit by tests) / step seconds.
+
+value : inputs already resident in HBM when the timed region starts (CUDA events on the library's stream).
+e2e   : the same step through the C ABI with HOST buffers: pinned host -> device copies of sources and targets and
+        the device -> host read of the target outputs are inside the timed region.
+The last line printed by rank 0 is the JSON record.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+THETA, ORDER, BLOCK = 1.4, 4, 128
+FLOP_PER_PAIR = 19          # reference ongrav3d.cpp:49,60
+FP32_SLOTS_PER_PAIR = 12    # 3 FADD + 6 FFMA + 3 FMUL in the SASS loop of k_p2p_lists<grav> (plus 1 MUFU)
+
+# exact dual-tree pair counts of `ongrav3d -n=N -t=1.4 -o=4 -b=128` (seed 12345), measured by the GPU list builder,
+# whose lists are bit-identical to the reference's (tests/test_gpu_parity.py). Used by the reference arm, which
+# cannot count them itself (the reference compiles its statistics out: ongrav3d.cpp:218 dostats=false).
+DTT_PAIRS = {}
+_pairs_file = os.path.join(ROOT, "tests", "golden", "dtt_pairs.json")
+if os.path.exists(_pairs_file):
+    with open(_pairs_file) as _f:
+        DTT_PAIRS = {int(k): int(v) for k, v in json.load(_f).items()}
+
+
+def pairs_estimate(n):
+    if n in DTT_PAIRS:
+        return DTT_PAIRS[n], "exact"
+    return int(n * 16500.0), "estimate(16.5k pairs/target)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = []; smax = 0; reasons = set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); smax = max(smax, float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0.5 * smax] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU implementation of the same step (its unmodified templates compiled in place into
+    oracle/_ref/fast with the reference's CMake flags), all host threads, on a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle.refapi import RefSession, ref_available
+    cores = os.cpu_count() or 1
+    if not ref_available("grav3d", "fast"):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/fast/libref_grav3d.so is not built"}))
+        return 0
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+
+    def step(n):
+        s = RefSession("grav3d", n, n, block=BLOCK, order=ORDER, eq_block=128, build="fast")
+        s.init_driver()
+        t0 = time.perf_counter()
+        s.make_tree(0); s.upward(0); s.make_tree(1); s.refine(1); s.upward(1)
+        t1 = time.perf_counter()
+        s.zero_vels(); s.fastsumm(THETA, parallel=True)       # the driver's own omp-task invocation (ongrav3d.cpp:880-884)
+        t2 = time.perf_counter()
+        s.close()
+        return t1 - t0, t2 - t1
+
+    # size the sample so that warmup+steps fit in ~150 s: probe at 1e5 (DTT is O(N))
+    tb, te = step(100000)
+    per_particle = (tb + te) / 1e5
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n = args.n_ref or 100000
+    if not args.n_ref:
+        for cand in (1000000, 500000, 200000, 100000):
+            if cand in DTT_PAIRS and per_particle * cand <= budget:
+                n = cand; break
+    for _ in range(args.warmup):
+        step(n)
+    tot_b = tot_e = 0.0
+    for _ in range(args.steps):
+        b, e = step(n)
+        tot_b += b; tot_e += e
+    pairs, how = pairs_estimate(n)
+    sec = (tot_b + tot_e) / args.steps
+    val = pairs / sec * 1e-9
+    rec = {
+        "impl": "reference", "metric": "ongrav3d_dualtree_pair_interactions_per_s", "value": val, "unit": "Ginteractions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ongrav3d -n=10000000 -t=1.4 -o=4 -b=128 charges, dual-tree (reference arm: bounded sample, see cpu_baseline.sample)",
+                   "theta": THETA, "order": ORDER, "block": BLOCK},
+        "seconds_per_eval": tot_e / args.steps, "seconds_tree_and_upward": tot_b / args.steps, "pairs_per_step": pairs, "pairs_count": how,
+        "cpu_baseline": {"value": val, "unit": "Ginteractions/s", "cores": cores, "kind": "reference",
+                         "sample": "N=%d particles of the same generator (whole step: trees+upward+dual-tree eval); the reference's dual tree is O(N)" % n},
+        "e2e": {"value": val, "unit": "Ginteractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(rec))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from onbody_b200.api import GpuSession, driver_inputs, ARITH_FAST
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N = args.n
+    physics = "grav3d"
+
+    # synthetic input exactly as the driver makes it, in pinned host memory
+    x, r, s = driver_inputs(physics, N, True)
+    hx = torch.from_numpy(x).pin_memory(); hr = torch.from_numpy(r).pin_memory(); hs = torch.from_numpy(s).pin_memory()
+    hu = torch.empty((3, N), dtype=torch.float32).pin_memory()
+    del x, r, s
+    # resident copies for the device-timed leg
+    dx = hx.cuda(); dr = hr.cuda(); ds = hs.cuda()
+    g = GpuSession(physics, N, N, block=BLOCK, order=ORDER, arith=ARITH_FAST, device=local)
+    g.set_shard(rank, world)
+    h2d = (hx.numel() + hr.numel() + hs.numel() + hx.numel() + hr.numel()) * 4
+    d2h = hu.numel() * 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    phases = {}
+
+    def hot_path():
+        g.make_tree(0); phases["src_tree"] = phases.get("src_tree", 0.0) + g.phase_ms("tree")
+        g.upward(0); phases["upward"] = phases.get("upward", 0.0) + g.phase_ms("upward")
+        g.make_tree(1); phases["tgt_tree"] = phases.get("tgt_tree", 0.0) + g.phase_ms("tree")
+        g.refine(1); phases["refine"] = phases.get("refine", 0.0) + g.phase_ms("refine")
+        g.upward(1); phases["tgt_equiv"] = phases.get("tgt_equiv", 0.0) + g.phase_ms("upward")
+        g.fastsumm(THETA)
+        for k in ("eval", "lists", "p2p", "downward"):
+            phases[k] = phases.get(k, 0.0) + g.phase_ms(k)
+
+    def step_resident():
+        g.set_sources_ptr(N, dx.data_ptr(), dr.data_ptr(), ds.data_ptr())      # device -> device, untimed
+        g.set_targets_ptr(N, dx.data_ptr(), dr.data_ptr())
+        g.timer_start()
+        hot_path()
+        return g.timer_stop_ms()
+
+    def step_e2e():
+        g.timer_start()
+        g.set_sources_ptr(N, hx.data_ptr(), hr.data_ptr(), hs.data_ptr())      # pinned host -> device
+        g.set_targets_ptr(N, hx.data_ptr(), hr.data_ptr())
+        hot_path()
+        g.results_into(hu.data_ptr())                                          # device -> pinned host
+        return g.timer_stop_ms()
+
+    for _ in range(max(args.warmup, 1)):
+        step_resident()
+    step_e2e()
+    peak_tf = g.measure_fp32_peak() if rank == 0 else 0.0
+
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    # ---- timed: K resident steps
+    phases.clear()
+    l0 = g.launch_count()
+    barrier()
+    t_res = 0.0
+    for _ in range(args.steps):
+        t_res += step_resident()
+    barrier()
+    launches = g.launch_count() - l0
+    ph_res = dict(phases)
+    pairs_local = g.last_pairs()
+    # ---- timed: K end-to-end steps
+    phases.clear()
+    barrier()
+    t_e2e = 0.0
+    for _ in range(args.steps):
+        t_e2e += step_e2e()
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # max over ranks for times, sum for work
+    red = torch.tensor([t_res, t_e2e, float(pairs_local), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = red.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = red.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t_res, t_e2e = mx[0].item(), mx[1].item()
+        pairs_total, launches_total = int(sm[2].item()), int(sm[3].item())
+    else:
+        pairs_total, launches_total = int(pairs_local), int(launches)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    K = args.steps
+    sec_res = t_res / K * 1e-3
+    sec_e2e = t_e2e / K * 1e-3
+    value = pairs_total / sec_res * 1e-9
+    e2e = pairs_total / sec_e2e * 1e-9
+    p2p_ms = ph_res.get("p2p", 0.0) / K
+    achieved_tf = pairs_local * FLOP_PER_PAIR / (p2p_ms * 1e-3) * 1e-12 if p2p_ms > 0 else 0.0
+    peaks, peaks_src = measured_peaks()
+    clocks = sampler.summary()
+    tree_ms = (ph_res.get("src_tree", 0) + ph_res.get("tgt_tree", 0)) / K
+    # algorithmic bytes of one tree build: every plane read once + written once: sources 6 planes + targets 4 planes + gidx
+    tree_bytes = N * (2 * 4 * (3 + 1 + 1) + 2 * 4 * (3 + 1) + 8)
+    rec = {
+        "metric": "ongrav3d_dualtree_pair_interactions_per_s", "value": value, "unit": "Ginteractions/s",
+        "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": sec_res * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ongrav3d -n=%d -t=1.4 -o=4 -b=128 charges, dual-tree (BASELINE.json configs[1])" % N,
+                   "theta": THETA, "order": ORDER, "block": BLOCK, "n_particles": N,
+                   "parallelism": "target-tree sharded x%d, source side replicated" % world,
+                   "l2_policy": "inputs larger than L2 (%.0f MB of particle planes per tree vs 126 MB L2); every step rebuilds from pristine input" % (N * 24 / 1e6)},
+        "seconds_per_step": sec_res, "seconds_per_eval": ph_res.get("eval", 0.0) / K * 1e-3, "pairs_per_step": pairs_total,
+        "phases_ms": {k: v / K for k, v in ph_res.items()},
+        "e2e": {"value": e2e, "unit": "Ginteractions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": sec_e2e * 1e3},
+        "gpu_launches": launches_total,
+        "clocks": clocks,
+        "roofline": {"kernel": "k_p2p_lists<grav3d,fast>", "bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (achieved_tf / peak_tf) if peak_tf else None, "traffic": None,
+                     "peak_source": "FP32 FMA issue microbenchmark run in this process (onb_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 SIMT figure",
+                     "flop_per_pair": FLOP_PER_PAIR,
+                     "fp32_issue_util": (pairs_local * FP32_SLOTS_PER_PAIR * 2 / (p2p_ms * 1e-3) * 1e-12 / peak_tf) if (peak_tf and p2p_ms > 0) else None,
+                     "share_of_step": (p2p_ms / (sec_res * 1e3)) if sec_res > 0 else None},
+        "roofline_tree": {"kernels": "k_node_split + k_gather (both trees)", "bound": "hbm", "achieved": tree_bytes / (tree_ms * 1e-3) * 1e-9 if tree_ms > 0 else None,
+                          "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "peak_source": peaks_src,
+                          "frac": (tree_bytes / (tree_ms * 1e-3) * 1e-9 / peaks.get("hbm_gbs")) if tree_ms > 0 else None, "traffic": None},
+    }
+    # ---- CPU baseline beside it (rank 0, N=1 only): the reference itself on a bounded sample
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle.refapi import RefSession, ref_available
+            cores = os.cpu_count() or 1
+            os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+            n_cpu = args.n_ref or (1000000 if 1000000 in DTT_PAIRS else 100000)
+            kind = "reference" if ref_available("grav3d", "fast") else "port"
+            if kind == "reference":
+                sref = RefSession("grav3d", n_cpu, n_cpu, block=BLOCK, order=ORDER, eq_block=128, build="fast")
+            else:
+                from oracle.refapi import PortSession
+                n_cpu = 100000
+                sref = PortSession("grav3d", n_cpu, n_cpu, block=BLOCK, order=ORDER, eq_block=128)
+            sref.init_driver()
+            t0 = time.perf_counter()
+            sref.make_tree(0); sref.upward(0); sref.make_tree(1); sref.refine(1); sref.upward(1)
+            sref.zero_vels(); sref.fastsumm(THETA, parallel=True)
+            dt = time.perf_counter() - t0
+            pr, how = pairs_estimate(n_cpu)
+            rec["cpu_baseline"] = {"value": pr / dt * 1e-9, "unit": "Ginteractions/s", "cores": cores if kind == "reference" else 1, "kind": kind,
+                                   "seconds": dt, "pairs": pr, "pairs_count": how,
+                                   "sample": "N=%d particles of the same generator, whole step (trees+upward+dual-tree eval) once; the dual tree is O(N)" % n_cpu}
+        except Exception as e:  # the baseline must never take the GPU number down with it
+            rec["cpu_baseline"] = {"value": None, "unit": "Ginteractions/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+    print(json.dumps(rec))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("ONB_BENCH_N", "10000000")))
+    ap.add_argument("--n-ref", type=int, default=0, help="sample size of the CPU reference leg (default: sized to a few minutes)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

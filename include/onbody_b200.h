@@ -74,7 +74,8 @@ ONB_API const char*  onb_last_create_error(void);
 ONB_API int onb_set_params(onb_context* c, int block_size, int order, int arith);
 ONB_API void onb_dims(const onb_context* c, int* pd, int* sd, int* od, int* has_fastsumm);
 
-/* inputs (host -> device copies) ------------------------------------------------------------- */
+/* inputs (copies into the context's own device arrays; the pointers may be host memory - pinned for full PCIe
+ * speed - or device memory, the copy kind is resolved by unified addressing) ------------------------------ */
 ONB_API int onb_set_sources(onb_context* c, uint64_t n, const float* x, const float* r, const float* s);
 ONB_API int onb_set_targets(onb_context* c, uint64_t n, const float* x, const float* r);
 /* the drivers' own synthetic initialisation (std::mt19937(12345), Parts.hpp:99-109,169-176), done on the
@@ -114,6 +115,9 @@ ONB_API int onb_get_stats(const onb_context* c, uint64_t out[9]);
 /* device time (CUDA events on the context's stream) of the named phase of the last call that ran it, in ms;
  * names: "tree", "refine", "upward", "lists", "p2p", "downward", "eval". Returns <0 if never run. */
 ONB_API double   onb_phase_ms(const onb_context* c, const char* name);
+/* step timer: CUDA events on the context's stream around everything issued between the two calls */
+ONB_API int      onb_timer_start(onb_context* c);
+ONB_API double   onb_timer_stop_ms(onb_context* c);
 /* exact number of source-target pairs the pair kernels evaluated in the last evaluation call */
 ONB_API uint64_t onb_last_pairs(const onb_context* c);
 /* number of kernel launches issued by this context since creation */

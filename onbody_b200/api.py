@@ -69,6 +69,9 @@ def load_library():
     L.onb_get_stats.argtypes = [C.c_void_p, C.c_uint64 * 9]
     L.onb_phase_ms.restype = C.c_double
     L.onb_phase_ms.argtypes = [C.c_void_p, C.c_char_p]
+    L.onb_timer_start.argtypes = [C.c_void_p]
+    L.onb_timer_stop_ms.restype = C.c_double
+    L.onb_timer_stop_ms.argtypes = [C.c_void_p]
     L.onb_last_pairs.restype = C.c_uint64
     L.onb_last_pairs.argtypes = [C.c_void_p]
     L.onb_launch_count.restype = C.c_uint64
@@ -242,6 +245,8 @@ class GpuSession:
         self._chk(self.lib.onb_get_build_stats(self.h, out))
         return dict(zip(("selects", "passes", "stalls", "scanned", "tie_sorts"), [int(v) for v in out]))
 
+    def timer_start(self): self._chk(self.lib.onb_timer_start(self.h))
+    def timer_stop_ms(self): return float(self.lib.onb_timer_stop_ms(self.h))
     def phase_ms(self, name): return float(self.lib.onb_phase_ms(self.h, name.encode()))
     def last_pairs(self): return int(self.lib.onb_last_pairs(self.h))
     def launch_count(self): return int(self.lib.onb_launch_count(self.h))

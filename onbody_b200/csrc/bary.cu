@@ -161,7 +161,7 @@ int onb_bary_upward(onb_context* c, DParts& p, DParts& ep, DTree& t) {
     if (!t.built) { c->err = "upward: tree not built"; return ONB_ERR_ARG; }
     const uint32_t need = (uint32_t)(t.numnodes / 2) * (uint32_t)c->ebs;                  // ongrav3d.cpp:645,696
     if (ep.n != need) {
-        onb_free_parts(ep);
+        onb_free_parts(c, ep);
         int rc = onb_alloc_parts(c, ep, need, p.are_sources);
         if (rc) return rc;
     }

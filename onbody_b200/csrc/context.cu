@@ -20,52 +20,52 @@ int onb_alloc_parts(onb_context* c, DParts& p, uint32_t n, bool are_sources) {
     p = DParts();
     p.n = n; p.cap = ((n + 63u) & ~31u) + 32u; p.PD = c->PD; p.SD = c->SD; p.OD = c->OD; p.are_sources = are_sources;
     const size_t bytes = (size_t)p.cap * sizeof(float);
-    for (int d = 0; d < c->PD; ++d) { ONB_CUDA(cudaMalloc(&p.x[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.x[d], 0, bytes, c->stream)); }
-    ONB_CUDA(cudaMalloc(&p.r, bytes)); ONB_CUDA(cudaMemsetAsync(p.r, 0, bytes, c->stream));
+    for (int d = 0; d < c->PD; ++d) { ONB_CUDA(onb_dmalloc(c, (void**)&p.x[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.x[d], 0, bytes, c->stream)); }
+    ONB_CUDA(onb_dmalloc(c, (void**)&p.r, bytes)); ONB_CUDA(cudaMemsetAsync(p.r, 0, bytes, c->stream));
     if (are_sources) {
-        for (int d = 0; d < c->SD; ++d) { ONB_CUDA(cudaMalloc(&p.s[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.s[d], 0, bytes, c->stream)); }
-        ONB_CUDA(cudaMalloc(&p.pk0, (size_t)p.cap * sizeof(float4)));
+        for (int d = 0; d < c->SD; ++d) { ONB_CUDA(onb_dmalloc(c, (void**)&p.s[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.s[d], 0, bytes, c->stream)); }
+        ONB_CUDA(onb_dmalloc(c, (void**)&p.pk0, (size_t)p.cap * sizeof(float4)));
         const bool nf2 = c->physics == ONB_VORT3D || c->physics == ONB_VORTGRAD3D;
-        if (nf2) ONB_CUDA(cudaMalloc(&p.pk1, (size_t)p.cap * sizeof(float4)));
-        if (c->physics == ONB_GRAV3D) ONB_CUDA(cudaMalloc(&p.pk2, bytes));
+        if (nf2) ONB_CUDA(onb_dmalloc(c, (void**)&p.pk1, (size_t)p.cap * sizeof(float4)));
+        if (c->physics == ONB_GRAV3D) ONB_CUDA(onb_dmalloc(c, (void**)&p.pk2, bytes));
     } else {
-        for (int d = 0; d < c->OD; ++d) { ONB_CUDA(cudaMalloc(&p.u[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.u[d], 0, bytes, c->stream)); }
+        for (int d = 0; d < c->OD; ++d) { ONB_CUDA(onb_dmalloc(c, (void**)&p.u[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.u[d], 0, bytes, c->stream)); }
     }
     return ONB_OK;
 }
-void onb_free_parts(DParts& p) {
-    for (int d = 0; d < ONB_MAX_PD; ++d) if (p.x[d]) cudaFree(p.x[d]);
-    if (p.r) cudaFree(p.r);
-    for (int d = 0; d < ONB_MAX_SD; ++d) if (p.s[d]) cudaFree(p.s[d]);
-    for (int d = 0; d < ONB_MAX_OD; ++d) if (p.u[d]) cudaFree(p.u[d]);
-    if (p.gidx) cudaFree(p.gidx);
-    if (p.pk0) cudaFree(p.pk0); if (p.pk1) cudaFree(p.pk1); if (p.pk2) cudaFree(p.pk2);
+void onb_free_parts(onb_context* c, DParts& p) {
+    for (int d = 0; d < ONB_MAX_PD; ++d) if (p.x[d]) onb_dfree(c, p.x[d]);
+    if (p.r) onb_dfree(c, p.r);
+    for (int d = 0; d < ONB_MAX_SD; ++d) if (p.s[d]) onb_dfree(c, p.s[d]);
+    for (int d = 0; d < ONB_MAX_OD; ++d) if (p.u[d]) onb_dfree(c, p.u[d]);
+    if (p.gidx) onb_dfree(c, p.gidx);
+    if (p.pk0) onb_dfree(c, p.pk0); if (p.pk1) onb_dfree(c, p.pk1); if (p.pk2) onb_dfree(c, p.pk2);
     p = DParts();
 }
 static inline uint32_t host_log2(uint32_t x) { return x == 0 ? 0 : 31 - __builtin_clz(x); }
 
 int onb_alloc_tree(onb_context* c, DTree& t, uint32_t n, int block) {
-    onb_free_tree(t);
+    onb_free_tree(c, t);
     const uint32_t numLeaf = 1 + (n - 1) / block;                                         // Tree.hpp:83-87
     t.levels = 1 + host_log2(2 * numLeaf - 1);
     t.numnodes = 1 << t.levels;
     const size_t fb = (size_t)t.numnodes * sizeof(float), ub = (size_t)t.numnodes * sizeof(uint32_t);
     for (int d = 0; d < c->PD; ++d) {
-        ONB_CUDA(cudaMalloc(&t.x[d], fb)); ONB_CUDA(cudaMalloc(&t.nc[d], fb)); ONB_CUDA(cudaMalloc(&t.ns[d], fb));
+        ONB_CUDA(onb_dmalloc(c, (void**)&t.x[d], fb)); ONB_CUDA(onb_dmalloc(c, (void**)&t.nc[d], fb)); ONB_CUDA(onb_dmalloc(c, (void**)&t.ns[d], fb));
         ONB_CUDA(cudaMemsetAsync(t.x[d], 0, fb, c->stream)); ONB_CUDA(cudaMemsetAsync(t.nc[d], 0, fb, c->stream)); ONB_CUDA(cudaMemsetAsync(t.ns[d], 0, fb, c->stream));
     }
-    ONB_CUDA(cudaMalloc(&t.nr, fb)); ONB_CUDA(cudaMalloc(&t.pr, fb));
+    ONB_CUDA(onb_dmalloc(c, (void**)&t.nr, fb)); ONB_CUDA(onb_dmalloc(c, (void**)&t.pr, fb));
     ONB_CUDA(cudaMemsetAsync(t.nr, 0, fb, c->stream)); ONB_CUDA(cudaMemsetAsync(t.pr, 0, fb, c->stream));
-    for (int d = 0; d < c->SD; ++d) { ONB_CUDA(cudaMalloc(&t.s[d], fb)); ONB_CUDA(cudaMemsetAsync(t.s[d], 0, fb, c->stream)); }
-    ONB_CUDA(cudaMalloc(&t.ioffset, ub)); ONB_CUDA(cudaMalloc(&t.num, ub));
+    for (int d = 0; d < c->SD; ++d) { ONB_CUDA(onb_dmalloc(c, (void**)&t.s[d], fb)); ONB_CUDA(cudaMemsetAsync(t.s[d], 0, fb, c->stream)); }
+    ONB_CUDA(onb_dmalloc(c, (void**)&t.ioffset, ub)); ONB_CUDA(onb_dmalloc(c, (void**)&t.num, ub));
     ONB_CUDA(cudaMemsetAsync(t.ioffset, 0, ub, c->stream)); ONB_CUDA(cudaMemsetAsync(t.num, 0, ub, c->stream));
     return ONB_OK;
 }
-void onb_free_tree(DTree& t) {
-    for (int d = 0; d < ONB_MAX_PD; ++d) { if (t.x[d]) cudaFree(t.x[d]); if (t.nc[d]) cudaFree(t.nc[d]); if (t.ns[d]) cudaFree(t.ns[d]); }
-    if (t.nr) cudaFree(t.nr); if (t.pr) cudaFree(t.pr);
-    for (int d = 0; d < ONB_MAX_SD; ++d) if (t.s[d]) cudaFree(t.s[d]);
-    if (t.ioffset) cudaFree(t.ioffset); if (t.num) cudaFree(t.num);
+void onb_free_tree(onb_context* c, DTree& t) {
+    for (int d = 0; d < ONB_MAX_PD; ++d) { if (t.x[d]) onb_dfree(c, t.x[d]); if (t.nc[d]) onb_dfree(c, t.nc[d]); if (t.ns[d]) onb_dfree(c, t.ns[d]); }
+    if (t.nr) onb_dfree(c, t.nr); if (t.pr) onb_dfree(c, t.pr);
+    for (int d = 0; d < ONB_MAX_SD; ++d) if (t.s[d]) onb_dfree(c, t.s[d]);
+    if (t.ioffset) onb_dfree(c, t.ioffset); if (t.num) onb_dfree(c, t.num);
     t = DTree();
 }
 int onb_check_flag(onb_context* c, const char* what) {
@@ -112,6 +112,7 @@ onb_context* onb_create(int physics, int device) {
         g_create_error = "context allocation failed"; delete c; return nullptr;
     }
     cudaMemset(c->d_flag, 0, sizeof(int));
+    { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); } }
     onb_set_params(c, 128, 4, ONB_ARITH_FAST);
     return c;
 }
@@ -119,8 +120,9 @@ onb_context* onb_create(int physics, int device) {
 void onb_destroy(onb_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (int i = 0; i < 4; ++i) onb_free_parts(c->parts[i]);
-    for (int i = 0; i < 2; ++i) onb_free_tree(c->trees[i]);
+    for (int i = 0; i < 4; ++i) onb_free_parts(c, c->parts[i]);
+    for (int i = 0; i < 2; ++i) onb_free_tree(c, c->trees[i]);
+    cudaStreamSynchronize(c->stream);
     if (c->d_flag) cudaFree(c->d_flag);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -156,12 +158,12 @@ static int set_parts(onb_context* c, int which, uint64_t n, const float* x, cons
     if (n == 0 || n >= 0xfffff000ull) { c->err = "particle count out of range for one GPU"; return ONB_ERR_ARG; }
     ONB_CUDA(cudaSetDevice(c->device));
     DParts& p = c->parts[which];
-    if (p.n != n) { onb_free_parts(p); int rc = onb_alloc_parts(c, p, (uint32_t)n, which == 0); if (rc) return rc; }
-    if (p.gidx) { cudaFree(p.gidx); p.gidx = nullptr; }
+    if (p.n != n) { onb_free_parts(c, p); int rc = onb_alloc_parts(c, p, (uint32_t)n, which == 0); if (rc) return rc; }
+    if (p.gidx) { onb_dfree(c, p.gidx); p.gidx = nullptr; }
     const size_t bytes = (size_t)n * sizeof(float);
-    for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(p.x[d], x + (size_t)d * n, bytes, cudaMemcpyHostToDevice, c->stream));
-    ONB_CUDA(cudaMemcpyAsync(p.r, r, bytes, cudaMemcpyHostToDevice, c->stream));
-    if (which == 0) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(p.s[d], s + (size_t)d * n, bytes, cudaMemcpyHostToDevice, c->stream));
+    for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(p.x[d], x + (size_t)d * n, bytes, cudaMemcpyDefault, c->stream));
+    ONB_CUDA(cudaMemcpyAsync(p.r, r, bytes, cudaMemcpyDefault, c->stream));
+    if (which == 0) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(p.s[d], s + (size_t)d * n, bytes, cudaMemcpyDefault, c->stream));
     ONB_CUDA(cudaStreamSynchronize(c->stream));
     p.packed_valid = false;
     c->trees[which].built = false;
@@ -248,7 +250,7 @@ int onb_treecode3(onb_context* c, float theta, float* flops) {
     WorkList wl;
     { PhaseTimer tl(c, "lists"); rc = onb_lists_boxwise(c, theta, wl); tl.stop(); }
     if (rc == ONB_OK) { PhaseTimer tp(c, "p2p"); rc = onb_p2p_lists(c, wl, 1, 1, true); tp.stop(); }
-    onb_free_worklist(wl);
+    onb_free_worklist(c, wl);
     te.stop();
     if (flops) *flops = (float)c->flops_per_pair * (float)c->block *
                         ((float)c->stats[0] * (float)c->block + (float)c->stats[1] * (float)c->num_eqps);        // :335-336
@@ -293,10 +295,10 @@ int onb_get_parts(onb_context* c, int which, float* x, float* r, float* s, float
     DParts& p = c->parts[which];
     const size_t n = p.n, bytes = n * sizeof(float);
     if (n == 0) return ONB_OK;
-    if (x) for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(x + d * n, p.x[d], bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (x) for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(x + d * n, p.x[d], bytes, cudaMemcpyDefault, c->stream));
     if (r) ONB_CUDA(cudaMemcpyAsync(r, p.r, bytes, cudaMemcpyDeviceToHost, c->stream));
     if (s && p.are_sources) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(s + d * n, p.s[d], bytes, cudaMemcpyDeviceToHost, c->stream));
-    if (u && !p.are_sources) for (int d = 0; d < c->OD; ++d) ONB_CUDA(cudaMemcpyAsync(u + d * n, p.u[d], bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (u && !p.are_sources) for (int d = 0; d < c->OD; ++d) ONB_CUDA(cudaMemcpyAsync(u + d * n, p.u[d], bytes, cudaMemcpyDefault, c->stream));
     ONB_CUDA(cudaStreamSynchronize(c->stream));
     if (gidx && p.gidx) {
         std::vector<uint32_t> tmp(n);
@@ -312,6 +314,7 @@ int onb_add_results_original_order(onb_context* c, float* u) {
     const size_t n = p.n;
     if (!p.gidx) { c->err = "targets have no tree order yet"; return ONB_ERR_ARG; }
     std::vector<uint32_t> g(n); std::vector<float> tmp(n);
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
     ONB_CUDA(cudaMemcpy(g.data(), p.gidx, n * 4, cudaMemcpyDeviceToHost));
     for (int d = 0; d < c->OD; ++d) {
         ONB_CUDA(cudaMemcpy(tmp.data(), p.u[d], n * 4, cudaMemcpyDeviceToHost));
@@ -363,6 +366,21 @@ double onb_phase_ms(const onb_context* c, const char* name) {
     return it == c->phase_ms.end() ? -1.0 : it->second;
 }
 uint64_t onb_last_pairs(const onb_context* c) { return c->last_pairs; }
+
+// step timer: two CUDA events on the context's stream bracket everything issued in between (host gaps included)
+int onb_timer_start(onb_context* c) {
+    ONB_CUDA(cudaSetDevice(c->device));
+    if (!c->ev_t0) { ONB_CUDA(cudaEventCreate(&c->ev_t0)); ONB_CUDA(cudaEventCreate(&c->ev_t1)); }
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    ONB_CUDA(cudaEventRecord(c->ev_t0, c->stream));
+    return ONB_OK;
+}
+double onb_timer_stop_ms(onb_context* c) {
+    if (!c->ev_t0) return -1.0;
+    if (cudaEventRecord(c->ev_t1, c->stream) != cudaSuccess || cudaEventSynchronize(c->ev_t1) != cudaSuccess) return -1.0;
+    float ms = 0.f; cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
+    return ms;
+}
 uint64_t onb_launch_count(const onb_context* c) { return c->launches; }
 
 void* onb_device_ptr(onb_context* c, int which, int field) {
@@ -382,6 +400,7 @@ int onb_load_tree(onb_context* c, int which, int levels, const float* x, const f
     int rc = onb_alloc_tree(c, t, c->parts[which].n, c->block);
     if (rc) return rc;
     if (t.levels != levels) { c->err = "load_tree: level count does not match Tree.hpp sizing"; return ONB_ERR_ARG; }
+    ONB_CUDA(cudaStreamSynchronize(c->stream));     // the allocation's zero-fills are stream ordered; the copies below are not
     const size_t n = t.numnodes, fb = n * sizeof(float);
     for (int d = 0; d < c->PD; ++d) {
         ONB_CUDA(cudaMemcpy(t.x[d], x + d * n, fb, cudaMemcpyHostToDevice));
@@ -397,7 +416,7 @@ int onb_load_tree(onb_context* c, int which, int levels, const float* x, const f
     ONB_CUDA(cudaMemcpy(t.num, nm.data(), n * 4, cudaMemcpyHostToDevice));
     if (which == 1) {   // targets loaded in tree order: original index = position
         DParts& p = c->parts[1];
-        if (!p.gidx) ONB_CUDA(cudaMalloc(&p.gidx, (size_t)p.n * 4));
+        if (!p.gidx) ONB_CUDA(onb_dmalloc(c, (void**)&p.gidx, (size_t)p.n * 4));
         std::vector<uint32_t> id(p.n); for (uint32_t i = 0; i < p.n; ++i) id[i] = i;
         ONB_CUDA(cudaMemcpy(p.gidx, id.data(), (size_t)p.n * 4, cudaMemcpyHostToDevice));
     }

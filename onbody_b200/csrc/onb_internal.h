@@ -97,6 +97,7 @@ struct onb_context {
     // error flag written by kernels (capacity overflow etc.)
     int* d_flag = nullptr;
     int* h_flag = nullptr;   // pinned
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
 };
 
 #define ONB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
@@ -104,6 +105,11 @@ struct onb_context {
     return ONB_ERR_CUDA; } } while (0)
 
 #define ONB_LAUNCH(c) ((c)->launches++)
+
+// all device memory comes from the device's stream-ordered pool (release threshold raised at context creation), so
+// the per-phase scratch of a repeated evaluation is recycled without touching the driver allocator
+static inline cudaError_t onb_dmalloc(onb_context* c, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 4, c->stream); }
+static inline void onb_dfree(onb_context* c, void* p) { if (p) cudaFreeAsync(p, c->stream); }
 
 static inline PartsView view_of(const DParts& p) {
     PartsView v; v.n = p.n;
@@ -142,9 +148,9 @@ struct PhaseTimer {
 // ---- implemented in the .cu files -------------------------------------------------------------
 // memory
 int onb_alloc_parts(onb_context* c, DParts& p, uint32_t n, bool are_sources);
-void onb_free_parts(DParts& p);
+void onb_free_parts(onb_context* c, DParts& p);
 int onb_alloc_tree(onb_context* c, DTree& t, uint32_t n, int block);
-void onb_free_tree(DTree& t);
+void onb_free_tree(onb_context* c, DTree& t);
 int onb_check_flag(onb_context* c, const char* what);
 void onb_shard_range(const onb_context* c, uint32_t* lo, uint32_t* hi);   // particle index range of this context's target shard
 // tree.cu
@@ -168,7 +174,7 @@ struct WorkList {
     uint64_t nentries = 0;
 };
 int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tgt_which_box, bool accumulate);
-void onb_free_worklist(WorkList& wl);
+void onb_free_worklist(onb_context* c, WorkList& wl);
 // traverse.cu
 int onb_lists_boxwise(onb_context* c, float theta, WorkList& wl);
 int onb_run_treecode2(onb_context* c, float theta, int variant);   // fused pointwise traversal + pair kernels (variant 1 = treecode1)

@@ -359,10 +359,10 @@ int onb_p2p_direct(onb_context* c, uint64_t tskip) {
     return ONB_OK;
 }
 
-void onb_free_worklist(WorkList& wl) {
-    if (wl.tgt_node) cudaFree(wl.tgt_node);
-    if (wl.start) cudaFree(wl.start);
-    if (wl.entries) cudaFree(wl.entries);
+void onb_free_worklist(onb_context* c, WorkList& wl) {
+    if (wl.tgt_node) onb_dfree(c, wl.tgt_node);
+    if (wl.start) onb_dfree(c, wl.start);
+    if (wl.entries) onb_dfree(c, wl.entries);
     wl = WorkList();
 }
 
@@ -370,7 +370,7 @@ extern "C" double onb_measure_fp32_peak(onb_context* c) {
     if (!c) return -1.0;
     const int blocks = c->sm_count * 8, threads = 256, iters = 2000;
     float* d = nullptr;
-    if (cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return -1.0;
+    if (onb_dmalloc(c, (void**)&d, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return -1.0;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
@@ -384,6 +384,6 @@ extern "C" double onb_measure_fp32_peak(onb_context* c) {
         const double tf = flop / (ms * 1e-3) * 1e-12;
         if (rep > 0 && tf > best) best = tf;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); onb_dfree(c, d);
     return best;
 }

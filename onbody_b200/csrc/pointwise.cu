@@ -160,7 +160,7 @@ int onb_run_treecode2(onb_context* c, float theta, int variant) {
     if (!srcs.packed_valid) { int rc = onb_pack_sources(c, srcs); if (rc) return rc; }
     if (variant == 2 && !eqs.packed_valid) { int rc = onb_pack_sources(c, eqs); if (rc) return rc; }
     unsigned long long* d_stats = nullptr;
-    ONB_CUDA(cudaMalloc(&d_stats, 10 * sizeof(unsigned long long)));
+    ONB_CUDA(onb_dmalloc(c, (void**)&d_stats, 10 * sizeof(unsigned long long)));
     ONB_CUDA(cudaMemsetAsync(d_stats, 0, 10 * sizeof(unsigned long long), c->stream));
     PwArgs a;
     for (int d = 0; d < 3; ++d) a.tx[d] = t.x[d];
@@ -196,6 +196,6 @@ int onb_run_treecode2(onb_context* c, float theta, int variant) {
     ONB_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < 9; ++i) c->stats[i] = h[i];
     c->last_pairs = h[9];
-    cudaFree(d_stats);
+    onb_dfree(c, d_stats);
     return ONB_OK;
 }

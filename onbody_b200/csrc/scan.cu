@@ -46,12 +46,12 @@ int onb_exclusive_scan_u32(onb_context* c, const uint32_t* in, uint32_t* out, ui
     (void)d_total;
     const uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t* sums = nullptr;
-    if (ntiles > 1) ONB_CUDA(cudaMalloc(&sums, (size_t)ntiles * 4));
+    if (ntiles > 1) ONB_CUDA(onb_dmalloc(c, (void**)&sums, (size_t)ntiles * 4));
     k_scan_tiles<<<ntiles, SCAN_T, 0, c->stream>>>(in, out, sums, n); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
     if (ntiles > 1) {
         int rc = onb_exclusive_scan_u32(c, sums, sums, ntiles, nullptr);
-        if (rc) { cudaFree(sums); return rc; }
+        if (rc) { onb_dfree(c, sums); return rc; }
         k_scan_add<<<(n + 255) / 256, 256, 0, c->stream>>>(out, sums, n); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
     }
@@ -61,6 +61,6 @@ int onb_exclusive_scan_u32(onb_context* c, const uint32_t* in, uint32_t* out, ui
         ONB_CUDA(cudaStreamSynchronize(c->stream));
         *total = (uint64_t)last_out + (uint64_t)last_in;
     }
-    if (sums) { ONB_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(sums); }
+    if (sums) { ONB_CUDA(cudaStreamSynchronize(c->stream)); onb_dfree(c, sums); }
     return ONB_OK;
 }

@@ -226,19 +226,19 @@ int onb_lists_boxwise(onb_context* c, float theta, WorkList& wl) {
     DTree& st = c->trees[0]; DTree& tt = c->trees[1];
     const uint32_t nleaf_all = (c->parts[1].n + c->block - 1) / c->block;
     uint32_t* leaf_all = nullptr;
-    ONB_CUDA(cudaMalloc(&leaf_all, (size_t)nleaf_all * 4));
+    ONB_CUDA(onb_dmalloc(c, (void**)&leaf_all, (size_t)nleaf_all * 4));
     k_leaf_table<<<(tt.numnodes + 255) / 256, 256, 0, c->stream>>>(view_of(tt), c->block, leaf_all); ONB_LAUNCH(c);
     uint32_t lo, hi; onb_shard_range(c, &lo, &hi);
     const uint32_t l0 = lo / c->block, l1 = (hi + c->block - 1) / c->block;
     const uint32_t nl = l1 - l0;
     unsigned long long* d_stats = nullptr;
-    ONB_CUDA(cudaMalloc(&d_stats, 10 * sizeof(unsigned long long)));
+    ONB_CUDA(onb_dmalloc(c, (void**)&d_stats, 10 * sizeof(unsigned long long)));
     ONB_CUDA(cudaMemsetAsync(d_stats, 0, 10 * sizeof(unsigned long long), c->stream));
     wl = WorkList(); wl.nitems = nl;
-    if (nl == 0) { cudaFree(leaf_all); cudaFree(d_stats); memset(c->stats, 0, sizeof(c->stats)); c->last_pairs = 0; return ONB_OK; }
-    ONB_CUDA(cudaMalloc(&wl.tgt_node, (size_t)nl * 4));
+    if (nl == 0) { onb_dfree(c, leaf_all); onb_dfree(c, d_stats); memset(c->stats, 0, sizeof(c->stats)); c->last_pairs = 0; return ONB_OK; }
+    ONB_CUDA(onb_dmalloc(c, (void**)&wl.tgt_node, (size_t)nl * 4));
     ONB_CUDA(cudaMemcpyAsync(wl.tgt_node, leaf_all + l0, (size_t)nl * 4, cudaMemcpyDeviceToDevice, c->stream));
-    ONB_CUDA(cudaMalloc(&wl.start, (size_t)(nl + 1) * 4));
+    ONB_CUDA(onb_dmalloc(c, (void**)&wl.start, (size_t)(nl + 1) * 4));
     BoxArgs a; a.st = view_of(st); a.tt = view_of(tt); a.leaf_nodes = wl.tgt_node; a.nleaves = nl;
     a.counts = wl.start; a.start = wl.start; a.entries = nullptr; a.stats = d_stats;
     a.block = c->block; a.num_eqps = c->num_eqps; a.PD = c->PD; a.theta = theta;
@@ -251,12 +251,12 @@ int onb_lists_boxwise(onb_context* c, float theta, WorkList& wl) {
     if (rc) return rc;
     if (total >= 0xffffffffull) { c->err = "boxwise: interaction list exceeds 2^32 entries on one GPU"; return ONB_ERR_CAPACITY; }
     wl.nentries = total;
-    ONB_CUDA(cudaMalloc(&wl.entries, std::max<size_t>(4, (size_t)total * 4)));
+    ONB_CUDA(onb_dmalloc(c, (void**)&wl.entries, std::max<size_t>(4, (size_t)total * 4)));
     a.entries = wl.entries;
     k_boxwise<true><<<(nl + TB - 1) / TB, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
     rc = fetch_stats(c, d_stats);
-    cudaFree(d_stats); cudaFree(leaf_all);
+    onb_dfree(c, d_stats); onb_dfree(c, leaf_all);
     return rc;
 }
 
@@ -264,13 +264,13 @@ int onb_run_fastsumm(onb_context* c, float theta) {
     DTree& st = c->trees[0]; DTree& tt = c->trees[1];
     uint32_t lo, hi; onb_shard_range(c, &lo, &hi);
     unsigned long long* d_stats = nullptr;
-    ONB_CUDA(cudaMalloc(&d_stats, 10 * sizeof(unsigned long long)));
+    ONB_CUDA(onb_dmalloc(c, (void**)&d_stats, 10 * sizeof(unsigned long long)));
     ONB_CUDA(cudaMemsetAsync(d_stats, 0, 10 * sizeof(unsigned long long), c->stream));
     const int TB = 256, WPB = TB / 32;
     const uint32_t max_blocks = (uint32_t)c->sm_count * 8u;
     const uint32_t qcap = 8192;
     uint32_t* queue = nullptr;
-    ONB_CUDA(cudaMalloc(&queue, (size_t)max_blocks * WPB * 2 * qcap * 4));
+    ONB_CUDA(onb_dmalloc(c, (void**)&queue, (size_t)max_blocks * WPB * 2 * qcap * 4));
 
     uint32_t *pc_start = nullptr, *pc_entries = nullptr;     // previous level's deferred lists
     double ms_lists = 0.0, ms_p2p = 0.0, ms_down = 0.0;
@@ -280,7 +280,7 @@ int onb_run_fastsumm(onb_context* c, float theta) {
         const uint32_t nn = 1u << lev;
         cudaEventRecord(ev[0], c->stream);
         uint32_t *istart = nullptr, *cstart = nullptr, *ientries = nullptr, *centries = nullptr;
-        ONB_CUDA(cudaMalloc(&istart, (size_t)(nn + 1) * 4)); ONB_CUDA(cudaMalloc(&cstart, (size_t)(nn + 1) * 4));
+        ONB_CUDA(onb_dmalloc(c, (void**)&istart, (size_t)(nn + 1) * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&cstart, (size_t)(nn + 1) * 4));
         DttArgs a; a.st = view_of(st); a.tt = view_of(tt); a.level = lev; a.nnodes = nn;
         a.pc_start = pc_start; a.pc_entries = pc_entries;
         a.icount = istart; a.ccount = cstart; a.istart = istart; a.cstart = cstart; a.ientries = nullptr; a.centries = nullptr;
@@ -295,8 +295,8 @@ int onb_run_fastsumm(onb_context* c, float theta) {
         if ((rc = onb_exclusive_scan_u32(c, cstart, cstart, nn + 1, &ctotal))) break;
         if ((rc = onb_check_flag(c, "dual-tree traversal: per-node source FIFO overflow"))) break;
         if (itotal >= 0xffffffffull || ctotal >= 0xffffffffull) { c->err = "fastsumm: list exceeds 2^32 entries on one GPU"; rc = ONB_ERR_CAPACITY; break; }
-        ONB_CUDA(cudaMalloc(&ientries, std::max<size_t>(4, (size_t)itotal * 4)));
-        ONB_CUDA(cudaMalloc(&centries, std::max<size_t>(4, (size_t)ctotal * 4)));
+        ONB_CUDA(onb_dmalloc(c, (void**)&ientries, std::max<size_t>(4, (size_t)itotal * 4)));
+        ONB_CUDA(onb_dmalloc(c, (void**)&centries, std::max<size_t>(4, (size_t)ctotal * 4)));
         a.ientries = ientries; a.centries = centries;
         k_dtt<true><<<blocks, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
@@ -312,15 +312,15 @@ int onb_run_fastsumm(onb_context* c, float theta) {
         float t01 = 0, t12 = 0, t23 = 0;
         cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
         ms_lists += t01; ms_down += t12; ms_p2p += t23;
-        cudaFree(istart); cudaFree(ientries);
-        if (pc_start) cudaFree(pc_start); if (pc_entries) cudaFree(pc_entries);
+        onb_dfree(c, istart); onb_dfree(c, ientries);
+        if (pc_start) onb_dfree(c, pc_start); if (pc_entries) onb_dfree(c, pc_entries);
         pc_start = cstart; pc_entries = centries;
     }
     for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
-    if (pc_start) cudaFree(pc_start); if (pc_entries) cudaFree(pc_entries);
-    cudaFree(queue);
+    if (pc_start) onb_dfree(c, pc_start); if (pc_entries) onb_dfree(c, pc_entries);
+    onb_dfree(c, queue);
     if (rc == ONB_OK) rc = fetch_stats(c, d_stats);
-    cudaFree(d_stats);
+    onb_dfree(c, d_stats);
     c->phase_ms["lists"] = ms_lists; c->phase_ms["downward"] = ms_down; c->phase_ms["p2p"] = ms_p2p;
     return rc;
 }

@@ -9,7 +9,7 @@
  * box. There is no Morton key and no radix sort in it, and the particle order that comes out (which the parity
  * contract requires bit-for-bit) is the composition of its Hoare partition passes. This file therefore runs the
  * SAME passes, level-synchronously and in closed form (proven equal to the recursive
- * two-pointer loop by oracle/port against the compiled reference):
+ * two-pointer loop by the test suite's CPU restatement against the compiled reference):
  *
  *   pass:  m = #{v < pivot in window}; B = wf + m;
  *          a_1 < a_2 < ...  positions in [wf,B) holding v >= pivot,   b_1 > b_2 > ...  positions in [B,wl] holding v < pivot
@@ -413,6 +413,7 @@ static unsigned long long* g_build_stats_dev = nullptr;   // per-process scratch
 extern "C" int onb_get_build_stats(onb_context* c, uint64_t out[5]) {
     if (!g_build_stats_dev) { for (int i = 0; i < 5; ++i) out[i] = 0; return ONB_OK; }
     unsigned long long h[5];
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
     ONB_CUDA(cudaMemcpy(h, g_build_stats_dev, sizeof(h), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 5; ++i) out[i] = h[i];
     return ONB_OK;
@@ -424,19 +425,19 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
     const uint32_t n = p.n;
     const int PD = c->PD, SD = p.are_sources ? c->SD : 0;
     if (n == 0) { c->err = "make_tree: no particles"; return ONB_ERR_ARG; }
-    if (!g_build_stats_dev) ONB_CUDA(cudaMalloc(&g_build_stats_dev, 5 * sizeof(unsigned long long)));
+    if (!g_build_stats_dev) ONB_CUDA(onb_dmalloc(c, (void**)&g_build_stats_dev, 5 * sizeof(unsigned long long)));
     ONB_CUDA(cudaMemsetAsync(g_build_stats_dev, 0, 4 * sizeof(unsigned long long), c->stream));
 
     // scratch: second copy of every plane (ping-pong), per-particle index planes, per-node split records
     const size_t capf = (size_t)p.cap * sizeof(float);
     float* alt_x[3] = {nullptr, nullptr, nullptr}; float* alt_r = nullptr; float* alt_s[3] = {nullptr, nullptr, nullptr};
     uint32_t *alt_g = nullptr, *cur_g = nullptr, *lidx = nullptr, *scr = nullptr, *owner = nullptr, *pmid = nullptr; uint8_t* axis_of = nullptr;
-    for (int d = 0; d < PD; ++d) ONB_CUDA(cudaMalloc(&alt_x[d], capf));
-    ONB_CUDA(cudaMalloc(&alt_r, capf));
-    for (int d = 0; d < SD; ++d) ONB_CUDA(cudaMalloc(&alt_s[d], capf));
-    ONB_CUDA(cudaMalloc(&alt_g, (size_t)n * 4)); ONB_CUDA(cudaMalloc(&cur_g, (size_t)n * 4));
-    ONB_CUDA(cudaMalloc(&lidx, (size_t)n * 4)); ONB_CUDA(cudaMalloc(&scr, (size_t)n * 4)); ONB_CUDA(cudaMalloc(&owner, (size_t)n * 4));
-    ONB_CUDA(cudaMalloc(&pmid, (size_t)t.numnodes * 4)); ONB_CUDA(cudaMalloc(&axis_of, (size_t)t.numnodes));
+    for (int d = 0; d < PD; ++d) ONB_CUDA(onb_dmalloc(c, (void**)&alt_x[d], capf));
+    ONB_CUDA(onb_dmalloc(c, (void**)&alt_r, capf));
+    for (int d = 0; d < SD; ++d) ONB_CUDA(onb_dmalloc(c, (void**)&alt_s[d], capf));
+    ONB_CUDA(onb_dmalloc(c, (void**)&alt_g, (size_t)n * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&cur_g, (size_t)n * 4));
+    ONB_CUDA(onb_dmalloc(c, (void**)&lidx, (size_t)n * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&scr, (size_t)n * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&owner, (size_t)n * 4));
+    ONB_CUDA(onb_dmalloc(c, (void**)&pmid, (size_t)t.numnodes * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&axis_of, (size_t)t.numnodes));
     for (int d = 0; d < PD; ++d) ONB_CUDA(cudaMemsetAsync(alt_x[d], 0, capf, c->stream));
     ONB_CUDA(cudaMemsetAsync(alt_r, 0, capf, c->stream));
     for (int d = 0; d < SD; ++d) ONB_CUDA(cudaMemsetAsync(alt_s[d], 0, capf, c->stream));
@@ -477,7 +478,7 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
     for (int d = 0; d < PD; ++d) p.x[d] = cx[d];
     p.r = cr;
     for (int d = 0; d < SD; ++d) p.s[d] = cs[d];
-    if (!p.are_sources) { if (p.gidx) cudaFree(p.gidx); p.gidx = cg; cg = nullptr; }
+    if (!p.are_sources) { if (p.gidx) onb_dfree(c, p.gidx); p.gidx = cg; cg = nullptr; }
     p.packed_valid = false;
 
     // finishTree
@@ -490,11 +491,11 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
     }
     ONB_CUDA(cudaGetLastError());
     ONB_CUDA(cudaStreamSynchronize(c->stream));
-    for (int d = 0; d < PD; ++d) cudaFree(ax[d]);
-    cudaFree(ar);
-    for (int d = 0; d < SD; ++d) cudaFree(as[d]);
-    cudaFree(ag); if (cg) cudaFree(cg);
-    cudaFree(lidx); cudaFree(scr); cudaFree(owner); cudaFree(pmid); cudaFree(axis_of);
+    for (int d = 0; d < PD; ++d) onb_dfree(c, ax[d]);
+    onb_dfree(c, ar);
+    for (int d = 0; d < SD; ++d) onb_dfree(c, as[d]);
+    onb_dfree(c, ag); if (cg) onb_dfree(c, cg);
+    onb_dfree(c, lidx); onb_dfree(c, scr); onb_dfree(c, owner); onb_dfree(c, pmid); onb_dfree(c, axis_of);
     t.built = true;
     return ONB_OK;
 }
@@ -502,7 +503,7 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
 int onb_tree_refine(onb_context* c, DParts& p, DTree& t) {
     if (!t.built) { c->err = "refine: tree not built"; return ONB_ERR_ARG; }
     if (c->block > 128) { c->err = "refine: block size > 128 not supported by the GPU build"; return ONB_ERR_UNSUPPORTED; }
-    if (!g_build_stats_dev) ONB_CUDA(cudaMalloc(&g_build_stats_dev, 5 * sizeof(unsigned long long)));
+    if (!g_build_stats_dev) ONB_CUDA(onb_dmalloc(c, (void**)&g_build_stats_dev, 5 * sizeof(unsigned long long)));
     ONB_CUDA(cudaMemsetAsync(g_build_stats_dev + 4, 0, sizeof(unsigned long long), c->stream));
     RefineArgs ra; ra.p = view_of(p); ra.n = p.n; ra.block = c->block; ra.PD = c->PD; ra.SD = c->SD; ra.OD = c->OD;
     ra.are_sources = p.are_sources ? 1 : 0; ra.flag = c->d_flag; ra.tie_sorts = g_build_stats_dev + 4;
