@@ -20,53 +20,88 @@ int onb_alloc_parts(onb_context* c, DParts& p, uint32_t n, bool are_sources) {
     p = DParts();
     p.n = n; p.cap = ((n + 63u) & ~31u) + 32u; p.PD = c->PD; p.SD = c->SD; p.OD = c->OD; p.are_sources = are_sources;
     const size_t bytes = (size_t)p.cap * sizeof(float);
-    for (int d = 0; d < c->PD; ++d) { ONB_CUDA(onb_dmalloc(c, (void**)&p.x[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.x[d], 0, bytes, c->stream)); }
-    ONB_CUDA(onb_dmalloc(c, (void**)&p.r, bytes)); ONB_CUDA(cudaMemsetAsync(p.r, 0, bytes, c->stream));
+    for (int d = 0; d < c->PD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.x[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.x[d], 0, bytes, c->stream)); }
+    ONB_CUDA(onb_pmalloc(c, (void**)&p.r, bytes)); ONB_CUDA(cudaMemsetAsync(p.r, 0, bytes, c->stream));
     if (are_sources) {
-        for (int d = 0; d < c->SD; ++d) { ONB_CUDA(onb_dmalloc(c, (void**)&p.s[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.s[d], 0, bytes, c->stream)); }
-        ONB_CUDA(onb_dmalloc(c, (void**)&p.pk0, (size_t)p.cap * sizeof(float4)));
+        for (int d = 0; d < c->SD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.s[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.s[d], 0, bytes, c->stream)); }
+        ONB_CUDA(onb_pmalloc(c, (void**)&p.pk0, (size_t)p.cap * sizeof(float4)));
         const bool nf2 = c->physics == ONB_VORT3D || c->physics == ONB_VORTGRAD3D;
-        if (nf2) ONB_CUDA(onb_dmalloc(c, (void**)&p.pk1, (size_t)p.cap * sizeof(float4)));
-        if (c->physics == ONB_GRAV3D) ONB_CUDA(onb_dmalloc(c, (void**)&p.pk2, bytes));
+        if (nf2) ONB_CUDA(onb_pmalloc(c, (void**)&p.pk1, (size_t)p.cap * sizeof(float4)));
+        if (c->physics == ONB_GRAV3D) ONB_CUDA(onb_pmalloc(c, (void**)&p.pk2, bytes));
     } else {
-        for (int d = 0; d < c->OD; ++d) { ONB_CUDA(onb_dmalloc(c, (void**)&p.u[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.u[d], 0, bytes, c->stream)); }
+        for (int d = 0; d < c->OD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.u[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.u[d], 0, bytes, c->stream)); }
     }
     return ONB_OK;
 }
 void onb_free_parts(onb_context* c, DParts& p) {
-    for (int d = 0; d < ONB_MAX_PD; ++d) if (p.x[d]) onb_dfree(c, p.x[d]);
-    if (p.r) onb_dfree(c, p.r);
-    for (int d = 0; d < ONB_MAX_SD; ++d) if (p.s[d]) onb_dfree(c, p.s[d]);
-    for (int d = 0; d < ONB_MAX_OD; ++d) if (p.u[d]) onb_dfree(c, p.u[d]);
-    if (p.gidx) onb_dfree(c, p.gidx);
-    if (p.pk0) onb_dfree(c, p.pk0); if (p.pk1) onb_dfree(c, p.pk1); if (p.pk2) onb_dfree(c, p.pk2);
+    for (int d = 0; d < ONB_MAX_PD; ++d) if (p.x[d]) onb_pfree(c, p.x[d]);
+    if (p.r) onb_pfree(c, p.r);
+    for (int d = 0; d < ONB_MAX_SD; ++d) if (p.s[d]) onb_pfree(c, p.s[d]);
+    for (int d = 0; d < ONB_MAX_OD; ++d) if (p.u[d]) onb_pfree(c, p.u[d]);
+    if (p.gidx) onb_pfree(c, p.gidx);
+    if (p.pk0) onb_pfree(c, p.pk0); if (p.pk1) onb_pfree(c, p.pk1); if (p.pk2) onb_pfree(c, p.pk2);
     p = DParts();
 }
 static inline uint32_t host_log2(uint32_t x) { return x == 0 ? 0 : 31 - __builtin_clz(x); }
 
 int onb_alloc_tree(onb_context* c, DTree& t, uint32_t n, int block) {
-    onb_free_tree(c, t);
     const uint32_t numLeaf = 1 + (n - 1) / block;                                         // Tree.hpp:83-87
-    t.levels = 1 + host_log2(2 * numLeaf - 1);
+    const int levels = 1 + host_log2(2 * numLeaf - 1);
+    if (t.numnodes == (1 << levels) && t.nr) {          // same shape as last time: reuse the arrays, just clear them
+        const size_t fb0 = (size_t)t.numnodes * sizeof(float);
+        for (int d = 0; d < c->PD; ++d) { ONB_CUDA(cudaMemsetAsync(t.x[d], 0, fb0, c->stream)); ONB_CUDA(cudaMemsetAsync(t.nc[d], 0, fb0, c->stream)); ONB_CUDA(cudaMemsetAsync(t.ns[d], 0, fb0, c->stream)); }
+        ONB_CUDA(cudaMemsetAsync(t.nr, 0, fb0, c->stream)); ONB_CUDA(cudaMemsetAsync(t.pr, 0, fb0, c->stream));
+        for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemsetAsync(t.s[d], 0, fb0, c->stream));
+        ONB_CUDA(cudaMemsetAsync(t.ioffset, 0, fb0, c->stream)); ONB_CUDA(cudaMemsetAsync(t.num, 0, fb0, c->stream));
+        t.built = false;
+        return ONB_OK;
+    }
+    onb_free_tree(c, t);
+    t.levels = levels;
     t.numnodes = 1 << t.levels;
     const size_t fb = (size_t)t.numnodes * sizeof(float), ub = (size_t)t.numnodes * sizeof(uint32_t);
     for (int d = 0; d < c->PD; ++d) {
-        ONB_CUDA(onb_dmalloc(c, (void**)&t.x[d], fb)); ONB_CUDA(onb_dmalloc(c, (void**)&t.nc[d], fb)); ONB_CUDA(onb_dmalloc(c, (void**)&t.ns[d], fb));
+        ONB_CUDA(onb_pmalloc(c, (void**)&t.x[d], fb)); ONB_CUDA(onb_pmalloc(c, (void**)&t.nc[d], fb)); ONB_CUDA(onb_pmalloc(c, (void**)&t.ns[d], fb));
         ONB_CUDA(cudaMemsetAsync(t.x[d], 0, fb, c->stream)); ONB_CUDA(cudaMemsetAsync(t.nc[d], 0, fb, c->stream)); ONB_CUDA(cudaMemsetAsync(t.ns[d], 0, fb, c->stream));
     }
-    ONB_CUDA(onb_dmalloc(c, (void**)&t.nr, fb)); ONB_CUDA(onb_dmalloc(c, (void**)&t.pr, fb));
+    ONB_CUDA(onb_pmalloc(c, (void**)&t.nr, fb)); ONB_CUDA(onb_pmalloc(c, (void**)&t.pr, fb));
     ONB_CUDA(cudaMemsetAsync(t.nr, 0, fb, c->stream)); ONB_CUDA(cudaMemsetAsync(t.pr, 0, fb, c->stream));
-    for (int d = 0; d < c->SD; ++d) { ONB_CUDA(onb_dmalloc(c, (void**)&t.s[d], fb)); ONB_CUDA(cudaMemsetAsync(t.s[d], 0, fb, c->stream)); }
-    ONB_CUDA(onb_dmalloc(c, (void**)&t.ioffset, ub)); ONB_CUDA(onb_dmalloc(c, (void**)&t.num, ub));
+    for (int d = 0; d < c->SD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&t.s[d], fb)); ONB_CUDA(cudaMemsetAsync(t.s[d], 0, fb, c->stream)); }
+    ONB_CUDA(onb_pmalloc(c, (void**)&t.ioffset, ub)); ONB_CUDA(onb_pmalloc(c, (void**)&t.num, ub));
     ONB_CUDA(cudaMemsetAsync(t.ioffset, 0, ub, c->stream)); ONB_CUDA(cudaMemsetAsync(t.num, 0, ub, c->stream));
     return ONB_OK;
 }
 void onb_free_tree(onb_context* c, DTree& t) {
-    for (int d = 0; d < ONB_MAX_PD; ++d) { if (t.x[d]) onb_dfree(c, t.x[d]); if (t.nc[d]) onb_dfree(c, t.nc[d]); if (t.ns[d]) onb_dfree(c, t.ns[d]); }
-    if (t.nr) onb_dfree(c, t.nr); if (t.pr) onb_dfree(c, t.pr);
-    for (int d = 0; d < ONB_MAX_SD; ++d) if (t.s[d]) onb_dfree(c, t.s[d]);
-    if (t.ioffset) onb_dfree(c, t.ioffset); if (t.num) onb_dfree(c, t.num);
+    for (int d = 0; d < ONB_MAX_PD; ++d) { if (t.x[d]) onb_pfree(c, t.x[d]); if (t.nc[d]) onb_pfree(c, t.nc[d]); if (t.ns[d]) onb_pfree(c, t.ns[d]); }
+    if (t.nr) onb_pfree(c, t.nr); if (t.pr) onb_pfree(c, t.pr);
+    for (int d = 0; d < ONB_MAX_SD; ++d) if (t.s[d]) onb_pfree(c, t.s[d]);
+    if (t.ioffset) onb_pfree(c, t.ioffset); if (t.num) onb_pfree(c, t.num);
     t = DTree();
+}
+cudaError_t onb_dmalloc(onb_context* c, void** p, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 4) + 255) & ~(size_t)255;
+    while (c->slab_cur < c->slabs.size()) {
+        onb_context::Slab& s = c->slabs[c->slab_cur];
+        if (c->slab_off + bytes <= s.cap) { *p = s.p + c->slab_off; c->slab_off += bytes; return cudaSuccess; }
+        ++c->slab_cur; c->slab_off = 0;
+    }
+    onb_context::Slab s; s.cap = std::max<size_t>(bytes, (size_t)64 << 20); s.p = nullptr;
+    cudaError_t e = cudaMalloc((void**)&s.p, s.cap);
+    if (e != cudaSuccess) return e;
+    c->slabs.push_back(s); c->slab_cur = c->slabs.size() - 1; c->slab_off = bytes;
+    *p = s.p;
+    return cudaSuccess;
+}
+void onb_scratch_reset(onb_context* c) {
+    if (c->slabs.size() > 1) {          // coalesce what the last call needed into one slab
+        cudaStreamSynchronize(c->stream);
+        size_t total = 0;
+        for (auto& s : c->slabs) { total += s.cap; cudaFree(s.p); }
+        c->slabs.clear();
+        onb_context::Slab s; s.cap = total; s.p = nullptr;
+        if (cudaMalloc((void**)&s.p, s.cap) == cudaSuccess) c->slabs.push_back(s);
+    }
+    c->slab_cur = 0; c->slab_off = 0;
 }
 int onb_check_flag(onb_context* c, const char* what) {
     ONB_CUDA(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -112,7 +147,7 @@ onb_context* onb_create(int physics, int device) {
         g_create_error = "context allocation failed"; delete c; return nullptr;
     }
     cudaMemset(c->d_flag, 0, sizeof(int));
-    { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); } }
+    cudaMalloc(&c->d_build_stats, 8 * sizeof(unsigned long long)); cudaMemset(c->d_build_stats, 0, 8 * sizeof(unsigned long long));
     onb_set_params(c, 128, 4, ONB_ARITH_FAST);
     return c;
 }
@@ -124,6 +159,8 @@ void onb_destroy(onb_context* c) {
     for (int i = 0; i < 2; ++i) onb_free_tree(c, c->trees[i]);
     cudaStreamSynchronize(c->stream);
     if (c->d_flag) cudaFree(c->d_flag);
+    if (c->d_build_stats) cudaFree(c->d_build_stats);
+    for (auto& sl : c->slabs) cudaFree(sl.p);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -159,7 +196,7 @@ static int set_parts(onb_context* c, int which, uint64_t n, const float* x, cons
     ONB_CUDA(cudaSetDevice(c->device));
     DParts& p = c->parts[which];
     if (p.n != n) { onb_free_parts(c, p); int rc = onb_alloc_parts(c, p, (uint32_t)n, which == 0); if (rc) return rc; }
-    if (p.gidx) { onb_dfree(c, p.gidx); p.gidx = nullptr; }
+    if (p.gidx) { onb_pfree(c, p.gidx); p.gidx = nullptr; }
     const size_t bytes = (size_t)n * sizeof(float);
     for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(p.x[d], x + (size_t)d * n, bytes, cudaMemcpyDefault, c->stream));
     ONB_CUDA(cudaMemcpyAsync(p.r, r, bytes, cudaMemcpyDefault, c->stream));
@@ -194,6 +231,7 @@ int onb_driver_inputs(int physics, uint64_t n, int strength_mode, float* x, floa
 // phases
 // ---------------------------------------------------------------------------------------------
 int onb_make_tree(onb_context* c, int which) {
+    onb_scratch_reset(c);
     if (which < 0 || which > 1 || c->parts[which].n == 0) { c->err = "make_tree: set the particles first"; return ONB_ERR_ARG; }
     ONB_CUDA(cudaSetDevice(c->device));
     int rc = onb_alloc_tree(c, c->trees[which], c->parts[which].n, c->block);
@@ -204,6 +242,7 @@ int onb_make_tree(onb_context* c, int which) {
     return rc;
 }
 int onb_refine(onb_context* c, int which) {
+    onb_scratch_reset(c);
     if (which < 0 || which > 1) return ONB_ERR_ARG;
     ONB_CUDA(cudaSetDevice(c->device));
     PhaseTimer tm(c, "refine");
@@ -212,6 +251,7 @@ int onb_refine(onb_context* c, int which) {
     return rc;
 }
 int onb_upward(onb_context* c, int which) {
+    onb_scratch_reset(c);
     if (which < 0 || which > 1) return ONB_ERR_ARG;
     ONB_CUDA(cudaSetDevice(c->device));
     PhaseTimer tm(c, "upward");
@@ -227,6 +267,7 @@ int onb_zero_vels(onb_context* c) {
     return ONB_OK;
 }
 int onb_naive(onb_context* c, uint64_t tskip, float* flops) {
+    onb_scratch_reset(c);
     ONB_CUDA(cudaSetDevice(c->device));
     if (c->parts[0].n == 0 || c->parts[1].n == 0) { c->err = "naive: set sources and targets first"; return ONB_ERR_ARG; }
     if (tskip < 1) tskip = 1;
@@ -244,6 +285,7 @@ static int need_trees(onb_context* c, bool target_tree, bool eq_targets) {
     return ONB_OK;
 }
 int onb_treecode3(onb_context* c, float theta, float* flops) {
+    onb_scratch_reset(c);
     ONB_CUDA(cudaSetDevice(c->device));
     int rc = need_trees(c, true, false); if (rc) return rc;
     PhaseTimer te(c, "eval");
@@ -257,6 +299,7 @@ int onb_treecode3(onb_context* c, float theta, float* flops) {
     return rc;
 }
 int onb_fastsumm(onb_context* c, float theta) {
+    onb_scratch_reset(c);
     ONB_CUDA(cudaSetDevice(c->device));
     if (!c->has_fastsumm) { c->err = "this physics has no dual-tree method in the reference (onvortgrad3d.cpp:264)"; return ONB_ERR_UNSUPPORTED; }
     int rc = need_trees(c, true, true); if (rc) return rc;
@@ -266,6 +309,7 @@ int onb_fastsumm(onb_context* c, float theta) {
     return rc;
 }
 int onb_treecode2(onb_context* c, float theta, float* flops) {
+    onb_scratch_reset(c);
     ONB_CUDA(cudaSetDevice(c->device));
     int rc = need_trees(c, false, false); if (rc) return rc;
     PhaseTimer te(c, "eval");
@@ -275,6 +319,7 @@ int onb_treecode2(onb_context* c, float theta, float* flops) {
     return rc;
 }
 int onb_treecode1(onb_context* c, float theta, float* flops) {
+    onb_scratch_reset(c);
     ONB_CUDA(cudaSetDevice(c->device));
     if (!c->trees[0].built) { c->err = "build the source tree first"; return ONB_ERR_ARG; }
     PhaseTimer te(c, "eval");
@@ -416,7 +461,7 @@ int onb_load_tree(onb_context* c, int which, int levels, const float* x, const f
     ONB_CUDA(cudaMemcpy(t.num, nm.data(), n * 4, cudaMemcpyHostToDevice));
     if (which == 1) {   // targets loaded in tree order: original index = position
         DParts& p = c->parts[1];
-        if (!p.gidx) ONB_CUDA(onb_dmalloc(c, (void**)&p.gidx, (size_t)p.n * 4));
+        if (!p.gidx) ONB_CUDA(onb_pmalloc(c, (void**)&p.gidx, (size_t)p.n * 4));
         std::vector<uint32_t> id(p.n); for (uint32_t i = 0; i < p.n; ++i) id[i] = i;
         ONB_CUDA(cudaMemcpy(p.gidx, id.data(), (size_t)p.n * 4, cudaMemcpyHostToDevice));
     }

@@ -98,6 +98,12 @@ struct onb_context {
     int* d_flag = nullptr;
     int* h_flag = nullptr;   // pinned
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    // scratch arena: grow-only device slabs, bump-allocated inside one API call and reset at the start of the next.
+    // After the first (warm-up) call of a phase no allocation reaches the driver any more.
+    struct Slab { char* p; size_t cap; };
+    std::vector<Slab> slabs;
+    size_t slab_cur = 0, slab_off = 0;
+    unsigned long long* d_build_stats = nullptr;   // selects, passes, stalls, scanned, tie sorts
 };
 
 #define ONB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
@@ -106,10 +112,13 @@ struct onb_context {
 
 #define ONB_LAUNCH(c) ((c)->launches++)
 
-// all device memory comes from the device's stream-ordered pool (release threshold raised at context creation), so
-// the per-phase scratch of a repeated evaluation is recycled without touching the driver allocator
-static inline cudaError_t onb_dmalloc(onb_context* c, void** p, size_t bytes) { return cudaMallocAsync(p, bytes ? bytes : 4, c->stream); }
-static inline void onb_dfree(onb_context* c, void* p) { if (p) cudaFreeAsync(p, c->stream); }
+// scratch (per-call) device memory: bump allocation from the context's arena; "free" is a no-op, the arena is reset by
+// onb_scratch_reset() at the start of every public phase call. Persistent arrays use onb_pmalloc / onb_pfree.
+cudaError_t onb_dmalloc(onb_context* c, void** p, size_t bytes);
+static inline void onb_dfree(onb_context*, void*) {}
+void onb_scratch_reset(onb_context* c);
+static inline cudaError_t onb_pmalloc(onb_context*, void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 4); }
+static inline void onb_pfree(onb_context*, void* p) { if (p) cudaFree(p); }
 
 static inline PartsView view_of(const DParts& p) {
     PartsView v; v.n = p.n;

@@ -339,7 +339,7 @@ int onb_p2p_direct(onb_context* c, uint64_t tskip) {
     nsplit = (ntiles + a.tiles_per_split - 1) / a.tiles_per_split;
     a.nsplit = nsplit;
     a.partial = nullptr;
-    if (nsplit > 1) ONB_CUDA(cudaMallocAsync(&a.partial, (size_t)nsplit * c->OD * a.nt_eff * sizeof(float), c->stream));
+    if (nsplit > 1) ONB_CUDA(onb_dmalloc(c, (void**)&a.partial, (size_t)nsplit * c->OD * a.nt_eff * sizeof(float)));
     switch (c->physics) {
         case ONB_GRAV3D:     launch_direct<ONB_GRAV3D>(c, a); break;
         case ONB_VORT3D:     launch_direct<ONB_VORT3D>(c, a); break;
@@ -353,7 +353,6 @@ int onb_p2p_direct(onb_context* c, uint64_t tskip) {
         k_reduce_partials<<<(a.nt_eff + 255) / 256, 256, 0, c->stream>>>(a, c->OD);
         ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
-        ONB_CUDA(cudaFreeAsync(a.partial, c->stream));
     }
     c->last_pairs = (uint64_t)a.nt_eff * (uint64_t)srcs.n;
     return ONB_OK;
@@ -368,6 +367,7 @@ void onb_free_worklist(onb_context* c, WorkList& wl) {
 
 extern "C" double onb_measure_fp32_peak(onb_context* c) {
     if (!c) return -1.0;
+    onb_scratch_reset(c);
     const int blocks = c->sm_count * 8, threads = 256, iters = 2000;
     float* d = nullptr;
     if (onb_dmalloc(c, (void**)&d, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return -1.0;

@@ -30,6 +30,19 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { for (int o = 16; o; o
 
 __device__ __forceinline__ uint32_t log_2(uint32_t x) { return x == 0 ? 0u : 31u - __clz(x); }   // Tree.hpp:30-33
 
+// barneshut.hpp:538-540 in the reference's exact IEEE sequence (mode 0) or as g++ -O3 -ffast-math contracts it (mode 1)
+__device__ __forceinline__ float select_pivot(uint32_t nless, uint32_t wf, uint32_t wl, float lo, float hi, float ideal, int mode) {
+    const float f0 = __fdiv_rn(__double2float_rn(__dsub_rn(__dsub_rn((double)nless, 0.5), (double)wf)), __uint2float_rn(wl - wf));
+    if (mode == 0) {
+        const float frac = __double2float_rn(__ddiv_rn(__dadd_rn(__dmul_rn(9.0, (double)f0), __dmul_rn(1.0, (double)ideal)), 10.0));
+        return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), frac));
+    }
+    const float frac = __double2float_rn(__dmul_rn(__fma_rn(9.0, (double)f0, (double)ideal), 0.1));
+    return __fmaf_rn(__fsub_rn(hi, lo), frac, lo);
+}
+__device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
 struct SplitArgs {
     float* x[3];            // current coordinate planes (the select permutes x[axis] in place)
     TreeView t;
@@ -38,7 +51,7 @@ struct SplitArgs {
     uint32_t* lidx;         // per particle: position before this level's select (barneshut.hpp:516)
     uint32_t* scr;          // per particle scratch for the ordered compactions
     unsigned long long* stats;   // selects, passes, stalls, scanned
-    uint32_t block;
+    uint32_t block, big;    // nodes with more than `big` particles are split by the grid-wide kernels below
     int level, PD, pivot_mode;
 };
 
@@ -48,7 +61,7 @@ constexpr int SPLIT_ROUNDS = 4;   // each warp handles 4 x 32 consecutive elemen
 __global__ void __launch_bounds__(1024) k_node_split(const SplitArgs a) {
     const uint32_t node = (1u << a.level) + blockIdx.x;
     const uint32_t n = a.t.num[node];
-    if (n == 0) return;
+    if (n == 0 || n > a.big) return;
     const uint32_t pf = a.t.ioffset[node], pl = pf + n;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
 
@@ -101,16 +114,7 @@ __global__ void __launch_bounds__(1024) k_node_split(const SplitArgs a) {
     int iters = 0;
     uint32_t n_pass = 0, n_stall = 0; unsigned long long n_scan = 0;
     while (wl > wf && iters < 100) {
-        // :538-540
-        const float f0 = __fdiv_rn(__double2float_rn(__dsub_rn(__dsub_rn((double)nless, 0.5), (double)wf)), __uint2float_rn(wl - wf));
-        float frac, pivot;
-        if (a.pivot_mode == 0) {
-            frac = __double2float_rn(__ddiv_rn(__dadd_rn(__dmul_rn(9.0, (double)f0), __dmul_rn(1.0, (double)ideal)), 10.0));
-            pivot = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), frac));
-        } else {   // what g++ -O3 -ffast-math emits for the same two lines
-            frac = __double2float_rn(__dmul_rn(__fma_rn(9.0, (double)f0, (double)ideal), 0.1));
-            pivot = __fmaf_rn(__fsub_rn(hi, lo), frac, lo);
-        }
+        const float pivot = select_pivot(nless, wf, wl, lo, hi, ideal, a.pivot_mode);                // :538-540
         // pass 1: m = #{v < pivot}, and the min/max the two possible next windows will have
         uint32_t cnt = 0; float mx_lt = -INFINITY, mn_ge = INFINITY;
         for (uint32_t i = wf + tid; i <= wl; i += T) {
@@ -403,63 +407,113 @@ __global__ void __launch_bounds__(128) k_refine(const RefineArgs a) {
     }
 }
 
+#include "tree_big.cuh"
+
+__global__ void k_copy_planes(GatherArgs a) {     // final buffers -> the particle set's own planes (identity gather)
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    for (int d = 0; d < a.PD; ++d) a.dx[d][i] = a.sx[d][i];
+    a.dr[i] = a.sr[i];
+    for (int d = 0; d < a.SD; ++d) a.ds[d][i] = a.ss[d][i];
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static unsigned long long* g_build_stats_dev = nullptr;   // per-process scratch (selects, passes, stalls, scanned, tie sorts)
-
 extern "C" int onb_get_build_stats(onb_context* c, uint64_t out[5]) {
-    if (!g_build_stats_dev) { for (int i = 0; i < 5; ++i) out[i] = 0; return ONB_OK; }
     unsigned long long h[5];
     ONB_CUDA(cudaStreamSynchronize(c->stream));
-    ONB_CUDA(cudaMemcpy(h, g_build_stats_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    ONB_CUDA(cudaMemcpy(h, c->d_build_stats, sizeof(h), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 5; ++i) out[i] = h[i];
     return ONB_OK;
 }
 static int onb_pivot_mode = 0;   // 0 = the reference source evaluated in IEEE order; 1 = as g++ -O3 -ffast-math contracts it
 extern "C" void onb_set_pivot_mode(int mode) { onb_pivot_mode = mode ? 1 : 0; }
 
+static const uint32_t BIG_NODE = 32768;     // nodes above this are split by the grid-wide kernels of tree_big.cuh
+
 int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
     const uint32_t n = p.n;
     const int PD = c->PD, SD = p.are_sources ? c->SD : 0;
     if (n == 0) { c->err = "make_tree: no particles"; return ONB_ERR_ARG; }
-    if (!g_build_stats_dev) ONB_CUDA(onb_dmalloc(c, (void**)&g_build_stats_dev, 5 * sizeof(unsigned long long)));
-    ONB_CUDA(cudaMemsetAsync(g_build_stats_dev, 0, 4 * sizeof(unsigned long long), c->stream));
+    ONB_CUDA(cudaMemsetAsync(c->d_build_stats, 0, 4 * sizeof(unsigned long long), c->stream));
 
     // scratch: second copy of every plane (ping-pong), per-particle index planes, per-node split records
     const size_t capf = (size_t)p.cap * sizeof(float);
     float* alt_x[3] = {nullptr, nullptr, nullptr}; float* alt_r = nullptr; float* alt_s[3] = {nullptr, nullptr, nullptr};
-    uint32_t *alt_g = nullptr, *cur_g = nullptr, *lidx = nullptr, *scr = nullptr, *owner = nullptr, *pmid = nullptr; uint8_t* axis_of = nullptr;
+    uint32_t *alt_g = nullptr, *lidx = nullptr, *scr = nullptr, *owner = nullptr, *pmid = nullptr; uint8_t* axis_of = nullptr;
     for (int d = 0; d < PD; ++d) ONB_CUDA(onb_dmalloc(c, (void**)&alt_x[d], capf));
     ONB_CUDA(onb_dmalloc(c, (void**)&alt_r, capf));
     for (int d = 0; d < SD; ++d) ONB_CUDA(onb_dmalloc(c, (void**)&alt_s[d], capf));
-    ONB_CUDA(onb_dmalloc(c, (void**)&alt_g, (size_t)n * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&cur_g, (size_t)n * 4));
+    ONB_CUDA(onb_dmalloc(c, (void**)&alt_g, (size_t)n * 4));
     ONB_CUDA(onb_dmalloc(c, (void**)&lidx, (size_t)n * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&scr, (size_t)n * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&owner, (size_t)n * 4));
     ONB_CUDA(onb_dmalloc(c, (void**)&pmid, (size_t)t.numnodes * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&axis_of, (size_t)t.numnodes));
-    for (int d = 0; d < PD; ++d) ONB_CUDA(cudaMemsetAsync(alt_x[d], 0, capf, c->stream));
-    ONB_CUDA(cudaMemsetAsync(alt_r, 0, capf, c->stream));
-    for (int d = 0; d < SD; ++d) ONB_CUDA(cudaMemsetAsync(alt_s[d], 0, capf, c->stream));
+    // the tree-order index plane is persistent for targets (gidx), scratch for sources (dropped, barneshut.hpp:853)
+    uint32_t* own_g = nullptr;
+    if (!p.are_sources) { if (!p.gidx) ONB_CUDA(onb_pmalloc(c, (void**)&p.gidx, (size_t)n * 4)); own_g = p.gidx; }
+    else ONB_CUDA(onb_dmalloc(c, (void**)&own_g, (size_t)n * 4));
+    // grid-wide select state for the big nodes of the top levels
+    const uint32_t max_big_nodes = n / BIG_NODE + 2, max_chunks = n / BIG_CH + max_big_nodes + 1;
+    BigNode* bignodes = nullptr; uint32_t *nbig = nullptr, *chunk_owner = nullptr, *cntA = nullptr, *cntB = nullptr;
+    if (n > BIG_NODE) {
+        ONB_CUDA(onb_dmalloc(c, (void**)&bignodes, (size_t)max_big_nodes * sizeof(BigNode)));
+        ONB_CUDA(onb_dmalloc(c, (void**)&nbig, 16));
+        ONB_CUDA(onb_dmalloc(c, (void**)&chunk_owner, (size_t)max_chunks * 4));
+        ONB_CUDA(onb_dmalloc(c, (void**)&cntA, (size_t)max_chunks * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&cntB, (size_t)max_chunks * 4));
+    }
 
     const int TB = 256; const uint32_t GB = (n + TB - 1) / TB;
-    k_fill_u32<<<GB, TB, 0, c->stream>>>(cur_g, n, 0, 1); ONB_LAUNCH(c);                 // gidx = iota :823
+    k_fill_u32<<<GB, TB, 0, c->stream>>>(own_g, n, 0, 1); ONB_LAUNCH(c);                 // gidx = iota :823
     k_fill_u32<<<GB, TB, 0, c->stream>>>(owner, n, 1, 0); ONB_LAUNCH(c);
     ONB_CUDA(cudaMemsetAsync(t.num, 0, (size_t)t.numnodes * 4, c->stream));
     ONB_CUDA(cudaMemsetAsync(t.ioffset, 0, (size_t)t.numnodes * 4, c->stream));
     { const uint32_t root[1] = { n }; ONB_CUDA(cudaMemcpyAsync(t.num + 1, root, 4, cudaMemcpyHostToDevice, c->stream)); }
 
-    float* cx[3] = { p.x[0], p.x[1], p.x[2] }; float* cr = p.r; float* cs[3] = { p.s[0], p.s[1], p.s[2] }; uint32_t* cg = cur_g;
+    float* cx[3] = { p.x[0], p.x[1], p.x[2] }; float* cr = p.r; float* cs[3] = { p.s[0], p.s[1], p.s[2] }; uint32_t* cg = own_g;
     float* ax[3] = { alt_x[0], alt_x[1], alt_x[2] }; float* ar = alt_r; float* as[3] = { alt_s[0], alt_s[1], alt_s[2] }; uint32_t* ag = alt_g;
 
     uint32_t leftmost = n;     // the leftmost node of a level is its largest
     for (int lev = 0; lev < t.levels; ++lev) {
+        if (leftmost > BIG_NODE) {
+            BigArgs ba;
+            for (int d = 0; d < 3; ++d) ba.x[d] = cx[d];
+            ba.t = view_of(t); ba.nodes = bignodes; ba.nbig = nbig; ba.chunk_owner = chunk_owner; ba.cntA = cntA; ba.cntB = cntB;
+            ba.lidx = lidx; ba.scr = scr; ba.axis_of = axis_of; ba.pmid = pmid; ba.stats = c->d_build_stats;
+            ba.block = c->block; ba.big = BIG_NODE; ba.level = lev; ba.PD = PD; ba.pivot_mode = onb_pivot_mode; ba.it = 0;
+            const uint32_t lev_nodes = std::min<uint64_t>(1ull << lev, max_big_nodes);
+            ba.max_nodes = lev_nodes; ba.max_chunks = max_chunks;
+            const uint32_t chunks_ub = std::min<uint32_t>(max_chunks, n / BIG_CH + lev_nodes + 1);
+            k_big_list<<<1, 256, 0, c->stream>>>(ba); ONB_LAUNCH(c);
+            k_big_bbox<<<chunks_ub, BIG_T, 0, c->stream>>>(ba); ONB_LAUNCH(c);
+            k_big_setup<<<(lev_nodes + 127) / 128, 128, 0, c->stream>>>(ba); ONB_LAUNCH(c);
+            int it = 0;
+            while (it < 104) {
+                for (int rep = 0; rep < 4; ++rep, ++it) {
+                    ba.it = it;
+                    k_big_count<<<chunks_ub, BIG_T, 0, c->stream>>>(ba);
+                    k_big_mis<<<chunks_ub, BIG_T, 0, c->stream>>>(ba);
+                    k_big_scan<<<lev_nodes, 256, 0, c->stream>>>(ba);
+                    k_big_compact<<<chunks_ub, BIG_T, 0, c->stream>>>(ba);
+                    k_big_swap<<<chunks_ub, BIG_T, 0, c->stream>>>(ba);
+                    c->launches += 5;
+                }
+                ONB_CUDA(cudaMemcpyAsync(c->h_flag, nbig + 2, 4, cudaMemcpyDeviceToHost, c->stream));
+                ONB_CUDA(cudaStreamSynchronize(c->stream));
+                if (*c->h_flag == 0) break;
+            }
+            *c->h_flag = 0;
+            k_big_finish<<<(lev_nodes + 127) / 128, 128, 0, c->stream>>>(ba); ONB_LAUNCH(c);
+            ONB_CUDA(cudaGetLastError());
+        }
         SplitArgs sa;
         for (int d = 0; d < 3; ++d) sa.x[d] = cx[d];
-        sa.t = view_of(t); sa.axis_of = axis_of; sa.pmid = pmid; sa.lidx = lidx; sa.scr = scr; sa.stats = g_build_stats_dev;
-        sa.block = c->block; sa.level = lev; sa.PD = PD; sa.pivot_mode = onb_pivot_mode;
+        sa.t = view_of(t); sa.axis_of = axis_of; sa.pmid = pmid; sa.lidx = lidx; sa.scr = scr; sa.stats = c->d_build_stats;
+        sa.block = c->block; sa.big = BIG_NODE; sa.level = lev; sa.PD = PD; sa.pivot_mode = onb_pivot_mode;
         int threads = 1024;
-        while (threads > 128 && (uint32_t)threads * 2 > leftmost) threads >>= 1;
+        const uint32_t largest_small = std::min(leftmost, BIG_NODE);
+        while (threads > 128 && (uint32_t)threads * 2 > largest_small) threads >>= 1;
         k_node_split<<<1u << lev, threads, 0, c->stream>>>(sa); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
         if (leftmost <= (uint32_t)c->block) break;     // every node of this level is a leaf: nothing below
@@ -474,11 +528,14 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
         std::swap(cr, ar); std::swap(cg, ag);
         leftmost = (uint32_t)c->block * (1u << (31 - __builtin_clz((leftmost - 1) / c->block)));
     }
-    // the particle set now owns whichever buffers hold the final order
-    for (int d = 0; d < PD; ++d) p.x[d] = cx[d];
-    p.r = cr;
-    for (int d = 0; d < SD; ++d) p.s[d] = cs[d];
-    if (!p.are_sources) { if (p.gidx) onb_dfree(c, p.gidx); p.gidx = cg; cg = nullptr; }
+    // after an odd number of levels the final order sits in the scratch copies: bring it home
+    if (cr != p.r) {
+        GatherArgs ga;
+        for (int d = 0; d < 3; ++d) { ga.sx[d] = cx[d]; ga.dx[d] = p.x[d]; ga.ss[d] = cs[d]; ga.ds[d] = p.s[d]; }
+        ga.sr = cr; ga.dr = p.r; ga.n = n; ga.PD = PD; ga.SD = SD;
+        k_copy_planes<<<GB, TB, 0, c->stream>>>(ga); ONB_LAUNCH(c);
+        if (!p.are_sources) ONB_CUDA(cudaMemcpyAsync(p.gidx, cg, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
     p.packed_valid = false;
 
     // finishTree
@@ -490,12 +547,6 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
         k_finish_parents<<<(nn + 127) / 128, 128, 0, c->stream>>>(fa, lev); ONB_LAUNCH(c);
     }
     ONB_CUDA(cudaGetLastError());
-    ONB_CUDA(cudaStreamSynchronize(c->stream));
-    for (int d = 0; d < PD; ++d) onb_dfree(c, ax[d]);
-    onb_dfree(c, ar);
-    for (int d = 0; d < SD; ++d) onb_dfree(c, as[d]);
-    onb_dfree(c, ag); if (cg) onb_dfree(c, cg);
-    onb_dfree(c, lidx); onb_dfree(c, scr); onb_dfree(c, owner); onb_dfree(c, pmid); onb_dfree(c, axis_of);
     t.built = true;
     return ONB_OK;
 }
@@ -503,10 +554,9 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
 int onb_tree_refine(onb_context* c, DParts& p, DTree& t) {
     if (!t.built) { c->err = "refine: tree not built"; return ONB_ERR_ARG; }
     if (c->block > 128) { c->err = "refine: block size > 128 not supported by the GPU build"; return ONB_ERR_UNSUPPORTED; }
-    if (!g_build_stats_dev) ONB_CUDA(onb_dmalloc(c, (void**)&g_build_stats_dev, 5 * sizeof(unsigned long long)));
-    ONB_CUDA(cudaMemsetAsync(g_build_stats_dev + 4, 0, sizeof(unsigned long long), c->stream));
+    ONB_CUDA(cudaMemsetAsync(c->d_build_stats + 4, 0, sizeof(unsigned long long), c->stream));
     RefineArgs ra; ra.p = view_of(p); ra.n = p.n; ra.block = c->block; ra.PD = c->PD; ra.SD = c->SD; ra.OD = c->OD;
-    ra.are_sources = p.are_sources ? 1 : 0; ra.flag = c->d_flag; ra.tie_sorts = g_build_stats_dev + 4;
+    ra.are_sources = p.are_sources ? 1 : 0; ra.flag = c->d_flag; ra.tie_sorts = c->d_build_stats + 4;
     const uint32_t nleaf = (p.n + c->block - 1) / c->block;
     k_refine<<<nleaf, 128, 0, c->stream>>>(ra); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());

@@ -1,0 +1,303 @@
+/*
+ * tree_big.cuh - the same partial select as k_node_split (tree.cu), for nodes too large for one CTA.
+ *
+ * The top levels of the k-d tree have few, huge nodes (the root holds every particle), so a CTA-per-node kernel would
+ * leave 147 SMs idle exactly where most of the data is. Here every "big" node of a level is cut into fixed chunks
+ * of 2048 particles and each partition pass (barneshut.hpp:527-586) becomes five grid-wide launches over all chunks
+ * of all big nodes of the level:
+ *
+ *   k_big_count    per chunk: #{v < pivot}, max{v < pivot}, min{v >= pivot}            -> atomics on the node
+ *   k_big_mis      per chunk: misplaced-left / misplaced-right counts (needs B = wf + m)
+ *   k_big_scan     per node : exclusive scan of the chunk counts, k, next window + next pivot (the reference's exit rules)
+ *   k_big_compact  per chunk: ordered compaction of the misplaced positions into scr[]
+ *   k_big_swap     per chunk: swap pair j of the node, a_j <-> b_j
+ *
+ * Node state lives in global memory, double buffered by pass parity so that compact/swap still see the window the
+ * pass started with while scan has already published the next one. Results are bit-identical to k_node_split: the
+ * passes, pivots and exit conditions are the same, only the parallel decomposition differs.
+ */
+#pragma once
+
+constexpr int BIG_T = 256;                 // threads per chunk CTA
+constexpr int BIG_ROUNDS = 8;              // 8 warps x 8 rounds x 32 lanes
+constexpr uint32_t BIG_CH = BIG_T * BIG_ROUNDS;   // 2048 particles per chunk
+
+struct BigWin { uint32_t wf, wl; float lo, hi, pivot; int done, iters, pad; };
+struct BigNode {
+    uint32_t node, pf, pl, nless, chunk0, nchunks; int axis; float ideal;
+    BigWin w[2];
+    uint32_t m, mx_enc, mn_enc;            // atomics of the current pass (reset by k_big_scan)
+    uint32_t B, k;
+    uint32_t bmin[3], bmax[3];             // order-encoded bounding box atomics
+    uint32_t npass, nstall; unsigned long long nscan;
+};
+
+struct BigArgs {
+    float* x[3]; TreeView t;
+    BigNode* nodes; uint32_t* nbig;        // nbig[0] = number of big nodes of this level, nbig[1] = total chunks, nbig[2] = still active
+    uint32_t* chunk_owner;                 // chunk -> index into nodes
+    uint32_t* cntA; uint32_t* cntB;        // per chunk: counts, then exclusive offsets
+    uint32_t* lidx; uint32_t* scr;
+    uint8_t* axis_of; uint32_t* pmid;
+    unsigned long long* stats;
+    uint32_t block, big, max_nodes, max_chunks; int level, PD, pivot_mode, it;
+};
+
+// one block: list the big nodes of this level (node order) and lay out their chunks
+__global__ void __launch_bounds__(256) k_big_list(const BigArgs a) {
+    __shared__ uint32_t s_n, s_c;
+    if (threadIdx.x == 0) { s_n = 0; s_c = 0; }
+    __syncthreads();
+    const uint32_t first = 1u << a.level, last = 2u << a.level;
+    // serial over nodes in order (<= a few thousand), parallel fill of the chunk table afterwards
+    if (threadIdx.x == 0) {
+        uint32_t nb = 0, nc = 0;
+        for (uint32_t node = first; node < last; ++node) {
+            const uint32_t n = a.t.num[node];
+            if (n > a.big && nb < a.max_nodes) {
+                BigNode& b = a.nodes[nb];
+                b.node = node; b.pf = a.t.ioffset[node]; b.pl = b.pf + n; b.chunk0 = nc; b.nchunks = (n + BIG_CH - 1) / BIG_CH;
+                for (int d = 0; d < 3; ++d) { b.bmin[d] = 0xffffffffu; b.bmax[d] = 0u; }
+                b.m = 0; b.mx_enc = 0u; b.mn_enc = 0xffffffffu; b.npass = 0; b.nstall = 0; b.nscan = 0;
+                nc += b.nchunks; ++nb;
+            }
+        }
+        s_n = nb; s_c = nc; a.nbig[0] = nb; a.nbig[1] = nc; a.nbig[2] = nb;
+    }
+    __syncthreads();
+    for (uint32_t b = 0; b < s_n; ++b) {
+        const uint32_t c0 = a.nodes[b].chunk0, nc = a.nodes[b].nchunks;
+        for (uint32_t q = threadIdx.x; q < nc; q += blockDim.x) a.chunk_owner[c0 + q] = b;
+    }
+}
+
+__device__ __forceinline__ float bw_min(float v) { for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ float bw_max(float v) { for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ uint32_t bw_sum(uint32_t v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+
+// per chunk: bounding box contribution and lidx = iota (barneshut.hpp:621-625, :516)
+__global__ void __launch_bounds__(BIG_T) k_big_bbox(const BigArgs a) {
+    const uint32_t chunk = blockIdx.x;
+    if (chunk >= a.nbig[1]) return;
+    BigNode& b = a.nodes[a.chunk_owner[chunk]];
+    const uint32_t i0 = b.pf + (chunk - b.chunk0) * BIG_CH, i1 = min(b.pl, i0 + BIG_CH);
+    __shared__ float s_lo[BIG_T / 32], s_hi[BIG_T / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i = i0 + threadIdx.x; i < i1; i += BIG_T) a.lidx[i] = i;
+    for (int d = 0; d < a.PD; ++d) {
+        float lo = INFINITY, hi = -INFINITY;
+        for (uint32_t i = i0 + threadIdx.x; i < i1; i += BIG_T) { const float v = a.x[d][i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        lo = bw_min(lo); hi = bw_max(hi);
+        if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+        __syncthreads();
+        if (warp == 0) {
+            lo = lane < BIG_T / 32 ? s_lo[lane] : INFINITY; hi = lane < BIG_T / 32 ? s_hi[lane] : -INFINITY;
+            lo = bw_min(lo); hi = bw_max(hi);
+            if (lane == 0) { atomicMin(&b.bmin[d], f2ord(lo)); atomicMax(&b.bmax[d], f2ord(hi)); }
+        }
+        __syncthreads();
+    }
+}
+
+// per node: node arrays, split axis, first window and pivot (barneshut.hpp:623-663, :519-540)
+__global__ void k_big_setup(const BigArgs a) {
+    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= a.nbig[0]) return;
+    BigNode& b = a.nodes[bi];
+    const uint32_t node = b.node;
+    float lo[3], hi[3], bsss = 0.0f;
+    int axis = 0; float axsz = -1.0f;
+    for (int d = 0; d < a.PD; ++d) {
+        lo[d] = ord2f(b.bmin[d]); hi[d] = ord2f(b.bmax[d]);
+        const float ns = __fsub_rn(hi[d], lo[d]);
+        a.t.ns[d][node] = ns;
+        a.t.nc[d][node] = __fmul_rn(0.5f, __fadd_rn(hi[d], lo[d]));
+        bsss = __double2float_rn(__dadd_rn((double)bsss, __dmul_rn((double)ns, (double)ns)));
+        if (ns > axsz) { axsz = ns; axis = d; }
+    }
+    a.t.nr[node] = __fmul_rn(0.5f, __fsqrt_rn(bsss));
+    const uint32_t n = b.pl - b.pf;
+    b.axis = axis;
+    b.nless = b.pf + a.block * (1u << (31 - __clz((n - 1) / a.block)));
+    b.ideal = __fdiv_rn(__uint2float_rn(b.nless - b.pf), __uint2float_rn(n));
+    BigWin w; w.wf = b.pf; w.wl = b.pl - 1; w.lo = lo[axis]; w.hi = hi[axis]; w.done = 0; w.iters = 0; w.pad = 0;
+    w.pivot = select_pivot(b.nless, w.wf, w.wl, w.lo, w.hi, b.ideal, a.pivot_mode);
+    b.w[0] = w; b.w[1] = w;
+}
+
+// element range of this chunk inside the node's current window; false if empty / node finished
+__device__ __forceinline__ bool big_range(const BigNode& b, const BigWin& w, uint32_t chunk, uint32_t& i0, uint32_t& i1) {
+    if (w.done) return false;
+    const uint32_t c0 = b.pf + (chunk - b.chunk0) * BIG_CH;
+    i0 = max(c0, w.wf); i1 = min(min(b.pl, c0 + BIG_CH), w.wl + 1);
+    return i0 < i1;
+}
+
+__global__ void __launch_bounds__(BIG_T) k_big_count(const BigArgs a) {
+    const uint32_t chunk = blockIdx.x;
+    if (chunk >= a.nbig[1]) return;
+    BigNode& b = a.nodes[a.chunk_owner[chunk]];
+    const BigWin w = b.w[a.it & 1];
+    uint32_t i0, i1;
+    if (!big_range(b, w, chunk, i0, i1)) return;
+    const float* key = a.x[b.axis];
+    uint32_t cnt = 0; float mx = -INFINITY, mn = INFINITY;
+    for (uint32_t i = i0 + threadIdx.x; i < i1; i += BIG_T) {
+        const float v = key[i];
+        if (v < w.pivot) { ++cnt; mx = fmaxf(mx, v); } else mn = fminf(mn, v);
+    }
+    __shared__ uint32_t s_c[BIG_T / 32]; __shared__ float s_mx[BIG_T / 32], s_mn[BIG_T / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    cnt = bw_sum(cnt); mx = bw_max(mx); mn = bw_min(mn);
+    if (lane == 0) { s_c[warp] = cnt; s_mx[warp] = mx; s_mn[warp] = mn; }
+    __syncthreads();
+    if (warp == 0) {
+        cnt = lane < BIG_T / 32 ? s_c[lane] : 0u; mx = lane < BIG_T / 32 ? s_mx[lane] : -INFINITY; mn = lane < BIG_T / 32 ? s_mn[lane] : INFINITY;
+        cnt = bw_sum(cnt); mx = bw_max(mx); mn = bw_min(mn);
+        if (lane == 0) {
+            if (cnt) atomicAdd(&b.m, cnt);
+            if (mx > -INFINITY) atomicMax(&b.mx_enc, f2ord(mx));
+            if (mn < INFINITY) atomicMin(&b.mn_enc, f2ord(mn));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BIG_T) k_big_mis(const BigArgs a) {
+    const uint32_t chunk = blockIdx.x;
+    if (chunk >= a.nbig[1]) return;
+    BigNode& b = a.nodes[a.chunk_owner[chunk]];
+    const BigWin w = b.w[a.it & 1];
+    if (w.done) return;
+    uint32_t i0, i1, ca = 0, cb = 0;
+    if (big_range(b, w, chunk, i0, i1)) {
+        const uint32_t B = w.wf + b.m;
+        const float* key = a.x[b.axis];
+        for (uint32_t i = i0 + threadIdx.x; i < i1; i += BIG_T) {
+            const bool lt = key[i] < w.pivot;
+            ca += (i < B && !lt); cb += (i >= B && lt);
+        }
+    }
+    __shared__ uint32_t s_a[BIG_T / 32], s_b[BIG_T / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ca = bw_sum(ca); cb = bw_sum(cb);
+    if (lane == 0) { s_a[warp] = ca; s_b[warp] = cb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t ta = 0, tb = 0;
+        for (int q = 0; q < BIG_T / 32; ++q) { ta += s_a[q]; tb += s_b[q]; }
+        a.cntA[chunk] = ta; a.cntB[chunk] = tb;
+    }
+}
+
+// one CTA per big node: chunk counts -> exclusive offsets, then the reference's window update (barneshut.hpp:565-585)
+__global__ void __launch_bounds__(256) k_big_scan(const BigArgs a) {
+    const uint32_t bi = blockIdx.x;
+    if (bi >= a.nbig[0]) return;
+    BigNode& b = a.nodes[bi];
+    const BigWin w = b.w[a.it & 1];
+    if (w.done) { if (threadIdx.x == 0) b.w[(a.it + 1) & 1] = w; return; }
+    __shared__ uint32_t s_wa[8], s_wb[8], s_carry[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+    __syncthreads();
+    for (uint32_t base = 0; base < b.nchunks; base += 256) {
+        const uint32_t q = base + threadIdx.x;
+        const uint32_t va = q < b.nchunks ? a.cntA[b.chunk0 + q] : 0u, vb = q < b.nchunks ? a.cntB[b.chunk0 + q] : 0u;
+        uint32_t ia = va, ib = vb;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o); if (lane >= o) { ia += ta; ib += tb; } }
+        if (lane == 31) { s_wa[warp] = ia; s_wb[warp] = ib; }
+        __syncthreads();
+        uint32_t pa = s_carry[0], pb = s_carry[1], ta = 0, tb = 0;
+        for (int q2 = 0; q2 < 8; ++q2) { if (q2 < warp) { pa += s_wa[q2]; pb += s_wb[q2]; } ta += s_wa[q2]; tb += s_wb[q2]; }
+        if (q < b.nchunks) { a.cntA[b.chunk0 + q] = pa + ia - va; a.cntB[b.chunk0 + q] = pb + ib - vb; }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_carry[0] += ta; s_carry[1] += tb; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t B = w.wf + b.m;
+        b.B = B; b.k = s_carry[0];
+        const float mx_lt = ord2f(b.mx_enc), mn_ge = ord2f(b.mn_enc);
+        b.npass += 1; b.nscan += (w.wl - w.wf + 1);
+        BigWin nw = w;
+        if (B == b.nless) nw.done = 1;
+        else {
+            if (B < b.nless) { nw.wf = B; nw.lo = mn_ge; } else { nw.wl = B - 1; nw.hi = mx_lt; }
+            if (nw.wf == w.wf && nw.wl == w.wl) { nw.done = 1; b.nstall += 1; }
+            else {
+                nw.iters = w.iters + 1;
+                if (!(nw.wl > nw.wf) || nw.iters >= 100) nw.done = 1;                      // loop condition :527
+                else nw.pivot = select_pivot(b.nless, nw.wf, nw.wl, nw.lo, nw.hi, b.ideal, a.pivot_mode);
+            }
+        }
+        b.w[(a.it + 1) & 1] = nw;
+        b.m = 0; b.mx_enc = 0u; b.mn_enc = 0xffffffffu;
+        if (nw.done) atomicSub(&a.nbig[2], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(BIG_T) k_big_compact(const BigArgs a) {
+    const uint32_t chunk = blockIdx.x;
+    if (chunk >= a.nbig[1]) return;
+    BigNode& b = a.nodes[a.chunk_owner[chunk]];
+    const BigWin w = b.w[a.it & 1];
+    uint32_t i0, i1;
+    if (!big_range(b, w, chunk, i0, i1)) return;
+    const uint32_t B = b.B;
+    const float* key = a.x[b.axis];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t c0 = b.pf + (chunk - b.chunk0) * BIG_CH;
+    uint32_t ba[BIG_ROUNDS], bb[BIG_ROUNDS], totA = 0, totB = 0;
+    #pragma unroll
+    for (int r = 0; r < BIG_ROUNDS; ++r) {
+        const uint32_t i = c0 + (uint32_t)warp * 32u * BIG_ROUNDS + (uint32_t)r * 32u + lane;
+        const bool valid = i >= i0 && i < i1;
+        const float v = valid ? key[i] : 0.f;
+        const bool lt = v < w.pivot;
+        ba[r] = __ballot_sync(0xffffffffu, valid && i < B && !lt);
+        bb[r] = __ballot_sync(0xffffffffu, valid && i >= B && lt);
+        totA += __popc(ba[r]); totB += __popc(bb[r]);
+    }
+    __shared__ uint32_t s_a[BIG_T / 32], s_b[BIG_T / 32];
+    if (lane == 0) { s_a[warp] = totA; s_b[warp] = totB; }
+    __syncthreads();
+    uint32_t offA = a.cntA[chunk], offB = a.cntB[chunk];
+    for (int q = 0; q < warp; ++q) { offA += s_a[q]; offB += s_b[q]; }
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    #pragma unroll
+    for (int r = 0; r < BIG_ROUNDS; ++r) {
+        const uint32_t i = c0 + (uint32_t)warp * 32u * BIG_ROUNDS + (uint32_t)r * 32u + lane;
+        if ((ba[r] >> lane) & 1u) a.scr[b.pf + offA + __popc(ba[r] & lt_mask)] = i;
+        if ((bb[r] >> lane) & 1u) a.scr[b.pl - 1u - (offB + __popc(bb[r] & lt_mask))] = i;
+        offA += __popc(ba[r]); offB += __popc(bb[r]);
+    }
+}
+
+__global__ void __launch_bounds__(BIG_T) k_big_swap(const BigArgs a) {
+    const uint32_t chunk = blockIdx.x;
+    if (chunk >= a.nbig[1]) return;
+    BigNode& b = a.nodes[a.chunk_owner[chunk]];
+    if (b.w[a.it & 1].done) return;
+    const uint32_t k = b.k, q = chunk - b.chunk0;
+    float* key = a.x[b.axis];
+    const uint32_t j1 = min(k, (q + 1) * BIG_CH);
+    for (uint32_t j = q * BIG_CH + threadIdx.x; j < j1; j += BIG_T) {                     // barneshut.hpp:549-556
+        const uint32_t pa = a.scr[b.pf + j], pb = a.scr[b.pl - k + j];
+        const float va = key[pa], vb = key[pb]; key[pa] = vb; key[pb] = va;
+        const uint32_t ia = a.lidx[pa], ib = a.lidx[pb]; a.lidx[pa] = ib; a.lidx[pb] = ia;
+    }
+}
+
+// per node: publish the split (barneshut.hpp:702-704) and the statistics
+__global__ void k_big_finish(const BigArgs a) {
+    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= a.nbig[0]) return;
+    const BigNode& b = a.nodes[bi];
+    const uint32_t node = b.node;
+    a.axis_of[node] = (uint8_t)b.axis; a.pmid[node] = b.nless;
+    a.t.ioffset[2 * node] = b.pf;        a.t.num[2 * node] = b.nless - b.pf;
+    a.t.ioffset[2 * node + 1] = b.nless; a.t.num[2 * node + 1] = b.pl - b.nless;
+    atomicAdd(&a.stats[0], 1ull); atomicAdd(&a.stats[1], (unsigned long long)b.npass);
+    atomicAdd(&a.stats[2], (unsigned long long)b.nstall); atomicAdd(&a.stats[3], b.nscan);
+}
