@@ -136,6 +136,9 @@ ONB_API int onb_get_build_stats(onb_context* c, uint64_t out[5]);
  * barneshut.hpp:538-540 (matches that build's intra-leaf source order as well). Process-wide. */
 ONB_API void onb_set_pivot_mode(int mode);
 
+/* tuning / tests: targets per thread of the list-driven pair kernel (1, 2 or 4; 0 = built-in per-physics default). Process-wide. */
+ONB_API void onb_set_p2p_tpt(int tpt);
+
 /* test support: install an already-built tree + already-ordered particles (lets each phase be parity-
  * tested in isolation against the oracle). Arrays as in onb_get_tree. */
 ONB_API int onb_load_tree(onb_context* c, int which, int levels, const float* x, const float* nc, const float* ns,

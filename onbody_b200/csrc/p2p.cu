@@ -119,9 +119,16 @@ __device__ __forceinline__ TileRef decode_entry(const P2PArgs& a, uint32_t entry
     return t;
 }
 
-template <int PHYS, bool STRICT>
-__global__ void __launch_bounds__(128) k_p2p_lists(const __grid_constant__ P2PArgs a) {
+// TPT targets per thread (register blocking): the CTA has 128/TPT threads, thread t owns targets t, t+NT, t+2NT, ...
+// Every shared-memory broadcast of a source then feeds TPT pairs, which is what lifts the kernel off the shared-memory
+// wavefront limit (3 wavefronts per source and warp: ncu showed the LSU data pipe at 66 % with TPT=1) and raises the
+// FP32 share of the issue slots. Each target still accumulates its sources in list order, so results do not change.
+template <int PHYS, bool STRICT, int TPT, bool PK>
+__global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__ P2PArgs a) {
     constexpr int OD = Phys<PHYS>::OD;
+    constexpr int NT = 128 / TPT;
+    constexpr int G = PK ? TPT / 2 : 1;          // packed target pairs per thread
+    static_assert(!PK || (TPT % 2 == 0 && !STRICT), "packed arithmetic needs an even TPT and the fast mode");
     __shared__ TileSmem<PHYS> sm;
     const int tid = threadIdx.x;
     const uint32_t w = blockIdx.x;
@@ -132,17 +139,34 @@ __global__ void __launch_bounds__(128) k_p2p_lists(const __grid_constant__ P2PAr
     const bool leaf = tn <= a.block;
     const uint32_t toff = leaf ? a.t_ioffset[T] : T * a.ebs;
     const uint32_t tcnt = leaf ? tn : a.num_eqps;
-    const bool valid = (uint32_t)tid < tcnt;
-    const uint32_t ti = toff + (valid ? tid : 0);
-    Tgt tg;
-    tg.x = leaf ? a.tx[0][ti] : a.bx[0][ti];
-    tg.y = leaf ? a.tx[1][ti] : a.bx[1][ti];
-    tg.z = Phys<PHYS>::PD > 2 ? (leaf ? a.tx[2][ti] : a.bx[2][ti]) : 0.f;
-    tg.r2 = 0.f;
-    if (Phys<PHYS>::TR) { const float r = leaf ? a.tr[ti] : a.br[ti]; tg.r2 = __fmul_rn(r, r); }
-    float acc[OD];
+    Tgt tg[TPT];
+    float acc[TPT][OD];
     #pragma unroll
-    for (int d = 0; d < OD; ++d) acc[d] = valid ? (leaf ? a.tu[d][ti] : a.bu[d][ti]) : 0.f;
+    for (int q = 0; q < TPT; ++q) {
+        const uint32_t slot = (uint32_t)tid + (uint32_t)q * NT;
+        const bool valid = slot < tcnt;
+        const uint32_t ti = toff + (valid ? slot : 0);
+        tg[q].x = leaf ? a.tx[0][ti] : a.bx[0][ti];
+        tg[q].y = leaf ? a.tx[1][ti] : a.bx[1][ti];
+        tg[q].z = Phys<PHYS>::PD > 2 ? (leaf ? a.tx[2][ti] : a.bx[2][ti]) : 0.f;
+        tg[q].r2 = 0.f;
+        if (Phys<PHYS>::TR) { const float r = leaf ? a.tr[ti] : a.br[ti]; tg[q].r2 = __fmul_rn(r, r); }
+        #pragma unroll
+        for (int d = 0; d < OD; ++d) acc[q][d] = valid ? (leaf ? a.tu[d][ti] : a.bu[d][ti]) : 0.f;
+    }
+    Tgt2 tg2[G];
+    f2 acc2[G][OD];
+    if (PK) {
+        #pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const Tgt& t0 = tg[2 * g]; const Tgt& t1 = tg[PK ? 2 * g + 1 : 0];
+            tg2[g].px = mk2(t0.x, t1.x); tg2[g].py = mk2(t0.y, t1.y); tg2[g].pz = mk2(t0.z, t1.z);
+            tg2[g].nx = mk2(-t0.x, -t1.x); tg2[g].ny = mk2(-t0.y, -t1.y); tg2[g].nz = mk2(-t0.z, -t1.z);
+            tg2[g].r2 = mk2(t0.r2, t1.r2);
+            #pragma unroll
+            for (int d = 0; d < OD; ++d) acc2[g][d] = mk2(acc[2 * g][d], acc[PK ? 2 * g + 1 : 0][d]);
+        }
+    }
 
     if (tid == 0) { ptx::mbar_init(&sm.bar[0], 1); ptx::mbar_init(&sm.bar[1], 1); ptx::fence_mbar_init(); }
     __syncthreads();
@@ -157,13 +181,43 @@ __global__ void __launch_bounds__(128) k_p2p_lists(const __grid_constant__ P2PAr
             if (tid == 0) tile_issue<PHYS>(sm, buf ^ 1, nxt);
         }
         ptx::mbar_wait(&sm.bar[buf], par);
-        tile_compute<PHYS, STRICT>(sm, buf, cur, tg, acc);
-        __syncthreads();          // everyone is done with `buf` before it is refilled two iterations later
+        {
+            const float4* __restrict__ A = sm.a[buf];
+            const float4* __restrict__ B = sm.b[buf];
+            const float*  __restrict__ C = sm.c[buf] + (Phys<PHYS>::F1 ? (cur.off & 3u) : 0u);
+            const int cnt = (int)cur.cnt;
+            #pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+                const float4 p0 = A[j];
+                const float4 p1 = Phys<PHYS>::NF4 > 1 ? B[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float p2 = Phys<PHYS>::F1 ? C[j] : 0.f;
+                if (PK) {
+                    #pragma unroll
+                    for (int g = 0; g < G; ++g) pair2<PHYS>(p0, p1, p2, tg2[g], acc2[g]);
+                } else {
+                    #pragma unroll
+                    for (int q = 0; q < TPT; ++q) pair<PHYS, STRICT>(p0, p1, p2, tg[q], acc[q]);
+                }
+            }
+        }
+        if (NT > 32) __syncthreads(); else __syncwarp();   // everyone is done with `buf` before it is refilled two iterations later
         cur = nxt;
     }
-    if (valid) {
+    if (PK) {
         #pragma unroll
-        for (int d = 0; d < OD; ++d) { if (leaf) a.tu[d][ti] = acc[d]; else a.bu[d][ti] = acc[d]; }
+        for (int g = 0; g < G; ++g) {
+            #pragma unroll
+            for (int d = 0; d < OD; ++d) { acc[2 * g][d] = lo2(acc2[g][d]); acc[PK ? 2 * g + 1 : 0][d] = hi2(acc2[g][d]); }
+        }
+    }
+    #pragma unroll
+    for (int q = 0; q < TPT; ++q) {
+        const uint32_t slot = (uint32_t)tid + (uint32_t)q * NT;
+        if (slot < tcnt) {
+            const uint32_t ti = toff + slot;
+            #pragma unroll
+            for (int d = 0; d < OD; ++d) { if (leaf) a.tu[d][ti] = acc[q][d]; else a.bu[d][ti] = acc[q][d]; }
+        }
     }
 }
 
@@ -248,10 +302,21 @@ __global__ void k_fma_peak(float* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+int g_p2p_tpt = 0;     // 0 = per-physics default; 1, 2 or 4 forces the register blocking; +16 = scalar instead of packed f32x2
+
+template <int PHYS, int TPT>
+void launch_lists_t(onb_context* c, const P2PArgs& a, uint32_t nitems, bool packed) {
+    if (c->arith == ONB_ARITH_STRICT) k_p2p_lists<PHYS, true, TPT, false><<<nitems, 128 / TPT, 0, c->stream>>>(a);
+    else if (packed && TPT > 1)       k_p2p_lists<PHYS, false, TPT, (TPT > 1)><<<nitems, 128 / TPT, 0, c->stream>>>(a);
+    else                              k_p2p_lists<PHYS, false, TPT, false><<<nitems, 128 / TPT, 0, c->stream>>>(a);
+}
 template <int PHYS>
 void launch_lists(onb_context* c, const P2PArgs& a, uint32_t nitems) {
-    if (c->arith == ONB_ARITH_STRICT) k_p2p_lists<PHYS, true><<<nitems, 128, 0, c->stream>>>(a);
-    else                              k_p2p_lists<PHYS, false><<<nitems, 128, 0, c->stream>>>(a);
+    const bool packed = !(g_p2p_tpt & 16);
+    int tpt = (g_p2p_tpt & 15) ? (g_p2p_tpt & 15) : (PHYS == ONB_VORTGRAD3D ? 2 : 4);
+    if (tpt == 1) launch_lists_t<PHYS, 1>(c, a, nitems, packed);
+    else if (tpt == 2) launch_lists_t<PHYS, 2>(c, a, nitems, packed);
+    else launch_lists_t<PHYS, 4>(c, a, nitems, packed);
 }
 template <int PHYS>
 void launch_direct(onb_context* c, const DirectArgs& a) {
@@ -364,6 +429,8 @@ void onb_free_worklist(onb_context* c, WorkList& wl) {
     if (wl.entries) onb_dfree(c, wl.entries);
     wl = WorkList();
 }
+
+extern "C" void onb_set_p2p_tpt(int tpt) { const int t = tpt & 15; g_p2p_tpt = (t == 0 || t == 1 || t == 2 || t == 4) ? tpt : 0; }
 
 extern "C" double onb_measure_fp32_peak(onb_context* c) {
     if (!c) return -1.0;

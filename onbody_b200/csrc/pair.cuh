@@ -127,3 +127,73 @@ __device__ __forceinline__ void pair(const float4 p0, const float4 p1, const flo
 
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// packed FP32x2 pair functions (fast arithmetic only).
+// sm_100 adds add/mul/fma.f32x2 (SASS FADD2/FMUL2/FFMA2): one issue slot drives two FP32 lanes-ops per thread. The pair
+// loop is issue-bound with scalar ops (ncu: issue active 90 %, FMA pipe 66 %), so each thread carries its targets two
+// at a time in 64-bit register pairs; the source is broadcast into both halves. Per-lane arithmetic and its order are
+// exactly those of the scalar fast path, so results are bit-identical to it.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 mk2(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ f2 dup2(float a) { return mk2(a, a); }
+__device__ __forceinline__ float lo2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+// two targets: positions (px) and negated positions (nx) packed, squared target radius packed (vort2dtr)
+struct Tgt2 { f2 px, py, pz, nx, ny, nz, r2; };
+
+template <int PHYS>
+__device__ __forceinline__ void pair2(const float4 p0, const float4 p1, const float p2, const Tgt2& t, f2* __restrict__ u) {
+    if (PHYS == ONB_GRAV3D) {
+        const f2 dx = add2(dup2(p0.x), t.nx), dy = add2(dup2(p0.y), t.ny), dz = add2(dup2(p0.z), t.nz);
+        const f2 r2 = fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, dup2(p2))));
+        const f2 ri = mk2(rsqrt_approx(lo2(r2)), rsqrt_approx(hi2(r2)));
+        const f2 r3 = mul2(mul2(dup2(p0.w), ri), mul2(ri, ri));
+        u[0] = fma2(r3, dx, u[0]); u[1] = fma2(r3, dy, u[1]); u[2] = fma2(r3, dz, u[2]);
+    } else if (PHYS == ONB_VORT3D) {
+        const f2 dx = add2(dup2(p0.x), t.nx), dy = add2(dup2(p0.y), t.ny), dz = add2(dup2(p0.z), t.nz);
+        const f2 r2 = fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, dup2(p0.w))));
+        const f2 ri = mk2(rsqrt_approx(lo2(r2)), rsqrt_approx(hi2(r2)));
+        const f2 r3 = mul2(ri, mul2(ri, ri));
+        const f2 wx = dup2(p1.x), wy = dup2(p1.y), wz = dup2(p1.z), nwx = dup2(-p1.x), nwy = dup2(-p1.y), nwz = dup2(-p1.z);
+        const f2 dxxw = fma2(dz, wy, mul2(dy, nwz));
+        const f2 dyxw = fma2(dx, wz, mul2(dz, nwx));
+        const f2 dzxw = fma2(dy, wx, mul2(dx, nwy));
+        u[0] = fma2(r3, dxxw, u[0]); u[1] = fma2(r3, dyxw, u[1]); u[2] = fma2(r3, dzxw, u[2]);
+    } else if (PHYS == ONB_VORTGRAD3D) {
+        const f2 dx = add2(t.px, dup2(-p0.x)), dy = add2(t.py, dup2(-p0.y)), dz = add2(t.pz, dup2(-p0.z));
+        const f2 r2 = fma2(dx, dx, fma2(dy, dy, fma2(dz, dz, dup2(p0.w))));
+        const f2 ri = mk2(rsqrt_approx(lo2(r2)), rsqrt_approx(hi2(r2)));
+        const f2 ri2 = mul2(ri, ri);
+        const f2 r3 = mul2(ri, ri2);
+        const f2 bbb = mul2(mul2(dup2(-3.0f), r3), ri2);
+        const f2 wx = dup2(p1.x), wy = dup2(p1.y), wz = dup2(p1.z), nwx = dup2(-p1.x), nwy = dup2(-p1.y), nwz = dup2(-p1.z);
+        f2 dxxw = fma2(dz, wy, mul2(dy, nwz));
+        f2 dyxw = fma2(dx, wz, mul2(dz, nwx));
+        f2 dzxw = fma2(dy, wx, mul2(dx, nwy));
+        u[0] = fma2(r3, dxxw, u[0]); u[1] = fma2(r3, dyxw, u[1]); u[2] = fma2(r3, dzxw, u[2]);
+        dxxw = mul2(dxxw, bbb); dyxw = mul2(dyxw, bbb); dzxw = mul2(dzxw, bbb);
+        u[3]  = fma2(dx, dxxw, u[3]);
+        u[4]  = fma2(dx, dyxw, fma2(wz, r3, u[4]));
+        u[5]  = fma2(dx, dzxw, fma2(nwy, r3, u[5]));
+        u[6]  = fma2(dy, dxxw, fma2(nwz, r3, u[6]));
+        u[7]  = fma2(dy, dyxw, u[7]);
+        u[8]  = fma2(dy, dzxw, fma2(wx, r3, u[8]));
+        u[9]  = fma2(dz, dxxw, fma2(wy, r3, u[9]));
+        u[10] = fma2(dz, dyxw, fma2(nwx, r3, u[10]));
+        u[11] = fma2(dz, dzxw, u[11]);
+    } else {
+        const f2 dx = add2(t.px, dup2(-p0.x)), dy = add2(t.py, dup2(-p0.y));
+        f2 r2c = fma2(dx, dx, fma2(dy, dy, dup2(p0.z)));
+        if (Phys<PHYS>::TR) r2c = add2(r2c, t.r2);
+        const f2 rc = mk2(rcp_approx(lo2(r2c)), rcp_approx(hi2(r2c)));
+        const f2 r2 = mul2(dup2(p0.w), rc);
+        const f2 nr2 = mul2(dup2(-p0.w), rc);
+        u[0] = fma2(nr2, dy, u[0]); u[1] = fma2(r2, dx, u[1]);
+    }
+}
