@@ -72,6 +72,9 @@ ONB_API const char*  onb_last_create_error(void);
 
 /* block size (-b, default 128), barycentric order (-o, >=1) and arithmetic; call before set_sources */
 ONB_API int onb_set_params(onb_context* c, int block_size, int order, int arith);
+/* the per-pair flop constant used in the returned flop estimates (defaults: the drivers' nbody_kernel_flops();
+ * interface2dvorttr.cpp:53 counts 13 where onvort2d.cpp:57 counts 15 for the same kernel) */
+ONB_API void onb_set_flops_per_pair(onb_context* c, int flops);
 ONB_API void onb_dims(const onb_context* c, int* pd, int* sd, int* od, int* has_fastsumm);
 
 /* inputs (copies into the context's own device arrays; the pointers may be host memory - pinned for full PCIe

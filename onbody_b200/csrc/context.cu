@@ -183,6 +183,8 @@ int onb_set_params(onb_context* c, int block_size, int order, int arith) {
 
 void onb_dims(const onb_context* c, int* pd, int* sd, int* od, int* hf) { *pd = c->PD; *sd = c->SD; *od = c->OD; *hf = c->has_fastsumm; }
 
+void onb_set_flops_per_pair(onb_context* c, int flops) { if (c && flops > 0) c->flops_per_pair = flops; }
+
 int onb_set_shard(onb_context* c, int rank, int nranks) {
     if (nranks < 1 || rank < 0 || rank >= nranks) { c->err = "bad shard"; return ONB_ERR_ARG; }
     c->shard_rank = rank; c->shard_n = nranks; return ONB_OK;

@@ -39,6 +39,7 @@ inline float run(int physics, bool direct, float theta, int ns, const float* con
                  int nt, const float* const* tx, const float* tr, float* const* out, int OD) {
     onb_context* c = context(physics);
     if (!c) return fail(nullptr, "create");
+    if (physics == ONB_VORT2DTR) onb_set_flops_per_pair(c, 13);      // interface2dvorttr.cpp:53
     std::vector<float> x, s, t, r0, u;
     planar(x, ns, sx, PD); planar(s, ns, ss, SD); planar(t, nt, tx, PD);
     const float* trp = tr;
