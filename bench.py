@@ -21,7 +21,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -50,32 +49,43 @@ def pairs_estimate(n):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region: ONE nvidia-smi process looping at 200 ms
+    (the B200_PROFILING.md recipe) - spawning a process per sample perturbs the run it is watching."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.samples = []
-        self.stop_flag = False
+        self.proc = None
+        self.path = "/tmp/onb_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
 
-    def run(self):
-        while not self.stop_flag:
+    def start(self):
+        try:
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.out, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([c.strip() for c in out.split(",")])
+                self.proc.wait(timeout=3)
             except Exception:
-                pass
-            time.sleep(0.2)
+                self.proc.kill()
+            self.out.close()
 
     def summary(self):
         sm = []; smax = 0; reasons = set()
-        for s in self.samples:
+        try:
+            lines = open(self.path).read().splitlines()
+        except Exception:
+            lines = []
+        for line in lines:
+            s = [c.strip() for c in line.split(",")]
             try:
                 sm.append(float(s[0])); smax = max(smax, float(s[1]))
             except Exception:
@@ -228,9 +238,9 @@ def run_ours(args):
     phases.clear()
     l0 = g.launch_count()
     barrier()
-    t_res = 0.0
+    t_res = 0.0; res_steps = []
     for _ in range(args.steps):
-        t_res += step_resident()
+        res_steps.append(step_resident()); t_res += res_steps[-1]
     barrier()
     launches = g.launch_count() - l0
     ph_res = dict(phases)
@@ -238,12 +248,11 @@ def run_ours(args):
     # ---- timed: K end-to-end steps
     phases.clear()
     barrier()
-    t_e2e = 0.0
+    t_e2e = 0.0; e2e_steps = []
     for _ in range(args.steps):
-        t_e2e += step_e2e()
+        e2e_steps.append(step_e2e()); t_e2e += e2e_steps[-1]
     barrier()
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.stop()
 
     # max over ranks for times, sum for work
     red = torch.tensor([t_res, t_e2e, float(pairs_local), float(launches)], dtype=torch.float64, device="cuda")
@@ -279,7 +288,7 @@ def run_ours(args):
                    "theta": THETA, "order": ORDER, "block": BLOCK, "n_particles": N,
                    "parallelism": "target-tree sharded x%d, source side replicated" % world,
                    "l2_policy": "inputs larger than L2 (%.0f MB of particle planes per tree vs 126 MB L2); every step rebuilds from pristine input" % (N * 24 / 1e6)},
-        "seconds_per_step": sec_res, "seconds_per_eval": ph_res.get("eval", 0.0) / K * 1e-3, "pairs_per_step": pairs_total,
+        "seconds_per_step": sec_res, "ms_steps": [round(v, 2) for v in res_steps], "e2e_ms_steps": [round(v, 2) for v in e2e_steps], "seconds_per_eval": ph_res.get("eval", 0.0) / K * 1e-3, "pairs_per_step": pairs_total,
         "phases_ms": {k: v / K for k, v in ph_res.items()},
         "e2e": {"value": e2e, "unit": "Ginteractions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": sec_e2e * 1e3},
         "gpu_launches": launches_total,

@@ -45,10 +45,11 @@ __device__ __forceinline__ float bary_row(int PD, int ncp, const float* wk, cons
     return __fdiv_rn(1.0f, denom);
 }
 
+template <int PD, int SD>
 __global__ void __launch_bounds__(128) k_upward(const UpArgs a) {
     const uint32_t node = (1u << a.level) + blockIdx.x;
     if (a.t.num[node] <= a.block) return;                                                 // :266 leaves have no equivalents
-    const int tid = threadIdx.x, PD = a.PD, SD = a.SD, ncp = a.ncp, numEqps = a.numEqps;
+    const int tid = threadIdx.x, ncp = a.ncp, numEqps = a.numEqps;
     __shared__ float lsk[3 * (ONB_MAX_ORDER + 1)];
     __shared__ float s_am[128 * AM_STRIDE];
     __shared__ float s_den[128];
@@ -60,10 +61,14 @@ __global__ void __launch_bounds__(128) k_upward(const UpArgs a) {
     }
     // my equivalent point's Chebyshev indices
     int kd[3] = {0, 0, 0};
-    { int q = tid; for (int d = 0; d < PD; ++d) { kd[d] = q % ncp; q /= ncp; } }
+    { int q = tid;
+      #pragma unroll
+      for (int d = 0; d < PD; ++d) { kd[d] = q % ncp; q /= ncp; } }
+    const int o0 = kd[0], o1 = ncp + kd[1], o2 = 2 * ncp + kd[2];      // column of my 1-D weight in a contributor's row
     __syncthreads();
     if ((uint32_t)tid < a.ebs) {
         const float rr = a.p.r[a.t.ioffset[node]];                                        // :353
+        #pragma unroll
         for (int d = 0; d < PD; ++d)
             a.ep.x[d][e0 + tid] = tid < numEqps ? lsk[d * ncp + kd[d]] : a.t.nc[d][node]; // :330, :336
         a.ep.r[e0 + tid] = rr;
@@ -79,22 +84,30 @@ __global__ void __launch_bounds__(128) k_upward(const UpArgs a) {
         const int cnt = leaf ? (int)cn : numEqps;
         if (tid < cnt) {
             float px[3];
+            #pragma unroll
             for (int d = 0; d < PD; ++d) px[d] = sp.x[d][is + tid];
             s_den[tid] = bary_row(PD, ncp, a.ch.wk, px, lsk, &s_am[tid * AM_STRIDE]);
+            #pragma unroll
             for (int d = 0; d < SD; ++d) s_str[d][tid] = sp.s[d][is + tid];
         }
         __syncthreads();
         if (tid < numEqps) {
+            #pragma unroll 4
             for (int j = 0; j < cnt; ++j) {                                               // :190, :228-241
                 const float* row = &s_am[j * AM_STRIDE];
-                float wgt = s_den[j];
-                for (int d = 0; d < PD; ++d) wgt = __fmul_rn(wgt, row[d * ncp + kd[d]]);
+                float wgt = __fmul_rn(s_den[j], row[o0]);
+                if (PD > 1) wgt = __fmul_rn(wgt, row[o1]);
+                if (PD > 2) wgt = __fmul_rn(wgt, row[o2]);
+                #pragma unroll
                 for (int d = 0; d < SD; ++d) acc[d] = __fadd_rn(acc[d], __fmul_rn(wgt, s_str[d][j]));
             }
         }
         __syncthreads();
     }
-    if ((uint32_t)tid < a.ebs) for (int d = 0; d < SD; ++d) a.ep.s[d][e0 + tid] = tid < numEqps ? acc[d] : 0.0f;
+    if ((uint32_t)tid < a.ebs) {
+        #pragma unroll
+        for (int d = 0; d < SD; ++d) a.ep.s[d][e0 + tid] = tid < numEqps ? acc[d] : 0.0f;
+    }
 }
 
 // ---- downward: zero-fill + interpolation from the parent, one CTA per target node of this level ----
@@ -103,13 +116,14 @@ struct DownArgs {
     uint32_t block, ebs, shard_lo, shard_hi; int level, PD, OD, ncp, numEqps;
 };
 
+template <int PD, int OD>
 __global__ void __launch_bounds__(128) k_downward(const DownArgs a) {
     const uint32_t T = (1u << a.level) + blockIdx.x;
     const uint32_t tn = a.t.num[T];
     if (tn < 1) return;                                                                   // ongrav3d.cpp:221
     const uint32_t tio = a.t.ioffset[T];
     if (!(tio < a.shard_hi && tio + tn > a.shard_lo)) return;                             // not needed by this shard
-    const int tid = threadIdx.x, PD = a.PD, OD = a.OD, ncp = a.ncp, numEqps = a.numEqps;
+    const int tid = threadIdx.x, ncp = a.ncp, numEqps = a.numEqps;
     const bool leaf = tn <= a.block;
     const PartsView& tp = leaf ? a.tl : a.tb;
     const uint32_t p0 = leaf ? tio : T * a.ebs;
@@ -133,10 +147,12 @@ __global__ void __launch_bounds__(128) k_downward(const DownArgs a) {
             float* row = &s_am[tid * AM_STRIDE];
             const float denom = bary_row(PD, ncp, a.ch.wk, px, lsk, row);
             int k0 = 0, k1 = 0, k2 = 0;
+            #pragma unroll 5
             for (int i = 0; i < numEqps; ++i) {                                           // :140-156
                 float wgt = __fmul_rn(denom, row[k0]);
                 if (PD > 1) wgt = __fmul_rn(wgt, row[ncp + k1]);
                 if (PD > 2) wgt = __fmul_rn(wgt, row[2 * ncp + k2]);
+                #pragma unroll
                 for (int d = 0; d < OD; ++d) acc[d] = __fadd_rn(acc[d], __fmul_rn(wgt, s_pu[d][i]));
                 if (++k0 == ncp) { k0 = 0; if (++k1 == ncp) { k1 = 0; ++k2; } }
             }
@@ -170,7 +186,11 @@ int onb_bary_upward(onb_context* c, DParts& p, DParts& ep, DTree& t) {
     a.are_sources = p.are_sources ? 1 : 0;
     for (int lev = t.levels - 2; lev >= 0; --lev) {      // the last level holds only leaves
         a.level = lev;
-        k_upward<<<1u << lev, 128, 0, c->stream>>>(a); ONB_LAUNCH(c);
+        const uint32_t G = 1u << lev;
+        if (c->PD == 3 && c->SD == 1) k_upward<3, 1><<<G, 128, 0, c->stream>>>(a);
+        else if (c->PD == 3) k_upward<3, 3><<<G, 128, 0, c->stream>>>(a);
+        else k_upward<2, 1><<<G, 128, 0, c->stream>>>(a);
+        ONB_LAUNCH(c);
     }
     ONB_CUDA(cudaGetLastError());
     ep.packed_valid = false;
@@ -183,7 +203,9 @@ int onb_bary_downward_level(onb_context* c, int level) {
     a.block = c->block; a.ebs = c->ebs; a.level = level; a.PD = c->PD; a.OD = c->OD; a.ncp = c->ncp; a.numEqps = c->num_eqps;
     // shard range in particle indices (contiguous target leaves)
     onb_shard_range(c, &a.shard_lo, &a.shard_hi);
-    k_downward<<<1u << level, 128, 0, c->stream>>>(a); ONB_LAUNCH(c);
+    if (c->PD == 3) k_downward<3, 3><<<1u << level, 128, 0, c->stream>>>(a);
+    else k_downward<2, 2><<<1u << level, 128, 0, c->stream>>>(a);
+    ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
     return ONB_OK;
 }

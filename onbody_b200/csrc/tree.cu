@@ -432,7 +432,7 @@ extern "C" int onb_get_build_stats(onb_context* c, uint64_t out[5]) {
 static int onb_pivot_mode = 0;   // 0 = the reference source evaluated in IEEE order; 1 = as g++ -O3 -ffast-math contracts it
 extern "C" void onb_set_pivot_mode(int mode) { onb_pivot_mode = mode ? 1 : 0; }
 
-static const uint32_t BIG_NODE = 32768;     // nodes above this are split by the grid-wide kernels of tree_big.cuh
+static const uint32_t BIG_NODE = 16384;     // nodes above this are split by the grid-wide kernels of tree_big.cuh
 
 int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
     const uint32_t n = p.n;
@@ -511,9 +511,10 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
         for (int d = 0; d < 3; ++d) sa.x[d] = cx[d];
         sa.t = view_of(t); sa.axis_of = axis_of; sa.pmid = pmid; sa.lidx = lidx; sa.scr = scr; sa.stats = c->d_build_stats;
         sa.block = c->block; sa.big = BIG_NODE; sa.level = lev; sa.PD = PD; sa.pivot_mode = onb_pivot_mode;
+        // ~8 particles per thread: small nodes get small CTAs so that several share an SM and hide each other's barriers
         int threads = 1024;
         const uint32_t largest_small = std::min(leftmost, BIG_NODE);
-        while (threads > 128 && (uint32_t)threads * 2 > largest_small) threads >>= 1;
+        while (threads > 64 && (uint32_t)threads * 8 > largest_small) threads >>= 1;
         k_node_split<<<1u << lev, threads, 0, c->stream>>>(sa); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
         if (leftmost <= (uint32_t)c->block) break;     // every node of this level is a leaf: nothing below
