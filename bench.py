@@ -50,52 +50,65 @@ def pairs_estimate(n):
 
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region: ONE nvidia-smi process looping at 200 ms
-    (the B200_PROFILING.md recipe) - spawning a process per sample perturbs the run it is watching."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, read in-process through NVML every 100 ms (the fields
+    of the B200_PROFILING.md clocks line). An external `nvidia-smi -lms` loop was measured to stall the step it was
+    watching by hundreds of ms on this driver, so it is only the fallback when pynvml is unavailable."""
 
     def __init__(self, gpu_index):
+        import threading
         self.gpu = gpu_index
-        self.proc = None
-        self.path = "/tmp/onb_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
+        self.samples = []        # (sm_mhz, sm_max_mhz, reasons_bitmask)
+        self.stop_flag = False
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = gpu_index
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _run(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                if n is not None:
+                    sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    self.samples.append((float(sm), float(mx), int(rs)))
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip().split(",")
+                    self.samples.append((float(out[0]), float(out[1]), 0))
+            except Exception:
+                pass
+            time.sleep(0.1 if n is not None else 1.0)
 
     def start(self):
-        try:
-            self.out = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=self.out, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        self.thread.start()
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=3)
-            except Exception:
-                self.proc.kill()
-            self.out.close()
+        self.stop_flag = True
+        self.thread.join(timeout=3)
 
     def summary(self):
-        sm = []; smax = 0; reasons = set()
-        try:
-            lines = open(self.path).read().splitlines()
-        except Exception:
-            lines = []
-        for line in lines:
-            s = [c.strip() for c in line.split(",")]
-            try:
-                sm.append(float(s[0])); smax = max(smax, float(s[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        sm = [s[0] for s in self.samples]; smax = max([s[1] for s in self.samples], default=0)
+        bits = 0
+        for s in self.samples:
+            bits |= s[2]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = sorted(v for k, v in names.items() if bits & k)
         busy = [v for v in sm if v > 0.5 * smax] or sm
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": smax or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peaks():

@@ -87,6 +87,15 @@ ONB_API int onb_driver_inputs(int physics, uint64_t n, int strength_mode, float*
 
 /* phases ------------------------------------------------------------------------------------- */
 ONB_API int onb_make_tree(onb_context* c, int which);
+/* multi-GPU: build only the part of the tree that overlaps the tree-order particle range [lo,hi) (leaf aligned, see
+ * onb_shard_particle_range). Ancestors of the range are split in full, siblings outside it are left unsorted; the node
+ * index/count arrays are complete (they depend on n and the block size only). For TARGETS that is all a rank needs.
+ * For SOURCES the ranks then exchange their ranges of the particle planes (onb_device_ptr + an NCCL all-gather issued by
+ * the host language) and call onb_finish_tree, which recomputes every node array bottom-up, bit-identical to a full build. */
+ONB_API int onb_make_tree_range(onb_context* c, int which, uint64_t lo, uint64_t hi);
+ONB_API int onb_finish_tree(onb_context* c, int which);
+/* the tree-order particle range of shard `rank` of `nranks` for a set of n particles (contiguous leaves) */
+ONB_API int onb_shard_particle_range(const onb_context* c, uint64_t n, int rank, int nranks, uint64_t* lo, uint64_t* hi);
 ONB_API int onb_refine(onb_context* c, int which);
 ONB_API int onb_upward(onb_context* c, int which);
 ONB_API int onb_zero_vels(onb_context* c);

@@ -54,6 +54,11 @@ def load_library():
     L.onb_driver_inputs.argtypes = [C.c_int, C.c_uint64, C.c_int, _f32p, _f32p, _f32p]
     for fn in ("onb_make_tree", "onb_refine", "onb_upward"):
         getattr(L, fn).argtypes = [C.c_void_p, C.c_int]
+    L.onb_make_tree_range.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
+    L.onb_finish_tree.argtypes = [C.c_void_p, C.c_int]
+    L.onb_shard_particle_range.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, _u64p, _u64p]
+    L.onb_device_ptr.restype = C.c_void_p
+    L.onb_device_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.onb_zero_vels.argtypes = [C.c_void_p]
     L.onb_naive.argtypes = [C.c_void_p, C.c_uint64, _f32p]
     for fn in ("onb_treecode1", "onb_treecode2", "onb_treecode3"):
@@ -172,6 +177,31 @@ class GpuSession:
 
     # ---- phases
     def make_tree(self, which): self._chk(self.lib.onb_make_tree(self.h, which))
+    def make_tree_range(self, which, lo, hi): self._chk(self.lib.onb_make_tree_range(self.h, which, lo, hi))
+    def finish_tree(self, which): self._chk(self.lib.onb_finish_tree(self.h, which))
+
+    def shard_particle_range(self, n, rank, nranks):
+        lo, hi = C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.onb_shard_particle_range(self.h, n, rank, nranks, C.byref(lo), C.byref(hi)))
+        return int(lo.value), int(hi.value)
+
+    def device_ptr(self, which, field):
+        """raw device pointer of a particle plane (field 0..2 x[d], 3 r, 4..6 s[d]) for zero-copy collectives"""
+        return self.lib.onb_device_ptr(self.h, which, field)
+
+    def plane_tensor(self, which, field, n):
+        """the plane as a torch CUDA tensor aliasing the library's memory (plumbing for torch.distributed collectives)"""
+        import torch
+
+        class _P:
+            pass
+        p = _P()
+        p.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(self.device_ptr(which, field)), False), "version": 2}
+        return torch.as_tensor(p, device="cuda")
+
+    def source_fields(self):
+        return list(range(self.PD)) + [3] + [4 + d for d in range(self.SD)]
+
     def refine(self, which): self._chk(self.lib.onb_refine(self.h, which))
     def upward(self, which): self._chk(self.lib.onb_upward(self.h, which))
     def zero_vels(self): self._chk(self.lib.onb_zero_vels(self.h))

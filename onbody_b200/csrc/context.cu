@@ -18,7 +18,7 @@ static std::string g_create_error;
 // ---------------------------------------------------------------------------------------------
 int onb_alloc_parts(onb_context* c, DParts& p, uint32_t n, bool are_sources) {
     p = DParts();
-    p.n = n; p.cap = ((n + 63u) & ~31u) + 32u; p.PD = c->PD; p.SD = c->SD; p.OD = c->OD; p.are_sources = are_sources;
+    p.n = n; p.cap = ((n + 63u) & ~31u) + 288u;      // slack: bulk copies round up to 16 B, padded all-gathers overrun by < one leaf p.PD = c->PD; p.SD = c->SD; p.OD = c->OD; p.are_sources = are_sources;
     const size_t bytes = (size_t)p.cap * sizeof(float);
     for (int d = 0; d < c->PD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.x[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.x[d], 0, bytes, c->stream)); }
     ONB_CUDA(onb_pmalloc(c, (void**)&p.r, bytes)); ONB_CUDA(cudaMemsetAsync(p.r, 0, bytes, c->stream));
@@ -232,16 +232,33 @@ int onb_driver_inputs(int physics, uint64_t n, int strength_mode, float* x, floa
 // ---------------------------------------------------------------------------------------------
 // phases
 // ---------------------------------------------------------------------------------------------
-int onb_make_tree(onb_context* c, int which) {
+int onb_make_tree_range(onb_context* c, int which, uint64_t lo, uint64_t hi) {
     onb_scratch_reset(c);
     if (which < 0 || which > 1 || c->parts[which].n == 0) { c->err = "make_tree: set the particles first"; return ONB_ERR_ARG; }
     ONB_CUDA(cudaSetDevice(c->device));
     int rc = onb_alloc_tree(c, c->trees[which], c->parts[which].n, c->block);
     if (rc) return rc;
     PhaseTimer tm(c, "tree");
-    rc = onb_tree_build(c, c->parts[which], c->trees[which]);
+    rc = onb_tree_build(c, c->parts[which], c->trees[which], (uint32_t)lo, (uint32_t)std::min<uint64_t>(hi, c->parts[which].n));
     tm.stop();
     return rc;
+}
+int onb_make_tree(onb_context* c, int which) { return onb_make_tree_range(c, which, 0, ~0ull); }
+int onb_finish_tree(onb_context* c, int which) {
+    onb_scratch_reset(c);
+    if (which < 0 || which > 1) return ONB_ERR_ARG;
+    ONB_CUDA(cudaSetDevice(c->device));
+    PhaseTimer tm(c, "finish");
+    int rc = onb_tree_finish_from_particles(c, c->parts[which], c->trees[which]);
+    tm.stop();
+    return rc;
+}
+int onb_shard_particle_range(const onb_context* c, uint64_t n, int rank, int nranks, uint64_t* lo, uint64_t* hi) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) return ONB_ERR_ARG;
+    const uint64_t nleaf = (n + c->block - 1) / c->block;
+    *lo = std::min<uint64_t>((nleaf * (uint64_t)rank / (uint64_t)nranks) * c->block, n);
+    *hi = std::min<uint64_t>((nleaf * (uint64_t)(rank + 1) / (uint64_t)nranks) * c->block, n);
+    return ONB_OK;
 }
 int onb_refine(onb_context* c, int which) {
     onb_scratch_reset(c);

@@ -42,6 +42,7 @@ struct DParts {
     float4* pk1 = nullptr;
     float*  pk2 = nullptr;
     bool packed_valid = false;
+    uint32_t build_lo = 0, build_hi = 0;     // particle range the last tree build was restricted to
 };
 
 struct DTree {
@@ -163,7 +164,8 @@ void onb_free_tree(onb_context* c, DTree& t);
 int onb_check_flag(onb_context* c, const char* what);
 void onb_shard_range(const onb_context* c, uint32_t* lo, uint32_t* hi);   // particle index range of this context's target shard
 // tree.cu
-int onb_tree_build(onb_context* c, DParts& p, DTree& t);
+int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t bhi);
+int onb_tree_finish_from_particles(onb_context* c, DParts& p, DTree& t);
 int onb_tree_refine(onb_context* c, DParts& p, DTree& t);
 // bary.cu
 int onb_bary_upward(onb_context* c, DParts& p, DParts& ep, DTree& t);

@@ -52,6 +52,7 @@ struct SplitArgs {
     uint32_t* scr;          // per particle scratch for the ordered compactions
     unsigned long long* stats;   // selects, passes, stalls, scanned
     uint32_t block, big;    // nodes with more than `big` particles are split by the grid-wide kernels below
+    uint32_t blo, bhi;      // build range: only nodes overlapping particles [blo,bhi) are split (multi-GPU: each rank its share)
     int level, PD, pivot_mode;
 };
 
@@ -61,8 +62,18 @@ constexpr int SPLIT_ROUNDS = 4;   // each warp handles 4 x 32 consecutive elemen
 __global__ void __launch_bounds__(1024) k_node_split(const SplitArgs a) {
     const uint32_t node = (1u << a.level) + blockIdx.x;
     const uint32_t n = a.t.num[node];
-    if (n == 0 || n > a.big) return;
+    if (n == 0) return;
     const uint32_t pf = a.t.ioffset[node], pl = pf + n;
+    if (!(pf < a.bhi && pl > a.blo)) {
+        // outside this rank's build range: not sorted here, but the shape of the tree below it is data independent
+        if (threadIdx.x == 0 && n > a.block) {
+            const uint32_t pm = pf + a.block * (1u << log_2((n - 1) / a.block));
+            a.t.ioffset[2 * node] = pf;     a.t.num[2 * node] = pm - pf;
+            a.t.ioffset[2 * node + 1] = pm; a.t.num[2 * node + 1] = pl - pm;
+        }
+        return;
+    }
+    if (n > a.big) return;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
 
     __shared__ float s_min[32], s_max[32];
@@ -194,14 +205,15 @@ struct GatherArgs {
     float* sx[3]; float* sr; float* ss[3]; uint32_t* sg;     // current
     float* dx[3]; float* dr; float* ds[3]; uint32_t* dg;     // destination
     const uint32_t* lidx; uint32_t* owner;
-    const uint8_t* axis_of; const uint32_t* pmid; const uint32_t* num;
-    uint32_t n, block; int level, PD, SD;
+    const uint8_t* axis_of; const uint32_t* pmid; const uint32_t* num; const uint32_t* ioffset;
+    uint32_t n, block, blo, bhi, span_lo; int level, PD, SD;
 };
 __global__ void k_gather(const GatherArgs a) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = a.span_lo + blockIdx.x * blockDim.x + threadIdx.x;      // n = end of the span covered at this level
     if (i >= a.n) return;
     const uint32_t node = a.owner[i];
-    const bool active = node >= (1u << a.level) && a.num[node] > a.block;
+    bool active = node >= (1u << a.level) && a.num[node] > a.block;
+    if (active) { const uint32_t pf = a.ioffset[node]; active = pf < a.bhi && pf + a.num[node] > a.blo; }
     const uint32_t j = active ? a.lidx[i] : i;
     const int ax = active ? (int)a.axis_of[node] : -1;
     for (int d = 0; d < a.PD; ++d) a.dx[d][i] = a.sx[d][d == ax ? i : j];
@@ -334,10 +346,10 @@ __device__ bool dev_libstdcxx_sort(int* first, int* last, IdxKey K) {
     return ok;
 }
 
-struct RefineArgs { PartsView p; uint32_t n, block; int PD, SD, OD, are_sources; int* flag; unsigned long long* tie_sorts; };
+struct RefineArgs { PartsView p; uint32_t n, block, leaf0; int PD, SD, OD, are_sources; int* flag; unsigned long long* tie_sorts; };
 
 __global__ void __launch_bounds__(128) k_refine(const RefineArgs a) {
-    const uint32_t pf = blockIdx.x * a.block;
+    const uint32_t pf = (a.leaf0 + blockIdx.x) * a.block;
     const int n = (int)min(a.block, a.n - pf);
     const int tid = threadIdx.x;
     __shared__ float sx[3][128];
@@ -407,10 +419,51 @@ __global__ void __launch_bounds__(128) k_refine(const RefineArgs a) {
     }
 }
 
+// ---- bottom-up bounding boxes (multi-GPU: after the exchange of a range-restricted build) ----
+__global__ void k_bbox_leaves(const FinishArgs a, float* lohi) {
+    const uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (node >= (uint32_t)a.t.numnodes || node == 0) return;
+    const uint32_t n = a.t.num[node];
+    if (n == 0 || n > a.block) return;
+    const uint32_t pf = a.t.ioffset[node], pl = pf + n;
+    const size_t nn = a.t.numnodes;
+    for (int d = 0; d < a.PD; ++d) {
+        float lo = INFINITY, hi = -INFINITY;
+        for (uint32_t i = pf + lane; i < pl; i += 32) { const float v = a.p.x[d][i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        lo = warp_min(lo); hi = warp_max(hi);
+        if (lane == 0) { lohi[(size_t)(2 * d) * nn + node] = lo; lohi[(size_t)(2 * d + 1) * nn + node] = hi; }
+    }
+}
+__global__ void k_bbox_parents(const FinishArgs a, float* lohi, int level) {
+    const uint32_t node = (1u << level) + blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= (2u << level)) return;
+    if (a.t.num[node] <= a.block) return;
+    const size_t nn = a.t.numnodes;
+    for (int d = 0; d < a.PD; ++d) {
+        lohi[(size_t)(2 * d) * nn + node] = fminf(lohi[(size_t)(2 * d) * nn + 2 * node], lohi[(size_t)(2 * d) * nn + 2 * node + 1]);
+        lohi[(size_t)(2 * d + 1) * nn + node] = fmaxf(lohi[(size_t)(2 * d + 1) * nn + 2 * node], lohi[(size_t)(2 * d + 1) * nn + 2 * node + 1]);
+    }
+}
+__global__ void k_bbox_final(const FinishArgs a, const float* lohi) {
+    const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node == 0 || node >= (uint32_t)a.t.numnodes || a.t.num[node] == 0) return;
+    const size_t nn = a.t.numnodes;
+    float bsss = 0.0f;
+    for (int d = 0; d < a.PD; ++d) {
+        const float lo = lohi[(size_t)(2 * d) * nn + node], hi = lohi[(size_t)(2 * d + 1) * nn + node];
+        const float ns = __fsub_rn(hi, lo);
+        a.t.ns[d][node] = ns;
+        a.t.nc[d][node] = __fmul_rn(0.5f, __fadd_rn(hi, lo));
+        bsss = __double2float_rn(__dadd_rn((double)bsss, __dmul_rn((double)ns, (double)ns)));
+    }
+    a.t.nr[node] = __fmul_rn(0.5f, __fsqrt_rn(bsss));
+}
+
 #include "tree_big.cuh"
 
 __global__ void k_copy_planes(GatherArgs a) {     // final buffers -> the particle set's own planes (identity gather)
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = a.span_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     for (int d = 0; d < a.PD; ++d) a.dx[d][i] = a.sx[d][i];
     a.dr[i] = a.sr[i];
@@ -434,8 +487,23 @@ extern "C" void onb_set_pivot_mode(int mode) { onb_pivot_mode = mode ? 1 : 0; }
 
 static const uint32_t BIG_NODE = 16384;     // nodes above this are split by the grid-wide kernels of tree_big.cuh
 
-int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
+static int run_finish(onb_context* c, DParts& p, DTree& t) {      // finishTree :717-807
+    FinishArgs fa; fa.p = view_of(p); fa.t = view_of(t); fa.block = c->block; fa.PD = c->PD; fa.SD = c->SD; fa.are_sources = p.are_sources ? 1 : 0;
+    k_finish_leaves<<<((size_t)t.numnodes * 32 + 255) / 256, 256, 0, c->stream>>>(fa); ONB_LAUNCH(c);
+    ONB_CUDA(cudaGetLastError());
+    for (int lev = t.levels - 2; lev >= 0; --lev) {
+        const uint32_t nn = 1u << lev;
+        k_finish_parents<<<(nn + 127) / 128, 128, 0, c->stream>>>(fa, lev); ONB_LAUNCH(c);
+    }
+    ONB_CUDA(cudaGetLastError());
+    return ONB_OK;
+}
+
+int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t bhi) {
     const uint32_t n = p.n;
+    if (bhi > n) bhi = n;
+    if (blo >= bhi) { c->err = "make_tree: empty build range"; return ONB_ERR_ARG; }
+    p.build_lo = blo; p.build_hi = bhi;
     const int PD = c->PD, SD = p.are_sources ? c->SD : 0;
     if (n == 0) { c->err = "make_tree: no particles"; return ONB_ERR_ARG; }
     ONB_CUDA(cudaMemsetAsync(c->d_build_stats, 0, 4 * sizeof(unsigned long long), c->stream));
@@ -475,6 +543,8 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
     float* ax[3] = { alt_x[0], alt_x[1], alt_x[2] }; float* ar = alt_r; float* as[3] = { alt_s[0], alt_s[1], alt_s[2] }; uint32_t* ag = alt_g;
 
     uint32_t leftmost = n;     // the leftmost node of a level is its largest
+    // the nodes of this level that contain the first / last particle of the build range: [spf, epl) is what this level touches
+    uint32_t spf = 0, spl = n, epf = 0, epl = n;
     for (int lev = 0; lev < t.levels; ++lev) {
         if (leftmost > BIG_NODE) {
             BigArgs ba;
@@ -482,6 +552,7 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
             ba.t = view_of(t); ba.nodes = bignodes; ba.nbig = nbig; ba.chunk_owner = chunk_owner; ba.cntA = cntA; ba.cntB = cntB;
             ba.lidx = lidx; ba.scr = scr; ba.axis_of = axis_of; ba.pmid = pmid; ba.stats = c->d_build_stats;
             ba.block = c->block; ba.big = BIG_NODE; ba.level = lev; ba.PD = PD; ba.pivot_mode = onb_pivot_mode; ba.it = 0;
+            ba.blo = blo; ba.bhi = bhi;
             const uint32_t lev_nodes = std::min<uint64_t>(1ull << lev, max_big_nodes);
             ba.max_nodes = lev_nodes; ba.max_chunks = max_chunks;
             const uint32_t chunks_ub = std::min<uint32_t>(max_chunks, n / BIG_CH + lev_nodes + 1);
@@ -510,7 +581,7 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
         SplitArgs sa;
         for (int d = 0; d < 3; ++d) sa.x[d] = cx[d];
         sa.t = view_of(t); sa.axis_of = axis_of; sa.pmid = pmid; sa.lidx = lidx; sa.scr = scr; sa.stats = c->d_build_stats;
-        sa.block = c->block; sa.big = BIG_NODE; sa.level = lev; sa.PD = PD; sa.pivot_mode = onb_pivot_mode;
+        sa.block = c->block; sa.big = BIG_NODE; sa.blo = blo; sa.bhi = bhi; sa.level = lev; sa.PD = PD; sa.pivot_mode = onb_pivot_mode;
         // ~8 particles per thread: small nodes get small CTAs so that several share an SM and hide each other's barriers
         int threads = 1024;
         const uint32_t largest_small = std::min(leftmost, BIG_NODE);
@@ -521,35 +592,51 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t) {
         GatherArgs ga;
         for (int d = 0; d < 3; ++d) { ga.sx[d] = cx[d]; ga.dx[d] = ax[d]; ga.ss[d] = cs[d]; ga.ds[d] = as[d]; }
         ga.sr = cr; ga.dr = ar; ga.sg = cg; ga.dg = ag;
-        ga.lidx = lidx; ga.owner = owner; ga.axis_of = axis_of; ga.pmid = pmid; ga.num = t.num;
-        ga.n = n; ga.block = c->block; ga.level = lev; ga.PD = PD; ga.SD = SD;
-        k_gather<<<GB, TB, 0, c->stream>>>(ga); ONB_LAUNCH(c);
+        ga.lidx = lidx; ga.owner = owner; ga.axis_of = axis_of; ga.pmid = pmid; ga.num = t.num; ga.ioffset = t.ioffset;
+        ga.n = epl; ga.span_lo = spf; ga.blo = blo; ga.bhi = bhi; ga.block = c->block; ga.level = lev; ga.PD = PD; ga.SD = SD;
+        k_gather<<<(epl - spf + TB - 1) / TB, TB, 0, c->stream>>>(ga); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
         for (int d = 0; d < 3; ++d) { std::swap(cx[d], ax[d]); std::swap(cs[d], as[d]); }
         std::swap(cr, ar); std::swap(cg, ag);
         leftmost = (uint32_t)c->block * (1u << (31 - __builtin_clz((leftmost - 1) / c->block)));
+        // descend the two boundary nodes (the split position of a node depends on its size only, barneshut.hpp:663)
+        if (spl - spf > (uint32_t)c->block) { const uint32_t pm = spf + (uint32_t)c->block * (1u << (31 - __builtin_clz((spl - spf - 1) / c->block))); if (blo < pm) spl = pm; else spf = pm; }
+        if (epl - epf > (uint32_t)c->block) { const uint32_t pm = epf + (uint32_t)c->block * (1u << (31 - __builtin_clz((epl - epf - 1) / c->block))); if (bhi - 1 < pm) epl = pm; else epf = pm; }
     }
     // after an odd number of levels the final order sits in the scratch copies: bring it home
     if (cr != p.r) {
         GatherArgs ga;
         for (int d = 0; d < 3; ++d) { ga.sx[d] = cx[d]; ga.dx[d] = p.x[d]; ga.ss[d] = cs[d]; ga.ds[d] = p.s[d]; }
-        ga.sr = cr; ga.dr = p.r; ga.n = n; ga.PD = PD; ga.SD = SD;
-        k_copy_planes<<<GB, TB, 0, c->stream>>>(ga); ONB_LAUNCH(c);
-        if (!p.are_sources) ONB_CUDA(cudaMemcpyAsync(p.gidx, cg, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+        ga.sr = cr; ga.dr = p.r; ga.n = epl; ga.span_lo = spf; ga.PD = PD; ga.SD = SD;
+        k_copy_planes<<<(epl - spf + TB - 1) / TB, TB, 0, c->stream>>>(ga); ONB_LAUNCH(c);
+        if (!p.are_sources) ONB_CUDA(cudaMemcpyAsync(p.gidx + spf, cg + spf, (size_t)(epl - spf) * 4, cudaMemcpyDeviceToDevice, c->stream));
     }
     p.packed_valid = false;
 
-    // finishTree
-    FinishArgs fa; fa.p = view_of(p); fa.t = view_of(t); fa.block = c->block; fa.PD = PD; fa.SD = c->SD; fa.are_sources = p.are_sources ? 1 : 0;
-    k_finish_leaves<<<((size_t)t.numnodes * 32 + 255) / 256, 256, 0, c->stream>>>(fa); ONB_LAUNCH(c);
-    ONB_CUDA(cudaGetLastError());
-    for (int lev = t.levels - 2; lev >= 0; --lev) {
-        const uint32_t nn = 1u << lev;
-        k_finish_parents<<<(nn + 127) / 128, 128, 0, c->stream>>>(fa, lev); ONB_LAUNCH(c);
-    }
-    ONB_CUDA(cudaGetLastError());
+    int rc = run_finish(c, p, t);
+    if (rc) return rc;
     t.built = true;
     return ONB_OK;
+}
+
+// Recompute EVERY node array bottom-up from complete, tree-ordered particle planes (after the ranks of a multi-GPU
+// run have exchanged their shares of a range-restricted build). Tight boxes are exact min/max, so leaf boxes from the
+// particles and parent boxes as the union of the children give bit-identical nc/ns/nr to the top-down build.
+int onb_tree_finish_from_particles(onb_context* c, DParts& p, DTree& t) {
+    if (!t.built) { c->err = "finish_tree: build the tree first"; return ONB_ERR_ARG; }
+    float* lohi = nullptr;
+    ONB_CUDA(onb_dmalloc(c, (void**)&lohi, (size_t)6 * t.numnodes * sizeof(float)));
+    FinishArgs fa; fa.p = view_of(p); fa.t = view_of(t); fa.block = c->block; fa.PD = c->PD; fa.SD = c->SD; fa.are_sources = p.are_sources ? 1 : 0;
+    k_bbox_leaves<<<((size_t)t.numnodes * 32 + 255) / 256, 256, 0, c->stream>>>(fa, lohi); ONB_LAUNCH(c);
+    for (int lev = t.levels - 2; lev >= 0; --lev) {
+        const uint32_t nn = 1u << lev;
+        k_bbox_parents<<<(nn + 127) / 128, 128, 0, c->stream>>>(fa, lohi, lev); ONB_LAUNCH(c);
+    }
+    k_bbox_final<<<(t.numnodes + 127) / 128, 128, 0, c->stream>>>(fa, lohi); ONB_LAUNCH(c);
+    ONB_CUDA(cudaGetLastError());
+    p.build_lo = 0; p.build_hi = p.n;
+    p.packed_valid = false;
+    return run_finish(c, p, t);
 }
 
 int onb_tree_refine(onb_context* c, DParts& p, DTree& t) {
@@ -558,8 +645,10 @@ int onb_tree_refine(onb_context* c, DParts& p, DTree& t) {
     ONB_CUDA(cudaMemsetAsync(c->d_build_stats + 4, 0, sizeof(unsigned long long), c->stream));
     RefineArgs ra; ra.p = view_of(p); ra.n = p.n; ra.block = c->block; ra.PD = c->PD; ra.SD = c->SD; ra.OD = c->OD;
     ra.are_sources = p.are_sources ? 1 : 0; ra.flag = c->d_flag; ra.tie_sorts = c->d_build_stats + 4;
-    const uint32_t nleaf = (p.n + c->block - 1) / c->block;
-    k_refine<<<nleaf, 128, 0, c->stream>>>(ra); ONB_LAUNCH(c);
+    // leaves of the build range only (whole tree unless onb_make_tree_range restricted it; ranges are leaf aligned)
+    const uint32_t leaf0 = p.build_lo / c->block, leaf1 = (std::min(p.build_hi, p.n) + c->block - 1) / c->block;
+    ra.leaf0 = leaf0;
+    k_refine<<<leaf1 - leaf0, 128, 0, c->stream>>>(ra); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
     p.packed_valid = false;
     return onb_check_flag(c, "refine (introsort depth limit: libstdc++ heapsort fallback is not restated)");

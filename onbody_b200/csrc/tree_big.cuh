@@ -40,7 +40,7 @@ struct BigArgs {
     uint32_t* lidx; uint32_t* scr;
     uint8_t* axis_of; uint32_t* pmid;
     unsigned long long* stats;
-    uint32_t block, big, max_nodes, max_chunks; int level, PD, pivot_mode, it;
+    uint32_t block, big, max_nodes, max_chunks, blo, bhi; int level, PD, pivot_mode, it;
 };
 
 // one block: list the big nodes of this level (node order) and lay out their chunks
@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(256) k_big_list(const BigArgs a) {
         uint32_t nb = 0, nc = 0;
         for (uint32_t node = first; node < last; ++node) {
             const uint32_t n = a.t.num[node];
-            if (n > a.big && nb < a.max_nodes) {
+            const uint32_t pf0 = a.t.ioffset[node];
+            if (n > a.big && nb < a.max_nodes && pf0 < a.bhi && pf0 + n > a.blo) {
                 BigNode& b = a.nodes[nb];
                 b.node = node; b.pf = a.t.ioffset[node]; b.pl = b.pf + n; b.chunk0 = nc; b.nchunks = (n + BIG_CH - 1) / BIG_CH;
                 for (int d = 0; d < 3; ++d) { b.bmin[d] = 0xffffffffu; b.bmax[d] = 0u; }

@@ -1,0 +1,48 @@
+"""Host-side plumbing of the multi-GPU source build: each rank builds its share of the source tree
+(onb_make_tree_range), the ranks exchange their tree-order ranges of the particle planes with one NCCL all-gather per
+plane over NVLink (torch.distributed on tensors that alias the library's device memory), then every rank completes the
+node arrays locally (onb_finish_tree). Only plumbing lives here; the kernels are in csrc/."""
+import torch
+import torch.distributed as dist
+
+
+def shard_ranges(session, n, world):
+    return [session.shard_particle_range(n, r, world) for r in range(world)]
+
+
+def exchange_source_planes(session, n, rank, world, ranges=None, group=None, scratch=None):
+    """all-gather of every source plane; ranks own unequal (leaf aligned) ranges, so the gather is padded to the longest"""
+    if world == 1:
+        return scratch
+    ranges = ranges or shard_ranges(session, n, world)
+    chunk = max(hi - lo for lo, hi in ranges)
+    lo, hi = ranges[rank]
+    if scratch is None or scratch.numel() < world * chunk:
+        scratch = torch.empty(world * chunk, dtype=torch.float32, device="cuda")
+    out = scratch[: world * chunk]
+    for f in session.source_fields():
+        plane = session.plane_tensor(0, f, n + 256)          # the library pads every plane by >= one leaf
+        dist.all_gather_into_tensor(out, plane[lo:lo + chunk], group=group)
+        for r, (a, b) in enumerate(ranges):
+            if r != rank:
+                plane[a:b].copy_(out[r * chunk: r * chunk + (b - a)])
+    torch.cuda.synchronize()
+    return scratch
+
+
+def build_sources_distributed(session, n, rank, world, scratch=None):
+    """source tree + equivalent particles, replicated on every rank with 1/world of the sorting work each"""
+    lo, hi = session.shard_particle_range(n, rank, world)
+    session.make_tree_range(0, lo, hi)
+    scratch = exchange_source_planes(session, n, rank, world, scratch=scratch)
+    if world > 1:
+        session.finish_tree(0)
+    session.upward(0)
+    return scratch
+
+
+def build_targets_sharded(session, n, rank, world):
+    lo, hi = session.shard_particle_range(n, rank, world)
+    session.make_tree_range(1, lo, hi)
+    session.refine(1)
+    session.upward(1)

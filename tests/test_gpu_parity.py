@@ -198,3 +198,46 @@ def test_c_abi_results_original_order():
     want = np.ones((12, n), np.float32)
     want[:, po["gidx"].astype(np.int64)] += po["u"]
     assert bits_equal(out, want)
+
+
+def test_range_restricted_builds_reproduce_the_full_build():
+    """multi-GPU source build emulated on one GPU: three contexts each sort one third of the source tree, exchange their
+    plane ranges (device copies standing in for the NCCL all-gather), finish bottom-up, and must then hold exactly the
+    arrays of a full build; sharded target builds + dual tree must reproduce the unsharded outputs bit for bit."""
+    import torch
+    n, theta, world = 70000, 1.4, 3
+    full = _gpu("grav3d", n)
+    full.init_driver(); full.make_tree(0); full.upward(0); full.make_tree(1); full.refine(1); full.upward(1)
+    full.zero_vels(); full.fastsumm(theta)
+    want_src = full.parts(0); want_eq = full.parts(2, ("x", "s")); want_tree = full.tree(0)
+    want_u = full.parts(1, ("u", "gidx"))
+    ranks = []
+    for rk in range(world):
+        g = _gpu("grav3d", n); g.set_shard(rk, world); g.init_driver()
+        lo, hi = g.shard_particle_range(n, rk, world)
+        g.make_tree_range(0, lo, hi)
+        ranks.append((g, lo, hi))
+    torch.cuda.synchronize()
+    for g, lo, hi in ranks:                      # "all-gather": everyone receives everyone else's range of every plane
+        for f in g.source_fields():
+            dst = g.plane_tensor(0, f, n)
+            for h, a, b in ranks:
+                if h is not g:
+                    dst[a:b].copy_(h.plane_tensor(0, f, n)[a:b])
+    torch.cuda.synchronize()
+    got_u = np.zeros_like(want_u["u"]); got_g = np.zeros_like(want_u["gidx"])
+    for g, lo, hi in ranks:
+        g.finish_tree(0); g.upward(0)
+        ps = g.parts(0)
+        for k in ("x", "r", "s"):
+            assert bits_equal(ps[k], want_src[k]), k
+        t = g.tree(0)
+        for k in ("num", "ioffset", "nc", "ns", "nr", "x", "s", "pr"):
+            assert bits_equal(t[k], want_tree[k]), k
+        assert bits_equal(g.parts(2, ("s",))["s"], want_eq["s"])
+        g.make_tree_range(1, lo, hi); g.refine(1); g.upward(1)
+        g.zero_vels(); g.fastsumm(theta)
+        p = g.parts(1, ("u", "gidx"))
+        got_u[:, lo:hi] = p["u"][:, lo:hi]; got_g[lo:hi] = p["gidx"][lo:hi]
+    assert bits_equal(got_g, want_u["gidx"])
+    assert bits_equal(got_u, want_u["u"])
