@@ -18,7 +18,8 @@ static std::string g_create_error;
 // ---------------------------------------------------------------------------------------------
 int onb_alloc_parts(onb_context* c, DParts& p, uint32_t n, bool are_sources) {
     p = DParts();
-    p.n = n; p.cap = ((n + 63u) & ~31u) + 288u;      // slack: bulk copies round up to 16 B, padded all-gathers overrun by < one leaf p.PD = c->PD; p.SD = c->SD; p.OD = c->OD; p.are_sources = are_sources;
+    // slack: bulk copies round up to 16 B, padded all-gathers overrun by < one leaf
+    p.n = n; p.cap = ((n + 63u) & ~31u) + 288u; p.PD = c->PD; p.SD = c->SD; p.OD = c->OD; p.are_sources = are_sources;
     const size_t bytes = (size_t)p.cap * sizeof(float);
     for (int d = 0; d < c->PD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.x[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.x[d], 0, bytes, c->stream)); }
     ONB_CUDA(onb_pmalloc(c, (void**)&p.r, bytes)); ONB_CUDA(cudaMemsetAsync(p.r, 0, bytes, c->stream));
