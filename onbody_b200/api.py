@@ -56,6 +56,7 @@ def load_library():
         getattr(L, fn).argtypes = [C.c_void_p, C.c_int]
     L.onb_make_tree_range.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
     L.onb_finish_tree.argtypes = [C.c_void_p, C.c_int]
+    L.onb_set_build_range.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
     L.onb_shard_particle_range.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, _u64p, _u64p]
     L.onb_device_ptr.restype = C.c_void_p
     L.onb_device_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -179,6 +180,7 @@ class GpuSession:
     def make_tree(self, which): self._chk(self.lib.onb_make_tree(self.h, which))
     def make_tree_range(self, which, lo, hi): self._chk(self.lib.onb_make_tree_range(self.h, which, lo, hi))
     def finish_tree(self, which): self._chk(self.lib.onb_finish_tree(self.h, which))
+    def set_build_range(self, which, lo, hi): self._chk(self.lib.onb_set_build_range(self.h, which, lo, hi))
 
     def shard_particle_range(self, n, rank, nranks):
         lo, hi = C.c_uint64(), C.c_uint64()

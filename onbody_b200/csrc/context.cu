@@ -254,6 +254,12 @@ int onb_finish_tree(onb_context* c, int which) {
     tm.stop();
     return rc;
 }
+int onb_set_build_range(onb_context* c, int which, uint64_t lo, uint64_t hi) {
+    if (which < 0 || which > 1) return ONB_ERR_ARG;
+    DParts& p = c->parts[which];
+    p.build_lo = (uint32_t)std::min<uint64_t>(lo, p.n); p.build_hi = (uint32_t)std::min<uint64_t>(hi, p.n);
+    return ONB_OK;
+}
 int onb_shard_particle_range(const onb_context* c, uint64_t n, int rank, int nranks, uint64_t* lo, uint64_t* hi) {
     if (nranks < 1 || rank < 0 || rank >= nranks) return ONB_ERR_ARG;
     const uint64_t nleaf = (n + c->block - 1) / c->block;

@@ -10,8 +10,9 @@ def shard_ranges(session, n, world):
     return [session.shard_particle_range(n, r, world) for r in range(world)]
 
 
-def exchange_source_planes(session, n, rank, world, ranges=None, group=None, scratch=None):
-    """all-gather of every source plane; ranks own unequal (leaf aligned) ranges, so the gather is padded to the longest"""
+def exchange_planes(session, which, n, rank, world, ranges=None, group=None, scratch=None):
+    """all-gather of every particle plane of set `which` (0 sources: x, r, s; 1 targets: x, r); ranks own unequal
+    (leaf aligned) ranges, so the gather is padded to the longest"""
     if world == 1:
         return scratch
     ranges = ranges or shard_ranges(session, n, world)
@@ -20,8 +21,9 @@ def exchange_source_planes(session, n, rank, world, ranges=None, group=None, scr
     if scratch is None or scratch.numel() < world * chunk:
         scratch = torch.empty(world * chunk, dtype=torch.float32, device="cuda")
     out = scratch[: world * chunk]
-    for f in session.source_fields():
-        plane = session.plane_tensor(0, f, n + 256)          # the library pads every plane by >= one leaf
+    fields = session.source_fields() if which == 0 else list(range(session.PD)) + [3]
+    for f in fields:
+        plane = session.plane_tensor(which, f, n + 256)          # the library pads every plane by >= one leaf
         dist.all_gather_into_tensor(out, plane[lo:lo + chunk], group=group)
         for r, (a, b) in enumerate(ranges):
             if r != rank:
@@ -34,15 +36,24 @@ def build_sources_distributed(session, n, rank, world, scratch=None):
     """source tree + equivalent particles, replicated on every rank with 1/world of the sorting work each"""
     lo, hi = session.shard_particle_range(n, rank, world)
     session.make_tree_range(0, lo, hi)
-    scratch = exchange_source_planes(session, n, rank, world, scratch=scratch)
+    scratch = exchange_planes(session, 0, n, rank, world, scratch=scratch)
     if world > 1:
         session.finish_tree(0)
     session.upward(0)
     return scratch
 
 
-def build_targets_sharded(session, n, rank, world):
+def build_targets_sharded(session, n, rank, world, scratch=None):
+    """target tree: each rank sorts (and later refines and evaluates) only its own leaves, but the centres of the
+    ancestor nodes enter the dual-tree MAC (ongrav3d.cpp:338) and depend on every particle below them, so the coordinate
+    planes are exchanged as well and the node arrays completed bottom-up - before the in-leaf refinement, as in the
+    reference (makeTree's finishTree runs before refineTree)."""
     lo, hi = session.shard_particle_range(n, rank, world)
     session.make_tree_range(1, lo, hi)
+    scratch = exchange_planes(session, 1, n, rank, world, scratch=scratch)
+    if world > 1:
+        session.finish_tree(1)
+        session.set_build_range(1, lo, hi)
     session.refine(1)
     session.upward(1)
+    return scratch

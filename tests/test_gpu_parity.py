@@ -235,7 +235,17 @@ def test_range_restricted_builds_reproduce_the_full_build():
         for k in ("num", "ioffset", "nc", "ns", "nr", "x", "s", "pr"):
             assert bits_equal(t[k], want_tree[k]), k
         assert bits_equal(g.parts(2, ("s",))["s"], want_eq["s"])
-        g.make_tree_range(1, lo, hi); g.refine(1); g.upward(1)
+        g.make_tree_range(1, lo, hi)
+    torch.cuda.synchronize()
+    for g, lo, hi in ranks:                      # target coordinates too: ancestor centres enter the dual-tree MAC
+        for f in (0, 1, 2, 3):
+            dst = g.plane_tensor(1, f, n)
+            for h, a, b in ranks:
+                if h is not g:
+                    dst[a:b].copy_(h.plane_tensor(1, f, n)[a:b])
+    torch.cuda.synchronize()
+    for g, lo, hi in ranks:
+        g.finish_tree(1); g.set_build_range(1, lo, hi); g.refine(1); g.upward(1)
         g.zero_vels(); g.fastsumm(theta)
         p = g.parts(1, ("u", "gidx"))
         got_u[:, lo:hi] = p["u"][:, lo:hi]; got_g[lo:hi] = p["gidx"][lo:hi]
