@@ -97,6 +97,8 @@ ONB_API int onb_finish_tree(onb_context* c, int which);
 /* restrict the following onb_refine to the leaves of [lo,hi) again (onb_finish_tree resets the range to the whole set) */
 ONB_API int onb_set_build_range(onb_context* c, int which, uint64_t lo, uint64_t hi);
 /* the tree-order particle range of shard `rank` of `nranks` for a set of n particles (contiguous leaves) */
+/* the same without a context (pure host arithmetic) */
+ONB_API int onb_shard_range_for(uint64_t n, int block, int rank, int nranks, uint64_t* lo, uint64_t* hi);
 ONB_API int onb_shard_particle_range(const onb_context* c, uint64_t n, int rank, int nranks, uint64_t* lo, uint64_t* hi);
 ONB_API int onb_refine(onb_context* c, int which);
 ONB_API int onb_upward(onb_context* c, int which);

@@ -260,12 +260,15 @@ int onb_set_build_range(onb_context* c, int which, uint64_t lo, uint64_t hi) {
     p.build_lo = (uint32_t)std::min<uint64_t>(lo, p.n); p.build_hi = (uint32_t)std::min<uint64_t>(hi, p.n);
     return ONB_OK;
 }
-int onb_shard_particle_range(const onb_context* c, uint64_t n, int rank, int nranks, uint64_t* lo, uint64_t* hi) {
-    if (nranks < 1 || rank < 0 || rank >= nranks) return ONB_ERR_ARG;
-    const uint64_t nleaf = (n + c->block - 1) / c->block;
-    *lo = std::min<uint64_t>((nleaf * (uint64_t)rank / (uint64_t)nranks) * c->block, n);
-    *hi = std::min<uint64_t>((nleaf * (uint64_t)(rank + 1) / (uint64_t)nranks) * c->block, n);
+int onb_shard_range_for(uint64_t n, int block, int rank, int nranks, uint64_t* lo, uint64_t* hi) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || block < 1) return ONB_ERR_ARG;
+    const uint64_t nleaf = (n + block - 1) / block;
+    *lo = std::min<uint64_t>((nleaf * (uint64_t)rank / (uint64_t)nranks) * block, n);
+    *hi = std::min<uint64_t>((nleaf * (uint64_t)(rank + 1) / (uint64_t)nranks) * block, n);
     return ONB_OK;
+}
+int onb_shard_particle_range(const onb_context* c, uint64_t n, int rank, int nranks, uint64_t* lo, uint64_t* hi) {
+    return onb_shard_range_for(n, c->block, rank, nranks, lo, hi);
 }
 int onb_refine(onb_context* c, int which) {
     onb_scratch_reset(c);

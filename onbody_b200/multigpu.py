@@ -10,24 +10,39 @@ def shard_ranges(session, n, world):
     return [session.shard_particle_range(n, r, world) for r in range(world)]
 
 
+def allgather_ranges(plane, ranges, rank, world, scratch=None, group=None):
+    """In-place all-gather of a 1-D tensor whose slice [lo_r, hi_r) is valid on rank r. Ranges are contiguous and leaf
+    aligned but not equal, so the collective is padded to the longest (the tensor must extend >= chunk past every lo).
+    Works on CUDA tensors over NCCL and on CPU tensors over gloo (tests)."""
+    if world == 1:
+        return scratch
+    chunk = max(hi - lo for lo, hi in ranges)
+    lo, hi = ranges[rank]
+    if scratch is None or scratch.numel() < world * chunk or scratch.device != plane.device:
+        scratch = torch.empty(world * chunk, dtype=plane.dtype, device=plane.device)
+    out = scratch[: world * chunk]
+    mine = plane[lo:lo + chunk]
+    if mine.numel() < chunk:
+        raise ValueError("plane is not padded enough for a padded all-gather")
+    if dist.get_backend(group) == "gloo":
+        dist.all_gather([out[r * chunk:(r + 1) * chunk] for r in range(world)], mine.contiguous(), group=group)
+    else:
+        dist.all_gather_into_tensor(out, mine, group=group)
+    for r, (a, b) in enumerate(ranges):
+        if r != rank:
+            plane[a:b].copy_(out[r * chunk: r * chunk + (b - a)])
+    return scratch
+
+
 def exchange_planes(session, which, n, rank, world, ranges=None, group=None, scratch=None):
-    """all-gather of every particle plane of set `which` (0 sources: x, r, s; 1 targets: x, r); ranks own unequal
-    (leaf aligned) ranges, so the gather is padded to the longest"""
+    """all-gather of every particle plane of set `which` (0 sources: x, r, s; 1 targets: x, r)"""
     if world == 1:
         return scratch
     ranges = ranges or shard_ranges(session, n, world)
-    chunk = max(hi - lo for lo, hi in ranges)
-    lo, hi = ranges[rank]
-    if scratch is None or scratch.numel() < world * chunk:
-        scratch = torch.empty(world * chunk, dtype=torch.float32, device="cuda")
-    out = scratch[: world * chunk]
     fields = session.source_fields() if which == 0 else list(range(session.PD)) + [3]
     for f in fields:
-        plane = session.plane_tensor(which, f, n + 256)          # the library pads every plane by >= one leaf
-        dist.all_gather_into_tensor(out, plane[lo:lo + chunk], group=group)
-        for r, (a, b) in enumerate(ranges):
-            if r != rank:
-                plane[a:b].copy_(out[r * chunk: r * chunk + (b - a)])
+        plane = session.plane_tensor(which, f, n + 256)      # the library pads every plane by >= one leaf
+        scratch = allgather_ranges(plane, ranges, rank, world, scratch, group)
     torch.cuda.synchronize()
     return scratch
 
