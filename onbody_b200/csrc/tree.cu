@@ -21,6 +21,8 @@
  * planes. All traffic is HBM/L2 streaming: the roofline for this file is memory bandwidth.
  */
 #include "onb_internal.h"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -551,31 +553,21 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
             for (int d = 0; d < 3; ++d) ba.x[d] = cx[d];
             ba.t = view_of(t); ba.nodes = bignodes; ba.nbig = nbig; ba.chunk_owner = chunk_owner; ba.cntA = cntA; ba.cntB = cntB;
             ba.lidx = lidx; ba.scr = scr; ba.axis_of = axis_of; ba.pmid = pmid; ba.stats = c->d_build_stats;
-            ba.block = c->block; ba.big = BIG_NODE; ba.level = lev; ba.PD = PD; ba.pivot_mode = onb_pivot_mode; ba.it = 0;
+            ba.block = c->block; ba.big = BIG_NODE; ba.level = lev; ba.PD = PD; ba.pivot_mode = onb_pivot_mode;
             ba.blo = blo; ba.bhi = bhi;
             const uint32_t lev_nodes = std::min<uint64_t>(1ull << lev, max_big_nodes);
             ba.max_nodes = lev_nodes; ba.max_chunks = max_chunks;
             const uint32_t chunks_ub = std::min<uint32_t>(max_chunks, n / BIG_CH + lev_nodes + 1);
-            k_big_list<<<1, 256, 0, c->stream>>>(ba); ONB_LAUNCH(c);
-            k_big_bbox<<<chunks_ub, BIG_T, 0, c->stream>>>(ba); ONB_LAUNCH(c);
-            k_big_setup<<<(lev_nodes + 127) / 128, 128, 0, c->stream>>>(ba); ONB_LAUNCH(c);
-            int it = 0;
-            while (it < 104) {
-                for (int rep = 0; rep < 4; ++rep, ++it) {
-                    ba.it = it;
-                    k_big_count<<<chunks_ub, BIG_T, 0, c->stream>>>(ba);
-                    k_big_mis<<<chunks_ub, BIG_T, 0, c->stream>>>(ba);
-                    k_big_scan<<<lev_nodes, 256, 0, c->stream>>>(ba);
-                    k_big_compact<<<chunks_ub, BIG_T, 0, c->stream>>>(ba);
-                    k_big_swap<<<chunks_ub, BIG_T, 0, c->stream>>>(ba);
-                    c->launches += 5;
+            {
+                static int coop_blocks_per_sm = 0;
+                if (!coop_blocks_per_sm) {
+                    ONB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks_per_sm, k_big_level, BIG_T, 0));
+                    coop_blocks_per_sm = std::max(1, std::min(coop_blocks_per_sm, 4));
                 }
-                ONB_CUDA(cudaMemcpyAsync(c->h_flag, nbig + 2, 4, cudaMemcpyDeviceToHost, c->stream));
-                ONB_CUDA(cudaStreamSynchronize(c->stream));
-                if (*c->h_flag == 0) break;
+                const uint32_t grid = std::min<uint32_t>(chunks_ub, (uint32_t)(c->sm_count * coop_blocks_per_sm));
+                void* args[] = { (void*)&ba };
+                ONB_CUDA(cudaLaunchCooperativeKernel((void*)k_big_level, dim3(grid), dim3(BIG_T), args, 0, c->stream)); ONB_LAUNCH(c);
             }
-            *c->h_flag = 0;
-            k_big_finish<<<(lev_nodes + 127) / 128, 128, 0, c->stream>>>(ba); ONB_LAUNCH(c);
             ONB_CUDA(cudaGetLastError());
         }
         SplitArgs sa;

@@ -17,6 +17,7 @@
  * passes, pivots and exit conditions are the same, only the parallel decomposition differs.
  */
 #pragma once
+// (tree.cu includes <cooperative_groups.h> at global scope and defines `namespace cg` before including this file)
 
 constexpr int BIG_T = 256;                 // threads per chunk CTA
 constexpr int BIG_ROUNDS = 8;              // 8 warps x 8 rounds x 32 lanes
@@ -40,11 +41,11 @@ struct BigArgs {
     uint32_t* lidx; uint32_t* scr;
     uint8_t* axis_of; uint32_t* pmid;
     unsigned long long* stats;
-    uint32_t block, big, max_nodes, max_chunks, blo, bhi; int level, PD, pivot_mode, it;
+    uint32_t block, big, max_nodes, max_chunks, blo, bhi; int level, PD, pivot_mode;
 };
 
 // one block: list the big nodes of this level (node order) and lay out their chunks
-__global__ void __launch_bounds__(256) k_big_list(const BigArgs a) {
+__device__ __forceinline__ void big_list(const BigArgs& a) {                         // one CTA
     __shared__ uint32_t s_n, s_c;
     if (threadIdx.x == 0) { s_n = 0; s_c = 0; }
     __syncthreads();
@@ -77,9 +78,7 @@ __device__ __forceinline__ float bw_max(float v) { for (int o = 16; o; o >>= 1) 
 __device__ __forceinline__ uint32_t bw_sum(uint32_t v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
 
 // per chunk: bounding box contribution and lidx = iota (barneshut.hpp:621-625, :516)
-__global__ void __launch_bounds__(BIG_T) k_big_bbox(const BigArgs a) {
-    const uint32_t chunk = blockIdx.x;
-    if (chunk >= a.nbig[1]) return;
+__device__ __forceinline__ void big_bbox(const BigArgs& a, const int it, const uint32_t chunk) {
     BigNode& b = a.nodes[a.chunk_owner[chunk]];
     const uint32_t i0 = b.pf + (chunk - b.chunk0) * BIG_CH, i1 = min(b.pl, i0 + BIG_CH);
     __shared__ float s_lo[BIG_T / 32], s_hi[BIG_T / 32];
@@ -101,9 +100,7 @@ __global__ void __launch_bounds__(BIG_T) k_big_bbox(const BigArgs a) {
 }
 
 // per node: node arrays, split axis, first window and pivot (barneshut.hpp:623-663, :519-540)
-__global__ void k_big_setup(const BigArgs a) {
-    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bi >= a.nbig[0]) return;
+__device__ __forceinline__ void big_setup(const BigArgs& a, const uint32_t bi) {      // one thread per node
     BigNode& b = a.nodes[bi];
     const uint32_t node = b.node;
     float lo[3], hi[3], bsss = 0.0f;
@@ -134,11 +131,9 @@ __device__ __forceinline__ bool big_range(const BigNode& b, const BigWin& w, uin
     return i0 < i1;
 }
 
-__global__ void __launch_bounds__(BIG_T) k_big_count(const BigArgs a) {
-    const uint32_t chunk = blockIdx.x;
-    if (chunk >= a.nbig[1]) return;
+__device__ __forceinline__ void big_count(const BigArgs& a, const int it, const uint32_t chunk) {
     BigNode& b = a.nodes[a.chunk_owner[chunk]];
-    const BigWin w = b.w[a.it & 1];
+    const BigWin w = b.w[it & 1];
     uint32_t i0, i1;
     if (!big_range(b, w, chunk, i0, i1)) return;
     const float* key = a.x[b.axis];
@@ -163,11 +158,9 @@ __global__ void __launch_bounds__(BIG_T) k_big_count(const BigArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(BIG_T) k_big_mis(const BigArgs a) {
-    const uint32_t chunk = blockIdx.x;
-    if (chunk >= a.nbig[1]) return;
+__device__ __forceinline__ void big_mis(const BigArgs& a, const int it, const uint32_t chunk) {
     BigNode& b = a.nodes[a.chunk_owner[chunk]];
-    const BigWin w = b.w[a.it & 1];
+    const BigWin w = b.w[it & 1];
     if (w.done) return;
     uint32_t i0, i1, ca = 0, cb = 0;
     if (big_range(b, w, chunk, i0, i1)) {
@@ -191,12 +184,10 @@ __global__ void __launch_bounds__(BIG_T) k_big_mis(const BigArgs a) {
 }
 
 // one CTA per big node: chunk counts -> exclusive offsets, then the reference's window update (barneshut.hpp:565-585)
-__global__ void __launch_bounds__(256) k_big_scan(const BigArgs a) {
-    const uint32_t bi = blockIdx.x;
-    if (bi >= a.nbig[0]) return;
+__device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const uint32_t bi) {   // one CTA per node
     BigNode& b = a.nodes[bi];
-    const BigWin w = b.w[a.it & 1];
-    if (w.done) { if (threadIdx.x == 0) b.w[(a.it + 1) & 1] = w; return; }
+    const BigWin w = b.w[it & 1];
+    if (w.done) { if (threadIdx.x == 0) b.w[(it + 1) & 1] = w; return; }
     __shared__ uint32_t s_wa[8], s_wb[8], s_carry[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
@@ -232,17 +223,15 @@ __global__ void __launch_bounds__(256) k_big_scan(const BigArgs a) {
                 else nw.pivot = select_pivot(b.nless, nw.wf, nw.wl, nw.lo, nw.hi, b.ideal, a.pivot_mode);
             }
         }
-        b.w[(a.it + 1) & 1] = nw;
+        b.w[(it + 1) & 1] = nw;
         b.m = 0; b.mx_enc = 0u; b.mn_enc = 0xffffffffu;
         if (nw.done) atomicSub(&a.nbig[2], 1u);
     }
 }
 
-__global__ void __launch_bounds__(BIG_T) k_big_compact(const BigArgs a) {
-    const uint32_t chunk = blockIdx.x;
-    if (chunk >= a.nbig[1]) return;
+__device__ __forceinline__ void big_compact(const BigArgs& a, const int it, const uint32_t chunk) {
     BigNode& b = a.nodes[a.chunk_owner[chunk]];
-    const BigWin w = b.w[a.it & 1];
+    const BigWin w = b.w[it & 1];
     uint32_t i0, i1;
     if (!big_range(b, w, chunk, i0, i1)) return;
     const uint32_t B = b.B;
@@ -275,11 +264,9 @@ __global__ void __launch_bounds__(BIG_T) k_big_compact(const BigArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(BIG_T) k_big_swap(const BigArgs a) {
-    const uint32_t chunk = blockIdx.x;
-    if (chunk >= a.nbig[1]) return;
+__device__ __forceinline__ void big_swap(const BigArgs& a, const int it, const uint32_t chunk) {
     BigNode& b = a.nodes[a.chunk_owner[chunk]];
-    if (b.w[a.it & 1].done) return;
+    if (b.w[it & 1].done) return;
     const uint32_t k = b.k, q = chunk - b.chunk0;
     float* key = a.x[b.axis];
     const uint32_t j1 = min(k, (q + 1) * BIG_CH);
@@ -291,9 +278,7 @@ __global__ void __launch_bounds__(BIG_T) k_big_swap(const BigArgs a) {
 }
 
 // per node: publish the split (barneshut.hpp:702-704) and the statistics
-__global__ void k_big_finish(const BigArgs a) {
-    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bi >= a.nbig[0]) return;
+__device__ __forceinline__ void big_finish(const BigArgs& a, const uint32_t bi) {     // one thread per node
     const BigNode& b = a.nodes[bi];
     const uint32_t node = b.node;
     a.axis_of[node] = (uint8_t)b.axis; a.pmid[node] = b.nless;
@@ -301,4 +286,34 @@ __global__ void k_big_finish(const BigArgs a) {
     a.t.ioffset[2 * node + 1] = b.nless; a.t.num[2 * node + 1] = b.pl - b.nless;
     atomicAdd(&a.stats[0], 1ull); atomicAdd(&a.stats[1], (unsigned long long)b.npass);
     atomicAdd(&a.stats[2], (unsigned long long)b.nstall); atomicAdd(&a.stats[3], b.nscan);
+}
+
+
+// ---- one cooperative launch per level: every phase of every pass, separated by grid-wide barriers -----------------
+// (one launch instead of ~60: at these sizes the passes are short enough that launch latency dominated them)
+__global__ void __launch_bounds__(BIG_T) k_big_level(const BigArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    if (blockIdx.x == 0) big_list(a);
+    grid.sync();
+    const uint32_t nnodes = a.nbig[0], nchunks = a.nbig[1];
+    if (nnodes == 0) return;
+    for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_bbox(a, 0, ch); __syncthreads(); }
+    grid.sync();
+    for (uint32_t bi = gtid; bi < nnodes; bi += gthreads) big_setup(a, bi);
+    grid.sync();
+    for (int it = 0; it < 104; ++it) {
+        for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_count(a, it, ch); __syncthreads(); }
+        grid.sync();
+        for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_mis(a, it, ch); __syncthreads(); }
+        grid.sync();
+        for (uint32_t bi = blockIdx.x; bi < nnodes; bi += gridDim.x) { big_scan(a, it, bi); __syncthreads(); }
+        grid.sync();
+        for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_compact(a, it, ch); __syncthreads(); }
+        grid.sync();
+        for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_swap(a, it, ch); __syncthreads(); }
+        grid.sync();
+        if (a.nbig[2] == 0) break;        // every node of the level has met one of the reference's exit conditions
+    }
+    for (uint32_t bi = gtid; bi < nnodes; bi += gthreads) big_finish(a, bi);
 }
