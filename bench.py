@@ -221,9 +221,9 @@ def run_ours(args):
         # completes the node arrays bottom-up and runs the (cheap) upward pass in full; evaluation is sharded by target leaves
         from onbody_b200 import multigpu
         t0 = time.perf_counter()
-        scratch["buf"] = multigpu.build_sources_distributed(g, N, rank, world, scratch["buf"])
+        scratch["buf"] = multigpu.build_sources_distributed(g, N, rank, world, scratch["buf"], phases)
         t1 = time.perf_counter()
-        scratch["buf"] = multigpu.build_targets_sharded(g, N, rank, world, scratch["buf"])
+        scratch["buf"] = multigpu.build_targets_sharded(g, N, rank, world, scratch["buf"], phases)
         t2 = time.perf_counter()
         phases["src_side_wall"] = phases.get("src_side_wall", 0.0) + (t1 - t0) * 1e3
         phases["tgt_side_wall"] = phases.get("tgt_side_wall", 0.0) + (t2 - t1) * 1e3

@@ -47,28 +47,39 @@ def exchange_planes(session, which, n, rank, world, ranges=None, group=None, scr
     return scratch
 
 
-def build_sources_distributed(session, n, rank, world, scratch=None):
+def _tick(times, key, t0):
+    import time
+    if times is not None:
+        times[key] = times.get(key, 0.0) + (time.perf_counter() - t0) * 1e3
+    return time.perf_counter()
+
+
+def build_sources_distributed(session, n, rank, world, scratch=None, times=None):
     """source tree + equivalent particles, replicated on every rank with 1/world of the sorting work each"""
+    import time
+    t = time.perf_counter()
     lo, hi = session.shard_particle_range(n, rank, world)
-    session.make_tree_range(0, lo, hi)
-    scratch = exchange_planes(session, 0, n, rank, world, scratch=scratch)
+    session.make_tree_range(0, lo, hi); t = _tick(times, "src_tree_range", t)
+    scratch = exchange_planes(session, 0, n, rank, world, scratch=scratch); t = _tick(times, "src_allgather", t)
     if world > 1:
-        session.finish_tree(0)
-    session.upward(0)
+        session.finish_tree(0); t = _tick(times, "src_finish", t)
+    session.upward(0); t = _tick(times, "upward", t)
     return scratch
 
 
-def build_targets_sharded(session, n, rank, world, scratch=None):
+def build_targets_sharded(session, n, rank, world, scratch=None, times=None):
     """target tree: each rank sorts (and later refines and evaluates) only its own leaves, but the centres of the
     ancestor nodes enter the dual-tree MAC (ongrav3d.cpp:338) and depend on every particle below them, so the coordinate
     planes are exchanged as well and the node arrays completed bottom-up - before the in-leaf refinement, as in the
     reference (makeTree's finishTree runs before refineTree)."""
+    import time
+    t = time.perf_counter()
     lo, hi = session.shard_particle_range(n, rank, world)
-    session.make_tree_range(1, lo, hi)
-    scratch = exchange_planes(session, 1, n, rank, world, scratch=scratch)
+    session.make_tree_range(1, lo, hi); t = _tick(times, "tgt_tree_range", t)
+    scratch = exchange_planes(session, 1, n, rank, world, scratch=scratch); t = _tick(times, "tgt_allgather", t)
     if world > 1:
-        session.finish_tree(1)
+        session.finish_tree(1); t = _tick(times, "tgt_finish", t)
         session.set_build_range(1, lo, hi)
-    session.refine(1)
-    session.upward(1)
+    session.refine(1); t = _tick(times, "refine", t)
+    session.upward(1); t = _tick(times, "tgt_equiv", t)
     return scratch
