@@ -7,7 +7,7 @@
  * of all big nodes of the level:
  *
  *   k_big_count    per chunk: #{v < pivot}, max{v < pivot}, min{v >= pivot}            -> atomics on the node
- *   k_big_mis      per chunk: misplaced-left / misplaced-right counts (needs B = wf + m)
+ *   (misplaced counts per chunk follow from the count and the chunk's position relative to B - no second pass)
  *   k_big_scan     per node : exclusive scan of the chunk counts, k, next window + next pivot (the reference's exit rules)
  *   k_big_compact  per chunk: ordered compaction of the misplaced positions into scr[]
  *   k_big_swap     per chunk: swap pair j of the node, a_j <-> b_j
@@ -86,7 +86,11 @@ __device__ __forceinline__ void big_bbox(const BigArgs& a, const int it, const u
     for (uint32_t i = i0 + threadIdx.x; i < i1; i += BIG_T) a.lidx[i] = i;
     for (int d = 0; d < a.PD; ++d) {
         float lo = INFINITY, hi = -INFINITY;
-        for (uint32_t i = i0 + threadIdx.x; i < i1; i += BIG_T) { const float v = a.x[d][i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        float v[BIG_ROUNDS];
+        #pragma unroll
+        for (int r = 0; r < BIG_ROUNDS; ++r) { const uint32_t i = i0 + (uint32_t)r * BIG_T + threadIdx.x; v[r] = i < i1 ? a.x[d][i] : NAN; }
+        #pragma unroll
+        for (int r = 0; r < BIG_ROUNDS; ++r) { lo = fminf(lo, v[r]); hi = fmaxf(hi, v[r]); }      // fminf/fmaxf ignore the NaN fillers
         lo = bw_min(lo); hi = bw_max(hi);
         if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
         __syncthreads();
@@ -137,11 +141,17 @@ __device__ __forceinline__ void big_count(const BigArgs& a, const int it, const 
     uint32_t i0, i1;
     if (!big_range(b, w, chunk, i0, i1)) return;
     const float* key = a.x[b.axis];
+    const uint32_t c0 = b.pf + (chunk - b.chunk0) * BIG_CH;
     uint32_t cnt = 0; float mx = -INFINITY, mn = INFINITY;
-    for (uint32_t i = i0 + threadIdx.x; i < i1; i += BIG_T) {
-        const float v = key[i];
-        if (v < w.pivot) { ++cnt; mx = fmaxf(mx, v); } else mn = fminf(mn, v);
+    float v[BIG_ROUNDS]; bool ok[BIG_ROUNDS];
+    #pragma unroll
+    for (int r = 0; r < BIG_ROUNDS; ++r) {            // 8 independent loads in flight per thread
+        const uint32_t i = c0 + (uint32_t)r * BIG_T + threadIdx.x;
+        ok[r] = i >= i0 && i < i1;
+        v[r] = ok[r] ? key[i] : 0.f;
     }
+    #pragma unroll
+    for (int r = 0; r < BIG_ROUNDS; ++r) if (ok[r]) { if (v[r] < w.pivot) { ++cnt; mx = fmaxf(mx, v[r]); } else mn = fminf(mn, v[r]); }
     __shared__ uint32_t s_c[BIG_T / 32]; __shared__ float s_mx[BIG_T / 32], s_mn[BIG_T / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     cnt = bw_sum(cnt); mx = bw_max(mx); mn = bw_min(mn);
@@ -151,6 +161,7 @@ __device__ __forceinline__ void big_count(const BigArgs& a, const int it, const 
         cnt = lane < BIG_T / 32 ? s_c[lane] : 0u; mx = lane < BIG_T / 32 ? s_mx[lane] : -INFINITY; mn = lane < BIG_T / 32 ? s_mn[lane] : INFINITY;
         cnt = bw_sum(cnt); mx = bw_max(mx); mn = bw_min(mn);
         if (lane == 0) {
+            a.cntA[chunk] = cnt;                       // elements < pivot in this chunk's part of the window
             if (cnt) atomicAdd(&b.m, cnt);
             if (mx > -INFINITY) atomicMax(&b.mx_enc, f2ord(mx));
             if (mn < INFINITY) atomicMin(&b.mn_enc, f2ord(mn));
@@ -158,43 +169,46 @@ __device__ __forceinline__ void big_count(const BigArgs& a, const int it, const 
     }
 }
 
-__device__ __forceinline__ void big_mis(const BigArgs& a, const int it, const uint32_t chunk) {
-    BigNode& b = a.nodes[a.chunk_owner[chunk]];
-    const BigWin w = b.w[it & 1];
-    if (w.done) return;
-    uint32_t i0, i1, ca = 0, cb = 0;
-    if (big_range(b, w, chunk, i0, i1)) {
-        const uint32_t B = w.wf + b.m;
-        const float* key = a.x[b.axis];
-        for (uint32_t i = i0 + threadIdx.x; i < i1; i += BIG_T) {
-            const bool lt = key[i] < w.pivot;
-            ca += (i < B && !lt); cb += (i >= B && lt);
-        }
-    }
-    __shared__ uint32_t s_a[BIG_T / 32], s_b[BIG_T / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    ca = bw_sum(ca); cb = bw_sum(cb);
-    if (lane == 0) { s_a[warp] = ca; s_b[warp] = cb; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t ta = 0, tb = 0;
-        for (int q = 0; q < BIG_T / 32; ++q) { ta += s_a[q]; tb += s_b[q]; }
-        a.cntA[chunk] = ta; a.cntB[chunk] = tb;
-    }
-}
-
-// one CTA per big node: chunk counts -> exclusive offsets, then the reference's window update (barneshut.hpp:565-585)
-__device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const uint32_t bi) {   // one CTA per node
+// one CTA per big node. The misplaced counts of a chunk follow from its "< pivot" count and its position relative to
+// B = wf + m (left of B: everything not "<" is misplaced; right of B: everything "<" is); only the one chunk that
+// straddles B needs a second look at its keys. Then: exclusive offsets per chunk, k, and the reference's window update
+// and exit rules (barneshut.hpp:565-585).
+__device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const uint32_t bi) {
     BigNode& b = a.nodes[bi];
     const BigWin w = b.w[it & 1];
     if (w.done) { if (threadIdx.x == 0) b.w[(it + 1) & 1] = w; return; }
-    __shared__ uint32_t s_wa[8], s_wb[8], s_carry[2];
+    __shared__ uint32_t s_wa[8], s_wb[8], s_carry[2], s_ltl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
-    __syncthreads();
+    const uint32_t B = w.wf + b.m;
+    // the straddling chunk: #{v < pivot} among its window elements left of B
+    {
+        const uint32_t qb = (B - b.pf) / BIG_CH;
+        const uint32_t c0 = b.pf + qb * BIG_CH;
+        const uint32_t i0 = max(c0, w.wf), i1 = min(min(b.pl, c0 + BIG_CH), w.wl + 1);
+        uint32_t ltl = 0;
+        if (B > i0 && B < i1) {
+            const float* key = a.x[b.axis];
+            for (uint32_t i = i0 + threadIdx.x; i < B; i += 256) ltl += (key[i] < w.pivot);
+        }
+        ltl = bw_sum(ltl);
+        if (lane == 0) s_wa[warp] = ltl;
+        __syncthreads();
+        if (threadIdx.x == 0) { uint32_t t = 0; for (int q = 0; q < 8; ++q) t += s_wa[q]; s_ltl = t; s_carry[0] = 0; s_carry[1] = 0; }
+        __syncthreads();
+    }
     for (uint32_t base = 0; base < b.nchunks; base += 256) {
         const uint32_t q = base + threadIdx.x;
-        const uint32_t va = q < b.nchunks ? a.cntA[b.chunk0 + q] : 0u, vb = q < b.nchunks ? a.cntB[b.chunk0 + q] : 0u;
+        uint32_t va = 0, vb = 0;
+        if (q < b.nchunks) {
+            const uint32_t c0 = b.pf + q * BIG_CH;
+            const uint32_t i0 = max(c0, w.wf), i1 = min(min(b.pl, c0 + BIG_CH), w.wl + 1);
+            if (i0 < i1) {
+                const uint32_t lt = a.cntA[b.chunk0 + q];
+                if (i1 <= B) va = (i1 - i0) - lt;
+                else if (i0 >= B) vb = lt;
+                else { va = (B - i0) - s_ltl; vb = lt - s_ltl; }
+            }
+        }
         uint32_t ia = va, ib = vb;
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o); if (lane >= o) { ia += ta; ib += tb; } }
@@ -208,7 +222,6 @@ __device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const u
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const uint32_t B = w.wf + b.m;
         b.B = B; b.k = s_carry[0];
         const float mx_lt = ord2f(b.mx_enc), mn_ge = ord2f(b.mn_enc);
         b.npass += 1; b.nscan += (w.wl - w.wf + 1);
@@ -304,8 +317,6 @@ __global__ void __launch_bounds__(BIG_T) k_big_level(const BigArgs a) {
     grid.sync();
     for (int it = 0; it < 104; ++it) {
         for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_count(a, it, ch); __syncthreads(); }
-        grid.sync();
-        for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_mis(a, it, ch); __syncthreads(); }
         grid.sync();
         for (uint32_t bi = blockIdx.x; bi < nnodes; bi += gridDim.x) { big_scan(a, it, bi); __syncthreads(); }
         grid.sync();
