@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - the hot path of ongrav3d (dual-tree, -t=1.4 -o=4 -b=128, charges) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n PARTICLES]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--particles N]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch of synthetic input (the drivers' own mt19937(12345) cloud):
@@ -372,7 +372,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("ONB_BENCH_N", "10000000")))
+    ap.add_argument("--particles", dest="n", type=int, default=int(os.environ.get("ONB_BENCH_N", "10000000")))
     ap.add_argument("--n-ref", type=int, default=0, help="sample size of the CPU reference leg (default: sized to a few minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
