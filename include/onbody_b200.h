@@ -141,7 +141,7 @@ ONB_API uint64_t onb_launch_count(const onb_context* c);
 /* FP32 FMA issue-rate microbenchmark on this device: returns measured TFLOP/s (2 flop per FMA lane) */
 ONB_API double   onb_measure_fp32_peak(onb_context* c);
 /* raw device pointers for zero-copy plumbing (e.g. an NCCL all-gather issued from the host language):
- * field: 0..2 x[d], 3 r, 4..6 s[d]; returns NULL if absent */
+ * field: 0..2 x[d], 3 r, 4..6 s[d], 7.. u[d]; returns NULL if absent */
 ONB_API void*    onb_device_ptr(onb_context* c, int which, int field);
 
 /* diagnostics of the last onb_make_tree / onb_refine: selects, partition passes, stall exits, elements scanned, and the

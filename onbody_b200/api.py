@@ -86,6 +86,8 @@ def load_library():
     L.onb_measure_fp32_peak.argtypes = [C.c_void_p]
     L.onb_load_tree.argtypes = [C.c_void_p, C.c_int, C.c_int] + [_f32p] * 6 + [_u64p] * 2
     L.onb_get_build_stats.argtypes = [C.c_void_p, C.c_uint64 * 5]
+    if os.environ.get("ONB_P2P_TPT"):          # tuning knob: targets per thread of the pair kernel (1, 2, 4; +16 = scalar arithmetic)
+        L.onb_set_p2p_tpt(int(os.environ["ONB_P2P_TPT"]))
     _lib = L
     return L
 

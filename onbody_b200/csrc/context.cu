@@ -463,6 +463,7 @@ void* onb_device_ptr(onb_context* c, int which, int field) {
     if (field >= 0 && field < 3) return p.x[field];
     if (field == 3) return p.r;
     if (field >= 4 && field < 7) return p.s[field - 4];
+    if (field >= 7 && field < 7 + ONB_MAX_OD) return p.u[field - 7];
     return nullptr;
 }
 
