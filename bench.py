@@ -265,24 +265,26 @@ def run_ours(args):
             stage["ds"] = torch.empty((1, N + per), dtype=torch.float32, device="cuda")
             stage["buf"] = None
         g.timer_start()
+        tt = [time.perf_counter()]
         lo, hi = stage["ranges"][rank]
         for d in range(3):
             stage["dx"][d, lo:hi].copy_(hx[d, lo:hi], non_blocking=True)
         stage["dr"][lo:hi].copy_(hr[lo:hi], non_blocking=True)
         stage["ds"][0, lo:hi].copy_(hs[0, lo:hi], non_blocking=True)
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(); tt.append(time.perf_counter())
         for plane in (stage["dx"][0], stage["dx"][1], stage["dx"][2], stage["dr"], stage["ds"][0]):
             stage["buf"] = multigpu.allgather_ranges(plane, stage["ranges"], rank, world, stage["buf"])
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(); tt.append(time.perf_counter())
         # planar [PD][n] views for the C ABI: rows of the staging tensors are N+per apart, so hand each set over plane by plane
         xs = torch.stack([stage["dx"][d, :N] for d in range(3)]).contiguous()
         g.set_sources_ptr(N, xs.data_ptr(), stage["dr"].data_ptr(), stage["ds"].data_ptr())
-        g.set_targets_ptr(N, xs.data_ptr(), stage["dr"].data_ptr())
-        hot_path()
+        g.set_targets_ptr(N, xs.data_ptr(), stage["dr"].data_ptr()); tt.append(time.perf_counter())
+        hot_path(); tt.append(time.perf_counter())
         slo, shi = g.shard_particle_range(N, rank, world)
         for d in range(3):
             hu[d, slo:shi].copy_(g.plane_tensor(1, 7 + d, N)[slo:shi], non_blocking=True)
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(); tt.append(time.perf_counter())
+        stage.setdefault("trace", []).append([round((b_ - a_) * 1e3, 1) for a_, b_ in zip(tt, tt[1:])])
         return g.timer_stop_ms()
 
     def step_e2e():
@@ -357,7 +359,7 @@ def run_ours(args):
                    "theta": THETA, "order": ORDER, "block": BLOCK, "n_particles": N,
                    "parallelism": ("target leaves sharded x%d; tree builds split by particle range, planes replicated by NCCL all-gather" % world) if world > 1 else "single GPU",
                    "l2_policy": "inputs larger than L2 (%.0f MB of particle planes per tree vs 126 MB L2); every step rebuilds from pristine input" % (N * 24 / 1e6)},
-        "seconds_per_step": sec_res, "ms_steps": [round(v, 2) for v in res_steps], "e2e_ms_steps": [round(v, 2) for v in e2e_steps], "seconds_per_eval": ph_res.get("eval", 0.0) / K * 1e-3, "pairs_per_step": pairs_total,
+        "seconds_per_step": sec_res, "ms_steps": [round(v, 2) for v in res_steps], "e2e_ms_steps": [round(v, 2) for v in e2e_steps], "e2e_trace_h2d_gather_set_hot_d2h": stage.get("trace", [])[-len(e2e_steps):], "seconds_per_eval": ph_res.get("eval", 0.0) / K * 1e-3, "pairs_per_step": pairs_total,
         "phases_ms": {k: v / K for k, v in ph_res.items()},
         "e2e": {"value": e2e, "unit": "Ginteractions/s", "h2d_bytes_per_step": h2d if world == 1 else hx.numel() * 4 + hr.numel() * 4 + hs.numel() * 4, "d2h_bytes_per_step": d2h, "ms_per_step": sec_e2e * 1e3,
                 "note": "single GPU: sources and targets are copied separately (same host arrays twice). multi GPU: every input plane crosses PCIe once in total (1/world per rank) and is replicated over NVLink; each rank returns its own target shard" if world > 1 else "sources and targets copied separately from pinned host memory; all outputs copied back"},

@@ -526,12 +526,13 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
     else ONB_CUDA(onb_dmalloc(c, (void**)&own_g, (size_t)n * 4));
     // grid-wide select state for the big nodes of the top levels
     const uint32_t max_big_nodes = n / BIG_NODE + 2, max_chunks = n / BIG_CH + max_big_nodes + 1;
-    BigNode* bignodes = nullptr; uint32_t *nbig = nullptr, *chunk_owner = nullptr, *cntA = nullptr, *cntB = nullptr;
+    BigNode* bignodes = nullptr; uint32_t *nbig = nullptr, *chunk_owner = nullptr, *cntA = nullptr, *cntB = nullptr, *bwl = nullptr;
     if (n > BIG_NODE) {
         ONB_CUDA(onb_dmalloc(c, (void**)&bignodes, (size_t)max_big_nodes * sizeof(BigNode)));
-        ONB_CUDA(onb_dmalloc(c, (void**)&nbig, 16));
+        ONB_CUDA(onb_dmalloc(c, (void**)&nbig, 64));
         ONB_CUDA(onb_dmalloc(c, (void**)&chunk_owner, (size_t)max_chunks * 4));
         ONB_CUDA(onb_dmalloc(c, (void**)&cntA, (size_t)max_chunks * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&cntB, (size_t)max_chunks * 4));
+        ONB_CUDA(onb_dmalloc(c, (void**)&bwl, (size_t)max_chunks * 8));
     }
 
     const int TB = 256; const uint32_t GB = (n + TB - 1) / TB;
@@ -551,7 +552,7 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
         if (leftmost > BIG_NODE) {
             BigArgs ba;
             for (int d = 0; d < 3; ++d) ba.x[d] = cx[d];
-            ba.t = view_of(t); ba.nodes = bignodes; ba.nbig = nbig; ba.chunk_owner = chunk_owner; ba.cntA = cntA; ba.cntB = cntB;
+            ba.t = view_of(t); ba.nodes = bignodes; ba.nbig = nbig; ba.chunk_owner = chunk_owner; ba.cntA = cntA; ba.cntB = cntB; ba.wl = bwl;
             ba.lidx = lidx; ba.scr = scr; ba.axis_of = axis_of; ba.pmid = pmid; ba.stats = c->d_build_stats;
             ba.block = c->block; ba.big = BIG_NODE; ba.level = lev; ba.PD = PD; ba.pivot_mode = onb_pivot_mode;
             ba.blo = blo; ba.bhi = bhi;

@@ -38,6 +38,7 @@ struct BigArgs {
     BigNode* nodes; uint32_t* nbig;        // nbig[0] = number of big nodes of this level, nbig[1] = total chunks, nbig[2] = still active
     uint32_t* chunk_owner;                 // chunk -> index into nodes
     uint32_t* cntA; uint32_t* cntB;        // per chunk: counts, then exclusive offsets
+    uint32_t* wl;                          // 2 x max_chunks: the chunks that intersect a live window, by pass parity (count in nbig[4], nbig[5])
     uint32_t* lidx; uint32_t* scr;
     uint8_t* axis_of; uint32_t* pmid;
     unsigned long long* stats;
@@ -239,6 +240,20 @@ __device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const u
         b.w[(it + 1) & 1] = nw;
         b.m = 0; b.mx_enc = 0u; b.mn_enc = 0xffffffffu;
         if (nw.done) atomicSub(&a.nbig[2], 1u);
+        // the chunks the next pass has to visit
+        s_carry[0] = 0; s_carry[1] = 0;
+        if (!nw.done) {
+            const uint32_t q0 = (nw.wf - b.pf) / BIG_CH, q1 = (nw.wl - b.pf) / BIG_CH;
+            s_carry[0] = q1 - q0 + 1;
+            s_carry[1] = atomicAdd(&a.nbig[4 + ((it + 1) & 1)], q1 - q0 + 1);
+            s_wa[0] = b.chunk0 + q0;
+        }
+    }
+    __syncthreads();
+    {
+        const uint32_t nq = s_carry[0], base = s_carry[1], first = s_wa[0];
+        uint32_t* out = a.wl + (size_t)((it + 1) & 1) * a.max_chunks + base;
+        for (uint32_t j = threadIdx.x; j < nq; j += 256) out[j] = first + j;
     }
 }
 
@@ -279,8 +294,9 @@ __device__ __forceinline__ void big_compact(const BigArgs& a, const int it, cons
 
 __device__ __forceinline__ void big_swap(const BigArgs& a, const int it, const uint32_t chunk) {
     BigNode& b = a.nodes[a.chunk_owner[chunk]];
-    if (b.w[it & 1].done) return;
-    const uint32_t k = b.k, q = chunk - b.chunk0;
+    const BigWin w = b.w[it & 1];
+    if (w.done) return;
+    const uint32_t k = b.k, q = (chunk - b.chunk0) - (w.wf - b.pf) / BIG_CH;      // my rank among the chunks of the node's window
     float* key = a.x[b.axis];
     const uint32_t j1 = min(k, (q + 1) * BIG_CH);
     for (uint32_t j = q * BIG_CH + threadIdx.x; j < j1; j += BIG_T) {                     // barneshut.hpp:549-556
@@ -314,15 +330,20 @@ __global__ void __launch_bounds__(BIG_T) k_big_level(const BigArgs a) {
     for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_bbox(a, 0, ch); __syncthreads(); }
     grid.sync();
     for (uint32_t bi = gtid; bi < nnodes; bi += gthreads) big_setup(a, bi);
+    for (uint32_t i = gtid; i < nchunks; i += gthreads) a.wl[i] = i;            // pass 0 visits every chunk
+    if (gtid == 0) { a.nbig[4] = nchunks; a.nbig[5] = 0; }
     grid.sync();
     for (int it = 0; it < 104; ++it) {
-        for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_count(a, it, ch); __syncthreads(); }
+        const uint32_t* wl = a.wl + (size_t)(it & 1) * a.max_chunks;
+        const uint32_t nw = a.nbig[4 + (it & 1)];
+        if (gtid == 0) a.nbig[4 + ((it + 1) & 1)] = 0;                            // filled by this pass's scan
+        for (uint32_t i = blockIdx.x; i < nw; i += gridDim.x) { big_count(a, it, wl[i]); __syncthreads(); }
         grid.sync();
         for (uint32_t bi = blockIdx.x; bi < nnodes; bi += gridDim.x) { big_scan(a, it, bi); __syncthreads(); }
         grid.sync();
-        for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_compact(a, it, ch); __syncthreads(); }
+        for (uint32_t i = blockIdx.x; i < nw; i += gridDim.x) { big_compact(a, it, wl[i]); __syncthreads(); }
         grid.sync();
-        for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_swap(a, it, ch); __syncthreads(); }
+        for (uint32_t i = blockIdx.x; i < nw; i += gridDim.x) { big_swap(a, it, wl[i]); __syncthreads(); }
         grid.sync();
         if (a.nbig[2] == 0) break;        // every node of the level has met one of the reference's exit conditions
     }
