@@ -21,6 +21,7 @@
  * planes. All traffic is HBM/L2 streaming: the roofline for this file is memory bandwidth.
  */
 #include "onb_internal.h"
+#include <cstdlib>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -487,7 +488,12 @@ extern "C" int onb_get_build_stats(onb_context* c, uint64_t out[5]) {
 static int onb_pivot_mode = 0;   // 0 = the reference source evaluated in IEEE order; 1 = as g++ -O3 -ffast-math contracts it
 extern "C" void onb_set_pivot_mode(int mode) { onb_pivot_mode = mode ? 1 : 0; }
 
-static const uint32_t BIG_NODE = 16384;     // nodes above this are split by the grid-wide kernels of tree_big.cuh
+static uint32_t big_node_threshold() {      // nodes above this are split by the grid-wide kernel of tree_big.cuh
+    static uint32_t v = 0;
+    if (!v) { v = 32768; if (const char* e = std::getenv("ONB_BIG_NODE")) v = (uint32_t)std::max(2048, atoi(e)); }
+    return v;
+}
+#define BIG_NODE (big_node_threshold())     // nodes above this are split by the grid-wide kernels of tree_big.cuh
 
 static int run_finish(onb_context* c, DParts& p, DTree& t) {      // finishTree :717-807
     FinishArgs fa; fa.p = view_of(p); fa.t = view_of(t); fa.block = c->block; fa.PD = c->PD; fa.SD = c->SD; fa.are_sources = p.are_sources ? 1 : 0;
@@ -563,7 +569,9 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
                 static int coop_blocks_per_sm = 0;
                 if (!coop_blocks_per_sm) {
                     ONB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks_per_sm, k_big_level, BIG_T, 0));
-                    coop_blocks_per_sm = std::max(1, std::min(coop_blocks_per_sm, 4));
+                    int want = 4;
+                    if (const char* e = std::getenv("ONB_BIG_BLOCKS_PER_SM")) want = std::max(1, atoi(e));
+                    coop_blocks_per_sm = std::max(1, std::min(coop_blocks_per_sm, want));
                 }
                 const uint32_t grid = std::min<uint32_t>(chunks_ub, (uint32_t)(c->sm_count * coop_blocks_per_sm));
                 void* args[] = { (void*)&ba };
