@@ -251,3 +251,44 @@ def test_range_restricted_builds_reproduce_the_full_build():
         got_u[:, lo:hi] = p["u"][:, lo:hi]; got_g[lo:hi] = p["gidx"][lo:hi]
     assert bits_equal(got_g, want_u["gidx"])
     assert bits_equal(got_u, want_u["u"])
+
+
+def _run_generic(s, xs, rs, ss, xt, rt, theta, tsk):
+    """phase sequence with caller-supplied, DIFFERENT source and target clouds"""
+    out = {}
+    s.set_sources(xs, rs, ss); s.set_targets(xt, rt)
+    s.make_tree(0); s.upward(0); s.make_tree(1); s.refine(1); s.upward(1)
+    out["srcs.x"] = s.parts(0)["x"]; out["targs.gidx"] = s.parts(1)["gidx"]; out["eqsrcs.s"] = s.parts(2)["s"]
+    s.zero_vels(); s.naive(tsk); out["naive.u"] = s.parts(1)["u"]
+    for name in ("treecode1", "treecode2", "treecode3"):
+        s.zero_vels(); out[name + ".flops"] = getattr(s, name)(theta); out[name + ".u"] = s.parts(1)["u"]
+    if s.has_fastsumm:
+        s.zero_vels(); s.fastsumm(theta); out["fastsumm.u"] = s.parts(1)["u"]
+    return out
+
+
+@pytest.mark.parametrize("physics,ns,nt,block,order", [
+    ("grav3d", 9000, 5000, 128, 4), ("grav3d", 5000, 9000, 64, 3), ("grav3d", 7001, 7003, 50, 2), ("grav3d", 3000, 300, 16, 1),
+    ("vort3d", 4000, 6000, 100, 4), ("vortgrad3d", 5000, 3000, 128, 3), ("vort2d", 6000, 8000, 128, 10), ("vort2dtr", 8000, 6000, 30, 6),
+    ("grav3d", 1, 1, 128, 4), ("grav3d", 2, 3, 128, 4), ("grav3d", 128, 129, 128, 4), ("vort2dtr", 257, 100, 128, 4)])
+def test_strict_bit_exact_unequal_clouds_blocks_orders(physics, ns, nt, block, order):
+    """sources != targets (count and positions), block sizes other than 128 (incl. one that is not a multiple of 4, which
+    exercises the unaligned-tile path of the pair kernel), orders 1..10, and degenerate sizes (single particle, single leaf)"""
+    from onbody_b200.api import GpuSession, ARITH_STRICT, _DIMS
+    from oracle.refapi import PortSession
+    PD, SD, OD = _DIMS[physics]
+    rng = np.random.RandomState(ns * 7 + nt)
+    f = lambda *sh: np.ascontiguousarray(rng.uniform(-1, 1, sh).astype(np.float32))
+    xs, ss, xt = f(PD, ns), (f(SD, ns) / ns).astype(np.float32), (0.9 * f(PD, nt) + 0.05).astype(np.float32)
+    rs = (np.full(ns, max(ns, 2) ** (-1.0 / PD)) * (0.5 + rng.rand(ns))).astype(np.float32)
+    rt = (np.full(nt, 0.3 * max(nt, 2) ** (-1.0 / PD))).astype(np.float32)
+    o = PortSession(physics, ns, nt, block=block, order=order, eq_block=128)
+    g = GpuSession(physics, ns, nt, block=block, order=order, arith=ARITH_STRICT)
+    theta, tsk = 1.25, max(1, nt // 300)
+    a = _run_generic(o, xs, rs, ss, xt, rt, theta, tsk)
+    b = _run_generic(g, xs, rs, ss, xt, rt, theta, tsk)
+    for k, v in a.items():
+        if isinstance(v, np.ndarray):
+            assert bits_equal(v, b[k]), k
+        else:
+            assert v == b[k], (k, v, b[k])
