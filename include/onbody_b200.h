@@ -94,6 +94,10 @@ ONB_API int onb_make_tree(onb_context* c, int which);
  * the host language) and call onb_finish_tree, which recomputes every node array bottom-up, bit-identical to a full build. */
 ONB_API int onb_make_tree_range(onb_context* c, int which, uint64_t lo, uint64_t hi);
 ONB_API int onb_finish_tree(onb_context* c, int which);
+/* source and target tree in one call: the two (independent) builds are enqueued on two streams and overlap on the device;
+ * results are identical to two onb_make_tree[_range] calls */
+ONB_API int onb_make_trees(onb_context* c);
+ONB_API int onb_make_trees_range(onb_context* c, uint64_t src_lo, uint64_t src_hi, uint64_t tgt_lo, uint64_t tgt_hi);
 /* restrict the following onb_refine to the leaves of [lo,hi) again (onb_finish_tree resets the range to the whole set) */
 ONB_API int onb_set_build_range(onb_context* c, int which, uint64_t lo, uint64_t hi);
 /* the tree-order particle range of shard `rank` of `nranks` for a set of n particles (contiguous leaves) */

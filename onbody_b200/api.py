@@ -56,6 +56,8 @@ def load_library():
         getattr(L, fn).argtypes = [C.c_void_p, C.c_int]
     L.onb_make_tree_range.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
     L.onb_finish_tree.argtypes = [C.c_void_p, C.c_int]
+    L.onb_make_trees.argtypes = [C.c_void_p]
+    L.onb_make_trees_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]
     L.onb_set_build_range.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
     L.onb_shard_particle_range.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, _u64p, _u64p]
     L.onb_device_ptr.restype = C.c_void_p
@@ -182,6 +184,8 @@ class GpuSession:
     def make_tree(self, which): self._chk(self.lib.onb_make_tree(self.h, which))
     def make_tree_range(self, which, lo, hi): self._chk(self.lib.onb_make_tree_range(self.h, which, lo, hi))
     def finish_tree(self, which): self._chk(self.lib.onb_finish_tree(self.h, which))
+    def make_trees(self): self._chk(self.lib.onb_make_trees(self.h))
+    def make_trees_range(self, slo, shi, tlo, thi): self._chk(self.lib.onb_make_trees_range(self.h, slo, shi, tlo, thi))
     def set_build_range(self, which, lo, hi): self._chk(self.lib.onb_set_build_range(self.h, which, lo, hi))
 
     def shard_particle_range(self, n, rank, nranks):

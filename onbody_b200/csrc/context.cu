@@ -148,7 +148,8 @@ onb_context* onb_create(int physics, int device) {
         g_create_error = "context allocation failed"; delete c; return nullptr;
     }
     cudaMemset(c->d_flag, 0, sizeof(int));
-    cudaMalloc(&c->d_build_stats, 8 * sizeof(unsigned long long)); cudaMemset(c->d_build_stats, 0, 8 * sizeof(unsigned long long));
+    cudaMalloc(&c->d_build_stats, 16 * sizeof(unsigned long long)); cudaMemset(c->d_build_stats, 0, 16 * sizeof(unsigned long long));
+    cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
     onb_set_params(c, 128, 4, ONB_ARITH_FAST);
     return c;
 }
@@ -163,6 +164,7 @@ void onb_destroy(onb_context* c) {
     if (c->d_build_stats) cudaFree(c->d_build_stats);
     for (auto& sl : c->slabs) cudaFree(sl.p);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -245,6 +247,38 @@ int onb_make_tree_range(onb_context* c, int which, uint64_t lo, uint64_t hi) {
     return rc;
 }
 int onb_make_tree(onb_context* c, int which) { return onb_make_tree_range(c, which, 0, ~0ull); }
+
+// Both trees at once: the two builds are independent and their top levels are latency bound (grid-wide barriers around
+// short passes), so they are enqueued on two streams and overlap on the device.
+int onb_make_trees_range(onb_context* c, uint64_t slo, uint64_t shi, uint64_t tlo, uint64_t thi) {
+    onb_scratch_reset(c);
+    if (c->parts[0].n == 0 || c->parts[1].n == 0) { c->err = "make_trees: set sources and targets first"; return ONB_ERR_ARG; }
+    ONB_CUDA(cudaSetDevice(c->device));
+    int rc = onb_alloc_tree(c, c->trees[0], c->parts[0].n, c->block);
+    if (rc == ONB_OK) rc = onb_alloc_tree(c, c->trees[1], c->parts[1].n, c->block);
+    if (rc) return rc;
+    cudaEvent_t e0, e1, e2;
+    ONB_CUDA(cudaEventCreate(&e0)); ONB_CUDA(cudaEventCreate(&e1)); ONB_CUDA(cudaEventCreate(&e2));
+    ONB_CUDA(cudaEventRecord(e0, c->stream));
+    ONB_CUDA(cudaStreamWaitEvent(c->stream2, e0, 0));
+    c->concurrent_builds = true;
+    rc = onb_tree_build(c, c->parts[0], c->trees[0], (uint32_t)slo, (uint32_t)std::min<uint64_t>(shi, c->parts[0].n));
+    if (rc == ONB_OK) {
+        c->cur_stream = c->stream2; c->cur_stats_off = 8;
+        rc = onb_tree_build(c, c->parts[1], c->trees[1], (uint32_t)tlo, (uint32_t)std::min<uint64_t>(thi, c->parts[1].n));
+        c->cur_stream = nullptr; c->cur_stats_off = 0;
+    }
+    c->concurrent_builds = false;
+    ONB_CUDA(cudaEventRecord(e1, c->stream2));
+    ONB_CUDA(cudaStreamWaitEvent(c->stream, e1, 0));
+    ONB_CUDA(cudaEventRecord(e2, c->stream));
+    ONB_CUDA(cudaEventSynchronize(e2));
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e2);
+    c->phase_ms["tree"] = ms; c->phase_ms["trees"] = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return rc;
+}
+int onb_make_trees(onb_context* c) { return onb_make_trees_range(c, 0, ~0ull, 0, ~0ull); }
 int onb_finish_tree(onb_context* c, int which) {
     onb_scratch_reset(c);
     if (which < 0 || which > 1) return ONB_ERR_ARG;

@@ -104,7 +104,10 @@ struct onb_context {
     struct Slab { char* p; size_t cap; };
     std::vector<Slab> slabs;
     size_t slab_cur = 0, slab_off = 0;
-    unsigned long long* d_build_stats = nullptr;   // selects, passes, stalls, scanned, tie sorts
+    unsigned long long* d_build_stats = nullptr;   // selects, passes, stalls, scanned, tie sorts (x2: second slot for a concurrent build)
+    cudaStream_t stream2 = nullptr, cur_stream = nullptr;   // second stream for building both trees concurrently
+    int cur_stats_off = 0;
+    bool concurrent_builds = false;
 };
 
 #define ONB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \

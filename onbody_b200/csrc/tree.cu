@@ -25,6 +25,10 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
+// the stream / statistics slot of the build being enqueued (onb_make_trees enqueues two builds on two streams)
+#define ONB_ST(c) ((c)->cur_stream ? (c)->cur_stream : (c)->stream)
+#define ONB_STATS(c) ((c)->d_build_stats + (c)->cur_stats_off)
+
 namespace {
 
 __device__ __forceinline__ float warp_min(float v) { for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
@@ -497,11 +501,11 @@ static uint32_t big_node_threshold() {      // nodes above this are split by the
 
 static int run_finish(onb_context* c, DParts& p, DTree& t) {      // finishTree :717-807
     FinishArgs fa; fa.p = view_of(p); fa.t = view_of(t); fa.block = c->block; fa.PD = c->PD; fa.SD = c->SD; fa.are_sources = p.are_sources ? 1 : 0;
-    k_finish_leaves<<<((size_t)t.numnodes * 32 + 255) / 256, 256, 0, c->stream>>>(fa); ONB_LAUNCH(c);
+    k_finish_leaves<<<((size_t)t.numnodes * 32 + 255) / 256, 256, 0, ONB_ST(c)>>>(fa); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
     for (int lev = t.levels - 2; lev >= 0; --lev) {
         const uint32_t nn = 1u << lev;
-        k_finish_parents<<<(nn + 127) / 128, 128, 0, c->stream>>>(fa, lev); ONB_LAUNCH(c);
+        k_finish_parents<<<(nn + 127) / 128, 128, 0, ONB_ST(c)>>>(fa, lev); ONB_LAUNCH(c);
     }
     ONB_CUDA(cudaGetLastError());
     return ONB_OK;
@@ -514,7 +518,7 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
     p.build_lo = blo; p.build_hi = bhi;
     const int PD = c->PD, SD = p.are_sources ? c->SD : 0;
     if (n == 0) { c->err = "make_tree: no particles"; return ONB_ERR_ARG; }
-    ONB_CUDA(cudaMemsetAsync(c->d_build_stats, 0, 4 * sizeof(unsigned long long), c->stream));
+    ONB_CUDA(cudaMemsetAsync(ONB_STATS(c), 0, 4 * sizeof(unsigned long long), ONB_ST(c)));
 
     // scratch: second copy of every plane (ping-pong), per-particle index planes, per-node split records
     const size_t capf = (size_t)p.cap * sizeof(float);
@@ -542,11 +546,11 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
     }
 
     const int TB = 256; const uint32_t GB = (n + TB - 1) / TB;
-    k_fill_u32<<<GB, TB, 0, c->stream>>>(own_g, n, 0, 1); ONB_LAUNCH(c);                 // gidx = iota :823
-    k_fill_u32<<<GB, TB, 0, c->stream>>>(owner, n, 1, 0); ONB_LAUNCH(c);
-    ONB_CUDA(cudaMemsetAsync(t.num, 0, (size_t)t.numnodes * 4, c->stream));
-    ONB_CUDA(cudaMemsetAsync(t.ioffset, 0, (size_t)t.numnodes * 4, c->stream));
-    { const uint32_t root[1] = { n }; ONB_CUDA(cudaMemcpyAsync(t.num + 1, root, 4, cudaMemcpyHostToDevice, c->stream)); }
+    k_fill_u32<<<GB, TB, 0, ONB_ST(c)>>>(own_g, n, 0, 1); ONB_LAUNCH(c);                 // gidx = iota :823
+    k_fill_u32<<<GB, TB, 0, ONB_ST(c)>>>(owner, n, 1, 0); ONB_LAUNCH(c);
+    ONB_CUDA(cudaMemsetAsync(t.num, 0, (size_t)t.numnodes * 4, ONB_ST(c)));
+    ONB_CUDA(cudaMemsetAsync(t.ioffset, 0, (size_t)t.numnodes * 4, ONB_ST(c)));
+    { const uint32_t root[1] = { n }; ONB_CUDA(cudaMemcpyAsync(t.num + 1, root, 4, cudaMemcpyHostToDevice, ONB_ST(c))); }
 
     float* cx[3] = { p.x[0], p.x[1], p.x[2] }; float* cr = p.r; float* cs[3] = { p.s[0], p.s[1], p.s[2] }; uint32_t* cg = own_g;
     float* ax[3] = { alt_x[0], alt_x[1], alt_x[2] }; float* ar = alt_r; float* as[3] = { alt_s[0], alt_s[1], alt_s[2] }; uint32_t* ag = alt_g;
@@ -559,7 +563,7 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
             BigArgs ba;
             for (int d = 0; d < 3; ++d) ba.x[d] = cx[d];
             ba.t = view_of(t); ba.nodes = bignodes; ba.nbig = nbig; ba.chunk_owner = chunk_owner; ba.cntA = cntA; ba.cntB = cntB; ba.wl = bwl;
-            ba.lidx = lidx; ba.scr = scr; ba.axis_of = axis_of; ba.pmid = pmid; ba.stats = c->d_build_stats;
+            ba.lidx = lidx; ba.scr = scr; ba.axis_of = axis_of; ba.pmid = pmid; ba.stats = ONB_STATS(c);
             ba.block = c->block; ba.big = BIG_NODE; ba.level = lev; ba.PD = PD; ba.pivot_mode = onb_pivot_mode;
             ba.blo = blo; ba.bhi = bhi;
             const uint32_t lev_nodes = std::min<uint64_t>(1ull << lev, max_big_nodes);
@@ -573,21 +577,23 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
                     if (const char* e = std::getenv("ONB_BIG_BLOCKS_PER_SM")) want = std::max(1, atoi(e));
                     coop_blocks_per_sm = std::max(1, std::min(coop_blocks_per_sm, want));
                 }
-                const uint32_t grid = std::min<uint32_t>(chunks_ub, (uint32_t)(c->sm_count * coop_blocks_per_sm));
+                // two builds in flight (onb_make_trees): both cooperative grids must be resident at once, one CTA per SM each
+                const int per_sm = c->concurrent_builds ? 1 : coop_blocks_per_sm;
+                const uint32_t grid = std::min<uint32_t>(chunks_ub, (uint32_t)(c->sm_count * per_sm));
                 void* args[] = { (void*)&ba };
-                ONB_CUDA(cudaLaunchCooperativeKernel((void*)k_big_level, dim3(grid), dim3(BIG_T), args, 0, c->stream)); ONB_LAUNCH(c);
+                ONB_CUDA(cudaLaunchCooperativeKernel((void*)k_big_level, dim3(grid), dim3(BIG_T), args, 0, ONB_ST(c))); ONB_LAUNCH(c);
             }
             ONB_CUDA(cudaGetLastError());
         }
         SplitArgs sa;
         for (int d = 0; d < 3; ++d) sa.x[d] = cx[d];
-        sa.t = view_of(t); sa.axis_of = axis_of; sa.pmid = pmid; sa.lidx = lidx; sa.scr = scr; sa.stats = c->d_build_stats;
+        sa.t = view_of(t); sa.axis_of = axis_of; sa.pmid = pmid; sa.lidx = lidx; sa.scr = scr; sa.stats = ONB_STATS(c);
         sa.block = c->block; sa.big = BIG_NODE; sa.blo = blo; sa.bhi = bhi; sa.level = lev; sa.PD = PD; sa.pivot_mode = onb_pivot_mode;
         // ~8 particles per thread: small nodes get small CTAs so that several share an SM and hide each other's barriers
         int threads = 1024;
         const uint32_t largest_small = std::min(leftmost, BIG_NODE);
         while (threads > 64 && (uint32_t)threads * 8 > largest_small) threads >>= 1;
-        k_node_split<<<1u << lev, threads, 0, c->stream>>>(sa); ONB_LAUNCH(c);
+        k_node_split<<<1u << lev, threads, 0, ONB_ST(c)>>>(sa); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
         if (leftmost <= (uint32_t)c->block) break;     // every node of this level is a leaf: nothing below
         GatherArgs ga;
@@ -595,7 +601,7 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
         ga.sr = cr; ga.dr = ar; ga.sg = cg; ga.dg = ag;
         ga.lidx = lidx; ga.owner = owner; ga.axis_of = axis_of; ga.pmid = pmid; ga.num = t.num; ga.ioffset = t.ioffset;
         ga.n = epl; ga.span_lo = spf; ga.blo = blo; ga.bhi = bhi; ga.block = c->block; ga.level = lev; ga.PD = PD; ga.SD = SD;
-        k_gather<<<(epl - spf + TB - 1) / TB, TB, 0, c->stream>>>(ga); ONB_LAUNCH(c);
+        k_gather<<<(epl - spf + TB - 1) / TB, TB, 0, ONB_ST(c)>>>(ga); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
         for (int d = 0; d < 3; ++d) { std::swap(cx[d], ax[d]); std::swap(cs[d], as[d]); }
         std::swap(cr, ar); std::swap(cg, ag);
@@ -609,8 +615,8 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
         GatherArgs ga;
         for (int d = 0; d < 3; ++d) { ga.sx[d] = cx[d]; ga.dx[d] = p.x[d]; ga.ss[d] = cs[d]; ga.ds[d] = p.s[d]; }
         ga.sr = cr; ga.dr = p.r; ga.n = epl; ga.span_lo = spf; ga.PD = PD; ga.SD = SD;
-        k_copy_planes<<<(epl - spf + TB - 1) / TB, TB, 0, c->stream>>>(ga); ONB_LAUNCH(c);
-        if (!p.are_sources) ONB_CUDA(cudaMemcpyAsync(p.gidx + spf, cg + spf, (size_t)(epl - spf) * 4, cudaMemcpyDeviceToDevice, c->stream));
+        k_copy_planes<<<(epl - spf + TB - 1) / TB, TB, 0, ONB_ST(c)>>>(ga); ONB_LAUNCH(c);
+        if (!p.are_sources) ONB_CUDA(cudaMemcpyAsync(p.gidx + spf, cg + spf, (size_t)(epl - spf) * 4, cudaMemcpyDeviceToDevice, ONB_ST(c)));
     }
     p.packed_valid = false;
 
@@ -628,12 +634,12 @@ int onb_tree_finish_from_particles(onb_context* c, DParts& p, DTree& t) {
     float* lohi = nullptr;
     ONB_CUDA(onb_dmalloc(c, (void**)&lohi, (size_t)6 * t.numnodes * sizeof(float)));
     FinishArgs fa; fa.p = view_of(p); fa.t = view_of(t); fa.block = c->block; fa.PD = c->PD; fa.SD = c->SD; fa.are_sources = p.are_sources ? 1 : 0;
-    k_bbox_leaves<<<((size_t)t.numnodes * 32 + 255) / 256, 256, 0, c->stream>>>(fa, lohi); ONB_LAUNCH(c);
+    k_bbox_leaves<<<((size_t)t.numnodes * 32 + 255) / 256, 256, 0, ONB_ST(c)>>>(fa, lohi); ONB_LAUNCH(c);
     for (int lev = t.levels - 2; lev >= 0; --lev) {
         const uint32_t nn = 1u << lev;
-        k_bbox_parents<<<(nn + 127) / 128, 128, 0, c->stream>>>(fa, lohi, lev); ONB_LAUNCH(c);
+        k_bbox_parents<<<(nn + 127) / 128, 128, 0, ONB_ST(c)>>>(fa, lohi, lev); ONB_LAUNCH(c);
     }
-    k_bbox_final<<<(t.numnodes + 127) / 128, 128, 0, c->stream>>>(fa, lohi); ONB_LAUNCH(c);
+    k_bbox_final<<<(t.numnodes + 127) / 128, 128, 0, ONB_ST(c)>>>(fa, lohi); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
     p.build_lo = 0; p.build_hi = p.n;
     p.packed_valid = false;
@@ -643,13 +649,13 @@ int onb_tree_finish_from_particles(onb_context* c, DParts& p, DTree& t) {
 int onb_tree_refine(onb_context* c, DParts& p, DTree& t) {
     if (!t.built) { c->err = "refine: tree not built"; return ONB_ERR_ARG; }
     if (c->block > 128) { c->err = "refine: block size > 128 not supported by the GPU build"; return ONB_ERR_UNSUPPORTED; }
-    ONB_CUDA(cudaMemsetAsync(c->d_build_stats + 4, 0, sizeof(unsigned long long), c->stream));
+    ONB_CUDA(cudaMemsetAsync(ONB_STATS(c) + 4, 0, sizeof(unsigned long long), ONB_ST(c)));
     RefineArgs ra; ra.p = view_of(p); ra.n = p.n; ra.block = c->block; ra.PD = c->PD; ra.SD = c->SD; ra.OD = c->OD;
-    ra.are_sources = p.are_sources ? 1 : 0; ra.flag = c->d_flag; ra.tie_sorts = c->d_build_stats + 4;
+    ra.are_sources = p.are_sources ? 1 : 0; ra.flag = c->d_flag; ra.tie_sorts = ONB_STATS(c) + 4;
     // leaves of the build range only (whole tree unless onb_make_tree_range restricted it; ranges are leaf aligned)
     const uint32_t leaf0 = p.build_lo / c->block, leaf1 = (std::min(p.build_hi, p.n) + c->block - 1) / c->block;
     ra.leaf0 = leaf0;
-    k_refine<<<leaf1 - leaf0, 128, 0, c->stream>>>(ra); ONB_LAUNCH(c);
+    k_refine<<<leaf1 - leaf0, 128, 0, ONB_ST(c)>>>(ra); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
     p.packed_valid = false;
     return onb_check_flag(c, "refine (introsort depth limit: libstdc++ heapsort fallback is not restated)");

@@ -292,3 +292,18 @@ def test_strict_bit_exact_unequal_clouds_blocks_orders(physics, ns, nt, block, o
             assert bits_equal(v, b[k]), k
         else:
             assert v == b[k], (k, v, b[k])
+
+
+def test_concurrent_tree_builds_equal_sequential():
+    """onb_make_trees (two streams) must give exactly the arrays of two onb_make_tree calls"""
+    n = 300000
+    a = _gpu("grav3d", n); a.init_driver(); a.make_tree(0); a.make_tree(1)
+    b = _gpu("grav3d", n); b.init_driver(); b.make_trees()
+    for which in (0, 1):
+        pa, pb = a.parts(which), b.parts(which)
+        for k in ("x", "r", "s", "gidx"):
+            if pa[k] is not None:
+                assert bits_equal(pa[k], pb[k]), (which, k)
+        ta, tb = a.tree(which), b.tree(which)
+        for k in ("num", "ioffset", "nc", "ns", "nr", "x", "s", "pr"):
+            assert bits_equal(ta[k], tb[k]), (which, k)
