@@ -108,6 +108,8 @@ struct onb_context {
     cudaStream_t stream2 = nullptr, cur_stream = nullptr;   // second stream for building both trees concurrently
     int cur_stats_off = 0;
     bool concurrent_builds = false;
+    std::vector<uint64_t> dtt_sizes;      // per level: interaction / deferred list sizes of the last dual-tree evaluation
+    bool dtt_sizes_valid = false;
 };
 
 #define ONB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \

@@ -108,7 +108,7 @@ struct P2PArgs {
     const float4* e_pk0; const float4* e_pk1; const float* e_pk2;   // equivalent sources
     const uint32_t* s_ioffset; const uint32_t* s_num;
     const uint32_t* item_node; const uint32_t* start; const uint32_t* entries;
-    uint32_t block, ebs, num_eqps, node_base;
+    uint32_t block, ebs, num_eqps, node_base, nentries;
 };
 
 __device__ __forceinline__ TileRef decode_entry(const P2PArgs& a, uint32_t entry) {
@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__
     __shared__ TileSmem<PHYS> sm;
     const int tid = threadIdx.x;
     const uint32_t w = blockIdx.x;
-    const uint32_t e0 = a.start[w], e1 = a.start[w + 1];
-    if (e0 == e1) return;
+    const uint32_t e0 = min(a.start[w], a.nentries), e1 = min(a.start[w + 1], a.nentries);   // never read past the allocated list
+    if (e0 >= e1) return;
     const uint32_t T = a.item_node ? a.item_node[w] : a.node_base + w;
     const uint32_t tn = a.t_num[T];
     const bool leaf = tn <= a.block;
@@ -365,7 +365,7 @@ int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tg
     a.e_pk0 = eqs.pk0; a.e_pk1 = eqs.pk1; a.e_pk2 = eqs.pk2;
     a.s_ioffset = c->trees[0].ioffset; a.s_num = c->trees[0].num;
     a.item_node = wl.tgt_node; a.start = wl.start; a.entries = wl.entries;
-    a.block = c->block; a.ebs = c->ebs; a.num_eqps = c->num_eqps; a.node_base = wl.node_base;
+    a.block = c->block; a.ebs = c->ebs; a.num_eqps = c->num_eqps; a.node_base = wl.node_base; a.nentries = (uint32_t)wl.nentries;
     switch (c->physics) {
         case ONB_GRAV3D:     launch_lists<ONB_GRAV3D>(c, a, wl.nitems); break;
         case ONB_VORT3D:     launch_lists<ONB_VORT3D>(c, a, wl.nitems); break;

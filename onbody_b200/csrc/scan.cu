@@ -61,6 +61,6 @@ int onb_exclusive_scan_u32(onb_context* c, const uint32_t* in, uint32_t* out, ui
         ONB_CUDA(cudaStreamSynchronize(c->stream));
         *total = (uint64_t)last_out + (uint64_t)last_in;
     }
-    if (sums) { ONB_CUDA(cudaStreamSynchronize(c->stream)); onb_dfree(c, sums); }
+    (void)sums;      // arena scratch: released at the next phase
     return ONB_OK;
 }

@@ -99,11 +99,12 @@ struct DttArgs {
     int level; uint32_t nnodes;             // target nodes of this level: T = 2^level + local
     // inherited lists = the parent's deferred list
     const uint32_t* pc_start;               // per node of level-1 (+1); null at the root level
-    const uint32_t* pc_entries;
+    const uint32_t* pc_entries; uint32_t pccap;
     // outputs
     uint32_t* icount; uint32_t* ccount;     // count pass, per node of this level
     const uint32_t* istart; const uint32_t* cstart;   // fill pass
     uint32_t* ientries; uint32_t* centries;
+    uint32_t icap, ccap;                    // allocated entries (a stale size cache must not cause out-of-bounds writes)
     uint32_t* queue; uint32_t qcap;         // per-warp FIFO scratch: 2 x qcap entries per warp slot
     unsigned long long* stats;              // [2] sltl [3] sbtl [4] sltb [5] sbtb [6] tlc [7] lpc [8] bpc [9] pairs
     int* flag;
@@ -135,7 +136,11 @@ __global__ void __launch_bounds__(256) k_dtt(const DttArgs a) {
         const uint32_t* cur; uint32_t len;
         uint32_t root_list = 1;
         if (a.level == 0) { cur = nullptr; len = 1; }
-        else { const uint32_t pl = (T >> 1) - (1u << (a.level - 1)); cur = a.pc_entries + a.pc_start[pl]; len = a.pc_start[pl + 1] - a.pc_start[pl]; }
+        else {
+            const uint32_t pl = (T >> 1) - (1u << (a.level - 1));
+            const uint32_t s0 = min(a.pc_start[pl], a.pccap), s1 = min(a.pc_start[pl + 1], a.pccap);     // clamp to the allocated list
+            cur = a.pc_entries + s0; len = s1 - s0;
+        }
         uint32_t nI = 0, nC = 0;
         uint32_t* oI = FILL ? a.ientries + a.istart[local] : nullptr;
         uint32_t* oC = FILL ? a.centries + a.cstart[local] : nullptr;
@@ -173,11 +178,12 @@ __global__ void __launch_bounds__(256) k_dtt(const DttArgs a) {
                 if (outcome == 4) { const uint32_t pos = nextlen + 2u * __popc(bX & lt_mask); nxt[pos] = 2 * S; nxt[pos + 1] = 2 * S + 1; }   // :374,:395
                 if (FILL) {
                     if (outcome == 1 || outcome == 2) {
-                        oI[nI + __popc(bE & lt_mask)] = outcome == 2 ? (S | 0x80000000u) : S;
+                        const uint32_t pos = a.istart[local] + nI + __popc(bE & lt_mask);
+                        if (pos < a.icap) a.ientries[pos] = outcome == 2 ? (S | 0x80000000u) : S;
                         st_pairs += (unsigned long long)(outcome == 2 ? a.num_eqps : sn) * tcnt;
                         if (outcome == 1) { if (tleaf) ++st_sltl; else ++st_sltb; } else { if (tleaf) ++st_sbtl; else ++st_sbtb; }
                     }
-                    if (outcome == 3) oC[nC + __popc(bC & lt_mask)] = S;
+                    if (outcome == 3) { const uint32_t pos = a.cstart[local] + nC + __popc(bC & lt_mask); if (pos < a.ccap) a.centries[pos] = S; }
                 }
                 nI += __popc(bE); nC += __popc(bC); nextlen += 2u * __popc(bX);
             }
@@ -260,7 +266,12 @@ int onb_lists_boxwise(onb_context* c, float theta, WorkList& wl) {
     return rc;
 }
 
-int onb_run_fastsumm(onb_context* c, float theta) {
+// One dual-tree evaluation. List storage for level l can only be sized once level l's count pass has run, which would cost
+// three host round trips per level (~70 per evaluation, each one exposed to host scheduling noise). The list sizes of the
+// previous evaluation are therefore cached per context: when they are available the whole evaluation is enqueued without a
+// single host synchronisation and the sizes are verified at the end (same particles, same theta -> same lists); on a miss
+// (first call, new input) the evaluation is redone on the synchronous path, which also refreshes the cache.
+static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cache_ok) {
     DTree& st = c->trees[0]; DTree& tt = c->trees[1];
     uint32_t lo, hi; onb_shard_range(c, &lo, &hi);
     unsigned long long* d_stats = nullptr;
@@ -271,18 +282,23 @@ int onb_run_fastsumm(onb_context* c, float theta) {
     const uint32_t qcap = 8192;
     uint32_t* queue = nullptr;
     ONB_CUDA(onb_dmalloc(c, (void**)&queue, (size_t)max_blocks * WPB * 2 * qcap * 4));
+    const int L = tt.levels;
+    uint32_t* d_totals = nullptr;            // [2*L]: itotal, ctotal per level (for the end-of-pass verification)
+    ONB_CUDA(onb_dmalloc(c, (void**)&d_totals, (size_t)2 * L * 4));
+    std::vector<uint64_t> sizes(2 * L, 0);
+    if (use_cache) sizes = c->dtt_sizes;
 
     uint32_t *pc_start = nullptr, *pc_entries = nullptr;     // previous level's deferred lists
-    double ms_lists = 0.0, ms_p2p = 0.0, ms_down = 0.0;
-    cudaEvent_t ev[4]; for (int i = 0; i < 4; ++i) cudaEventCreate(&ev[i]);
+    std::vector<cudaEvent_t> ev((size_t)4 * L);
+    for (auto& e : ev) cudaEventCreate(&e);
     int rc = ONB_OK;
-    for (int lev = 0; lev < tt.levels && rc == ONB_OK; ++lev) {
+    for (int lev = 0; lev < L && rc == ONB_OK; ++lev) {
         const uint32_t nn = 1u << lev;
-        cudaEventRecord(ev[0], c->stream);
+        cudaEventRecord(ev[4 * lev + 0], c->stream);
         uint32_t *istart = nullptr, *cstart = nullptr, *ientries = nullptr, *centries = nullptr;
         ONB_CUDA(onb_dmalloc(c, (void**)&istart, (size_t)(nn + 1) * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&cstart, (size_t)(nn + 1) * 4));
         DttArgs a; a.st = view_of(st); a.tt = view_of(tt); a.level = lev; a.nnodes = nn;
-        a.pc_start = pc_start; a.pc_entries = pc_entries;
+        a.pc_start = pc_start; a.pc_entries = pc_entries; a.pccap = lev > 0 ? (uint32_t)sizes[2 * (lev - 1) + 1] : 0u;
         a.icount = istart; a.ccount = cstart; a.istart = istart; a.cstart = cstart; a.ientries = nullptr; a.centries = nullptr;
         a.queue = queue; a.qcap = qcap; a.stats = d_stats; a.flag = c->d_flag;
         a.block = c->block; a.num_eqps = c->num_eqps; a.shard_lo = lo; a.shard_hi = hi; a.PD = c->PD; a.theta = theta;
@@ -291,36 +307,68 @@ int onb_run_fastsumm(onb_context* c, float theta) {
         ONB_CUDA(cudaGetLastError());
         ONB_CUDA(cudaMemsetAsync(istart + nn, 0, 4, c->stream)); ONB_CUDA(cudaMemsetAsync(cstart + nn, 0, 4, c->stream));
         uint64_t itotal = 0, ctotal = 0;
-        if ((rc = onb_exclusive_scan_u32(c, istart, istart, nn + 1, &itotal))) break;
-        if ((rc = onb_exclusive_scan_u32(c, cstart, cstart, nn + 1, &ctotal))) break;
-        if ((rc = onb_check_flag(c, "dual-tree traversal: per-node source FIFO overflow"))) break;
-        if (itotal >= 0xffffffffull || ctotal >= 0xffffffffull) { c->err = "fastsumm: list exceeds 2^32 entries on one GPU"; rc = ONB_ERR_CAPACITY; break; }
+        if (use_cache) {
+            if ((rc = onb_exclusive_scan_u32(c, istart, istart, nn + 1, nullptr))) break;
+            if ((rc = onb_exclusive_scan_u32(c, cstart, cstart, nn + 1, nullptr))) break;
+            itotal = sizes[2 * lev]; ctotal = sizes[2 * lev + 1];
+        } else {
+            if ((rc = onb_exclusive_scan_u32(c, istart, istart, nn + 1, &itotal))) break;
+            if ((rc = onb_exclusive_scan_u32(c, cstart, cstart, nn + 1, &ctotal))) break;
+            if ((rc = onb_check_flag(c, "dual-tree traversal: per-node source FIFO overflow"))) break;
+            if (itotal >= 0xffffffffull || ctotal >= 0xffffffffull) { c->err = "fastsumm: list exceeds 2^32 entries on one GPU"; rc = ONB_ERR_CAPACITY; break; }
+            sizes[2 * lev] = itotal; sizes[2 * lev + 1] = ctotal;
+        }
+        // after the exclusive scan the appended last element holds the total
+        ONB_CUDA(cudaMemcpyAsync(d_totals + 2 * lev, istart + nn, 4, cudaMemcpyDeviceToDevice, c->stream));
+        ONB_CUDA(cudaMemcpyAsync(d_totals + 2 * lev + 1, cstart + nn, 4, cudaMemcpyDeviceToDevice, c->stream));
         ONB_CUDA(onb_dmalloc(c, (void**)&ientries, std::max<size_t>(4, (size_t)itotal * 4)));
         ONB_CUDA(onb_dmalloc(c, (void**)&centries, std::max<size_t>(4, (size_t)ctotal * 4)));
         a.ientries = ientries; a.centries = centries;
+        a.icap = (uint32_t)itotal; a.ccap = (uint32_t)ctotal;
         k_dtt<true><<<blocks, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
-        cudaEventRecord(ev[1], c->stream);
+        cudaEventRecord(ev[4 * lev + 1], c->stream);
         // node entry: zero + interpolate from the parent (ongrav3d.cpp:232-304)
         if ((rc = onb_bary_downward_level(c, lev))) break;
-        cudaEventRecord(ev[2], c->stream);
+        cudaEventRecord(ev[4 * lev + 2], c->stream);
         // then this level's interactions, in list order, on top of the interpolated values (:315-402)
         WorkList wl; wl.nitems = nn; wl.tgt_node = nullptr; wl.node_base = nn; wl.start = istart; wl.entries = ientries; wl.nentries = itotal;
         if (itotal > 0) if ((rc = onb_p2p_lists(c, wl, 1, 3, true))) break;
-        cudaEventRecord(ev[3], c->stream);
-        ONB_CUDA(cudaStreamSynchronize(c->stream));
-        float t01 = 0, t12 = 0, t23 = 0;
-        cudaEventElapsedTime(&t01, ev[0], ev[1]); cudaEventElapsedTime(&t12, ev[1], ev[2]); cudaEventElapsedTime(&t23, ev[2], ev[3]);
-        ms_lists += t01; ms_down += t12; ms_p2p += t23;
-        onb_dfree(c, istart); onb_dfree(c, ientries);
-        if (pc_start) onb_dfree(c, pc_start); if (pc_entries) onb_dfree(c, pc_entries);
+        cudaEventRecord(ev[4 * lev + 3], c->stream);
         pc_start = cstart; pc_entries = centries;
     }
-    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
-    if (pc_start) onb_dfree(c, pc_start); if (pc_entries) onb_dfree(c, pc_entries);
-    onb_dfree(c, queue);
-    if (rc == ONB_OK) rc = fetch_stats(c, d_stats);
-    onb_dfree(c, d_stats);
+    double ms_lists = 0.0, ms_p2p = 0.0, ms_down = 0.0;
+    *cache_ok = true;
+    if (rc == ONB_OK) {
+        std::vector<uint32_t> h_tot(2 * L);
+        ONB_CUDA(cudaMemcpyAsync(h_tot.data(), d_totals, (size_t)2 * L * 4, cudaMemcpyDeviceToHost, c->stream));
+        ONB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int lev = 0; lev < L; ++lev) {
+            float t01 = 0, t12 = 0, t23 = 0;
+            cudaEventElapsedTime(&t01, ev[4 * lev], ev[4 * lev + 1]); cudaEventElapsedTime(&t12, ev[4 * lev + 1], ev[4 * lev + 2]); cudaEventElapsedTime(&t23, ev[4 * lev + 2], ev[4 * lev + 3]);
+            ms_lists += t01; ms_down += t12; ms_p2p += t23;
+            if (h_tot[2 * lev] != (uint32_t)sizes[2 * lev] || h_tot[2 * lev + 1] != (uint32_t)sizes[2 * lev + 1]) *cache_ok = false;
+        }
+        if (use_cache && *cache_ok) rc = onb_check_flag(c, "dual-tree traversal: per-node source FIFO overflow");
+        if (!use_cache) { c->dtt_sizes = sizes; c->dtt_sizes_valid = true; }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc == ONB_OK && *cache_ok) rc = fetch_stats(c, d_stats);
     c->phase_ms["lists"] = ms_lists; c->phase_ms["downward"] = ms_down; c->phase_ms["p2p"] = ms_p2p;
     return rc;
+}
+
+int onb_run_fastsumm(onb_context* c, float theta) {
+    const bool try_cache = c->dtt_sizes_valid && (int)c->dtt_sizes.size() == 2 * c->trees[1].levels;
+    bool ok = true;
+    if (try_cache) {
+        int rc = fastsumm_pass(c, theta, true, &ok);
+        if (rc != ONB_OK) return rc;
+        if (ok) return ONB_OK;
+        // the cached list sizes did not match this input: discard the pass (kernels clamp their writes to the allocated
+        // capacity) and redo it on the synchronous path
+        ONB_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+        onb_scratch_reset(c);
+    }
+    return fastsumm_pass(c, theta, false, &ok);
 }

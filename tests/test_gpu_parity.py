@@ -307,3 +307,22 @@ def test_concurrent_tree_builds_equal_sequential():
         ta, tb = a.tree(which), b.tree(which)
         for k in ("num", "ioffset", "nc", "ns", "nr", "x", "s", "pr"):
             assert bits_equal(ta[k], tb[k]), (which, k)
+
+
+def test_fastsumm_size_cache_hit_and_miss():
+    """second evaluation runs without host synchronisation from cached list sizes; a different theta must fall back cleanly"""
+    n = 60000
+    g = _gpu("grav3d", n)
+    g.init_driver(); g.make_trees(); g.upward(0); g.refine(1); g.upward(1)
+    res = {}
+    for i, th in enumerate((1.4, 1.4, 1.4, 1.1, 1.1, 1.4)):       # miss(first), hit, hit, miss, hit, miss
+        g.zero_vels(); g.fastsumm(th)
+        u = g.parts(1, ("u",))["u"]; st = g.stats(); pr = g.last_pairs()
+        if th in res:
+            assert bits_equal(u, res[th][0]) and st == res[th][1] and pr == res[th][2], (i, th)
+        else:
+            res[th] = (u, st, pr)
+    h = _gpu("grav3d", n)
+    h.init_driver(); h.make_tree(0); h.upward(0); h.make_tree(1); h.refine(1); h.upward(1)
+    h.zero_vels(); h.fastsumm(1.1)
+    assert bits_equal(h.parts(1, ("u",))["u"], res[1.1][0]) and h.stats() == res[1.1][1]
