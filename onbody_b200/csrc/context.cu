@@ -5,6 +5,7 @@
  * device is missing.
  */
 #include "onb_internal.h"
+#include <cstdlib>
 
 #include <algorithm>
 #include <cmath>
@@ -261,10 +262,11 @@ int onb_make_trees_range(onb_context* c, uint64_t slo, uint64_t shi, uint64_t tl
     ONB_CUDA(cudaEventCreate(&e0)); ONB_CUDA(cudaEventCreate(&e1)); ONB_CUDA(cudaEventCreate(&e2));
     ONB_CUDA(cudaEventRecord(e0, c->stream));
     ONB_CUDA(cudaStreamWaitEvent(c->stream2, e0, 0));
-    c->concurrent_builds = true;
+    static const bool seq_builds = std::getenv("ONB_SEQ_BUILDS") != nullptr;      // diagnostics: one build after the other
+    c->concurrent_builds = !seq_builds;
     rc = onb_tree_build(c, c->parts[0], c->trees[0], (uint32_t)slo, (uint32_t)std::min<uint64_t>(shi, c->parts[0].n));
     if (rc == ONB_OK) {
-        c->cur_stream = c->stream2; c->cur_stats_off = 8;
+        c->cur_stream = seq_builds ? nullptr : c->stream2; c->cur_stats_off = 8;
         rc = onb_tree_build(c, c->parts[1], c->trees[1], (uint32_t)tlo, (uint32_t)std::min<uint64_t>(thi, c->parts[1].n));
         c->cur_stream = nullptr; c->cur_stats_off = 0;
     }

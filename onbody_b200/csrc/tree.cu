@@ -207,13 +207,15 @@ __global__ void __launch_bounds__(1024) k_node_split(const SplitArgs a) {
     }
 }
 
-// ---- per level: permute the other planes by lidx (reorder :475-485, reorder_idx Parts.hpp:188-196) ----
+// ---- per level: permute the other coordinate planes and the composed index plane by lidx (reorder :475-485,
+// reorder_idx Parts.hpp:188-196). Radii and strengths do not travel with the levels: they are permuted once at the
+// end of the build through the composed index (k_apply_perm in tree_sub.cuh).
 struct GatherArgs {
-    float* sx[3]; float* sr; float* ss[3]; uint32_t* sg;     // current
-    float* dx[3]; float* dr; float* ds[3]; uint32_t* dg;     // destination
+    float* sx[3]; uint32_t* sg;     // current
+    float* dx[3]; uint32_t* dg;     // destination
     const uint32_t* lidx; uint32_t* owner;
     const uint8_t* axis_of; const uint32_t* pmid; const uint32_t* num; const uint32_t* ioffset;
-    uint32_t n, block, blo, bhi, span_lo; int level, PD, SD;
+    uint32_t n, block, blo, bhi, span_lo; int level, PD;
 };
 __global__ void k_gather(const GatherArgs a) {
     const uint32_t i = a.span_lo + blockIdx.x * blockDim.x + threadIdx.x;      // n = end of the span covered at this level
@@ -224,8 +226,6 @@ __global__ void k_gather(const GatherArgs a) {
     const uint32_t j = active ? a.lidx[i] : i;
     const int ax = active ? (int)a.axis_of[node] : -1;
     for (int d = 0; d < a.PD; ++d) a.dx[d][i] = a.sx[d][d == ax ? i : j];
-    a.dr[i] = a.sr[j];
-    for (int d = 0; d < a.SD; ++d) a.ds[d][i] = a.ss[d][j];
     a.dg[i] = a.sg[j];
     if (active) a.owner[i] = 2u * node + (i >= a.pmid[node] ? 1u : 0u);
 }
@@ -468,14 +468,7 @@ __global__ void k_bbox_final(const FinishArgs a, const float* lohi) {
 }
 
 #include "tree_big.cuh"
-
-__global__ void k_copy_planes(GatherArgs a) {     // final buffers -> the particle set's own planes (identity gather)
-    const uint32_t i = a.span_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    for (int d = 0; d < a.PD; ++d) a.dx[d][i] = a.sx[d][i];
-    a.dr[i] = a.sr[i];
-    for (int d = 0; d < a.SD; ++d) a.ds[d][i] = a.ss[d][i];
-}
+#include "tree_sub.cuh"
 
 }  // namespace
 
@@ -552,13 +545,27 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
     ONB_CUDA(cudaMemsetAsync(t.ioffset, 0, (size_t)t.numnodes * 4, ONB_ST(c)));
     { const uint32_t root[1] = { n }; ONB_CUDA(cudaMemcpyAsync(t.num + 1, root, 4, cudaMemcpyHostToDevice, ONB_ST(c))); }
 
-    float* cx[3] = { p.x[0], p.x[1], p.x[2] }; float* cr = p.r; float* cs[3] = { p.s[0], p.s[1], p.s[2] }; uint32_t* cg = own_g;
-    float* ax[3] = { alt_x[0], alt_x[1], alt_x[2] }; float* ar = alt_r; float* as[3] = { alt_s[0], alt_s[1], alt_s[2] }; uint32_t* ag = alt_g;
+    float* cx[3] = { p.x[0], p.x[1], p.x[2] }; uint32_t* cg = own_g;
+    float* ax[3] = { alt_x[0], alt_x[1], alt_x[2] }; uint32_t* ag = alt_g;
 
     uint32_t leftmost = n;     // the leftmost node of a level is its largest
     // the nodes of this level that contain the first / last particle of the build range: [spf, epl) is what this level touches
     uint32_t spf = 0, spl = n, epf = 0, epl = n;
     for (int lev = 0; lev < t.levels; ++lev) {
+        if (leftmost <= SUB_MAX && (t.levels - lev) <= 10) {
+            // every node of this level fits in shared memory: one kernel does all the levels below and writes the
+            // final order of the coordinates and the index plane (tree_sub.cuh)
+            static bool attr_set = false;
+            const size_t sub_smem = (size_t)SUB_MAX * (3 * sizeof(float) + 2 * sizeof(uint16_t));
+            if (!attr_set) { ONB_CUDA(cudaFuncSetAttribute(k_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sub_smem)); attr_set = true; }
+            SubArgs sa;
+            for (int d = 0; d < 3; ++d) { sa.x[d] = cx[d]; sa.ox[d] = p.x[d]; }
+            sa.g = cg; sa.og = own_g; sa.t = view_of(t); sa.stats = ONB_STATS(c);
+            sa.block = c->block; sa.blo = blo; sa.bhi = bhi; sa.level = lev; sa.nsub = t.levels - lev; sa.PD = PD; sa.pivot_mode = onb_pivot_mode;
+            k_subtree<<<1u << lev, SUB_T, sub_smem, ONB_ST(c)>>>(sa); ONB_LAUNCH(c);
+            ONB_CUDA(cudaGetLastError());
+            break;
+        }
         if (leftmost > BIG_NODE) {
             BigArgs ba;
             for (int d = 0; d < 3; ++d) ba.x[d] = cx[d];
@@ -570,15 +577,16 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
             ba.max_nodes = lev_nodes; ba.max_chunks = max_chunks;
             const uint32_t chunks_ub = std::min<uint32_t>(max_chunks, n / BIG_CH + lev_nodes + 1);
             {
-                static int coop_blocks_per_sm = 0;
-                if (!coop_blocks_per_sm) {
-                    ONB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks_per_sm, k_big_level, BIG_T, 0));
-                    int want = 4;
-                    if (const char* e = std::getenv("ONB_BIG_BLOCKS_PER_SM")) want = std::max(1, atoi(e));
-                    coop_blocks_per_sm = std::max(1, std::min(coop_blocks_per_sm, want));
+                static int coop_max = 0, coop_want = 4, coop_want_conc = 2;
+                if (!coop_max) {
+                    ONB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_max, k_big_level, BIG_T, 0));
+                    if (const char* e = std::getenv("ONB_BIG_BLOCKS_PER_SM")) coop_want = std::max(1, atoi(e));
+                    if (const char* e = std::getenv("ONB_BIG_BLOCKS_PER_SM_CONC")) coop_want_conc = std::max(1, atoi(e));
+                    coop_max = std::max(1, coop_max);
                 }
-                // two builds in flight (onb_make_trees): both cooperative grids must be resident at once, one CTA per SM each
-                const int per_sm = c->concurrent_builds ? 1 : coop_blocks_per_sm;
+                // two builds in flight (onb_make_trees): both cooperative grids must be resident at once, so each takes
+                // at most half of what fits on an SM
+                const int per_sm = c->concurrent_builds ? std::max(1, std::min(coop_max / 2, coop_want_conc)) : std::min(coop_max, coop_want);
                 const uint32_t grid = std::min<uint32_t>(chunks_ub, (uint32_t)(c->sm_count * per_sm));
                 void* args[] = { (void*)&ba };
                 ONB_CUDA(cudaLaunchCooperativeKernel((void*)k_big_level, dim3(grid), dim3(BIG_T), args, 0, ONB_ST(c))); ONB_LAUNCH(c);
@@ -595,28 +603,31 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
         while (threads > 64 && (uint32_t)threads * 8 > largest_small) threads >>= 1;
         k_node_split<<<1u << lev, threads, 0, ONB_ST(c)>>>(sa); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
-        if (leftmost <= (uint32_t)c->block) break;     // every node of this level is a leaf: nothing below
         GatherArgs ga;
-        for (int d = 0; d < 3; ++d) { ga.sx[d] = cx[d]; ga.dx[d] = ax[d]; ga.ss[d] = cs[d]; ga.ds[d] = as[d]; }
-        ga.sr = cr; ga.dr = ar; ga.sg = cg; ga.dg = ag;
+        for (int d = 0; d < 3; ++d) { ga.sx[d] = cx[d]; ga.dx[d] = ax[d]; }
+        ga.sg = cg; ga.dg = ag;
         ga.lidx = lidx; ga.owner = owner; ga.axis_of = axis_of; ga.pmid = pmid; ga.num = t.num; ga.ioffset = t.ioffset;
-        ga.n = epl; ga.span_lo = spf; ga.blo = blo; ga.bhi = bhi; ga.block = c->block; ga.level = lev; ga.PD = PD; ga.SD = SD;
+        ga.n = epl; ga.span_lo = spf; ga.blo = blo; ga.bhi = bhi; ga.block = c->block; ga.level = lev; ga.PD = PD;
         k_gather<<<(epl - spf + TB - 1) / TB, TB, 0, ONB_ST(c)>>>(ga); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
-        for (int d = 0; d < 3; ++d) { std::swap(cx[d], ax[d]); std::swap(cs[d], as[d]); }
-        std::swap(cr, ar); std::swap(cg, ag);
+        for (int d = 0; d < 3; ++d) std::swap(cx[d], ax[d]);
+        std::swap(cg, ag);
         leftmost = (uint32_t)c->block * (1u << (31 - __builtin_clz((leftmost - 1) / c->block)));
         // descend the two boundary nodes (the split position of a node depends on its size only, barneshut.hpp:663)
         if (spl - spf > (uint32_t)c->block) { const uint32_t pm = spf + (uint32_t)c->block * (1u << (31 - __builtin_clz((spl - spf - 1) / c->block))); if (blo < pm) spl = pm; else spf = pm; }
         if (epl - epf > (uint32_t)c->block) { const uint32_t pm = epf + (uint32_t)c->block * (1u << (31 - __builtin_clz((epl - epf - 1) / c->block))); if (bhi - 1 < pm) epl = pm; else epf = pm; }
     }
-    // after an odd number of levels the final order sits in the scratch copies: bring it home
-    if (cr != p.r) {
-        GatherArgs ga;
-        for (int d = 0; d < 3; ++d) { ga.sx[d] = cx[d]; ga.dx[d] = p.x[d]; ga.ss[d] = cs[d]; ga.ds[d] = p.s[d]; }
-        ga.sr = cr; ga.dr = p.r; ga.n = epl; ga.span_lo = spf; ga.PD = PD; ga.SD = SD;
-        k_copy_planes<<<(epl - spf + TB - 1) / TB, TB, 0, ONB_ST(c)>>>(ga); ONB_LAUNCH(c);
-        if (!p.are_sources) ONB_CUDA(cudaMemcpyAsync(p.gidx + spf, cg + spf, (size_t)(epl - spf) * 4, cudaMemcpyDeviceToDevice, ONB_ST(c)));
+    // radii and strengths: one gather through the composed index (own_g[i] = position of particle i before the build),
+    // out of place into the scratch copies, then home
+    {
+        PermArgs pa; pa.g = own_g; pa.lo = spf; pa.hi = epl; pa.nplanes = 1 + SD;
+        pa.src[0] = p.r; pa.dst[0] = alt_r;
+        for (int d = 0; d < 3; ++d) { pa.src[1 + d] = d < SD ? p.s[d] : nullptr; pa.dst[1 + d] = d < SD ? alt_s[d] : nullptr; }
+        k_apply_perm<<<(epl - spf + TB - 1) / TB, TB, 0, ONB_ST(c)>>>(pa); ONB_LAUNCH(c);
+        PermArgs pb = pa;
+        for (int q = 0; q < 4; ++q) { pb.src[q] = pa.dst[q]; pb.dst[q] = const_cast<float*>(pa.src[q]); }
+        k_copy_back<<<(epl - spf + TB - 1) / TB, TB, 0, ONB_ST(c)>>>(pb); ONB_LAUNCH(c);
+        ONB_CUDA(cudaGetLastError());
     }
     p.packed_valid = false;
 
