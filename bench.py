@@ -90,7 +90,7 @@ class ClockSampler:
                     self.samples.append((float(out[0]), float(out[1]), 0))
             except Exception:
                 pass
-            time.sleep(0.1 if n is not None else 1.0)
+            time.sleep(float(os.environ.get("ONB_CLOCK_PERIOD", "0.1")) if n is not None else 1.0)
 
     def start(self):
         self.thread.start()

@@ -41,6 +41,7 @@ void onb_free_parts(onb_context* c, DParts& p) {
     for (int d = 0; d < ONB_MAX_SD; ++d) if (p.s[d]) onb_pfree(c, p.s[d]);
     for (int d = 0; d < ONB_MAX_OD; ++d) if (p.u[d]) onb_pfree(c, p.u[d]);
     if (p.gidx) onb_pfree(c, p.gidx);
+    if (p.gidx_spare) onb_pfree(c, p.gidx_spare);
     if (p.pk0) onb_pfree(c, p.pk0); if (p.pk1) onb_pfree(c, p.pk1); if (p.pk2) onb_pfree(c, p.pk2);
     p = DParts();
 }
@@ -202,7 +203,7 @@ static int set_parts(onb_context* c, int which, uint64_t n, const float* x, cons
     ONB_CUDA(cudaSetDevice(c->device));
     DParts& p = c->parts[which];
     if (p.n != n) { onb_free_parts(c, p); int rc = onb_alloc_parts(c, p, (uint32_t)n, which == 0); if (rc) return rc; }
-    if (p.gidx) { onb_pfree(c, p.gidx); p.gidx = nullptr; }
+    if (p.gidx) { p.gidx_spare = p.gidx; p.gidx = nullptr; }      // no cudaFree/cudaMalloc per step: the next build takes it back
     const size_t bytes = (size_t)n * sizeof(float);
     for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(p.x[d], x + (size_t)d * n, bytes, cudaMemcpyDefault, c->stream));
     ONB_CUDA(cudaMemcpyAsync(p.r, r, bytes, cudaMemcpyDefault, c->stream));
@@ -527,6 +528,7 @@ int onb_load_tree(onb_context* c, int which, int levels, const float* x, const f
     ONB_CUDA(cudaMemcpy(t.num, nm.data(), n * 4, cudaMemcpyHostToDevice));
     if (which == 1) {   // targets loaded in tree order: original index = position
         DParts& p = c->parts[1];
+        if (!p.gidx && p.gidx_spare) { p.gidx = p.gidx_spare; p.gidx_spare = nullptr; }
         if (!p.gidx) ONB_CUDA(onb_pmalloc(c, (void**)&p.gidx, (size_t)p.n * 4));
         std::vector<uint32_t> id(p.n); for (uint32_t i = 0; i < p.n; ++i) id[i] = i;
         ONB_CUDA(cudaMemcpy(p.gidx, id.data(), (size_t)p.n * 4, cudaMemcpyHostToDevice));

@@ -34,6 +34,7 @@ struct DParts {
     float* s[ONB_MAX_SD] = {nullptr, nullptr, nullptr};
     float* u[ONB_MAX_OD] = {nullptr};
     uint32_t* gidx = nullptr;
+    uint32_t* gidx_spare = nullptr;   // the index plane of the previous build, kept for reuse (gidx == nullptr means "no tree order yet")
     // packed planes for the pair kernels (see p2p.cu):
     //   grav3d          pk0 = (x,y,z,s)      pk2 = r^2
     //   vort3d/vortgrad pk0 = (x,y,z,r^2)    pk1 = (sx,sy,sz,0)

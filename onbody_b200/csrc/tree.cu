@@ -525,7 +525,11 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
     ONB_CUDA(onb_dmalloc(c, (void**)&pmid, (size_t)t.numnodes * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&axis_of, (size_t)t.numnodes));
     // the tree-order index plane is persistent for targets (gidx), scratch for sources (dropped, barneshut.hpp:853)
     uint32_t* own_g = nullptr;
-    if (!p.are_sources) { if (!p.gidx) ONB_CUDA(onb_pmalloc(c, (void**)&p.gidx, (size_t)n * 4)); own_g = p.gidx; }
+    if (!p.are_sources) {
+        if (!p.gidx && p.gidx_spare) { p.gidx = p.gidx_spare; p.gidx_spare = nullptr; }
+        if (!p.gidx) ONB_CUDA(onb_pmalloc(c, (void**)&p.gidx, (size_t)n * 4));
+        own_g = p.gidx;
+    }
     else ONB_CUDA(onb_dmalloc(c, (void**)&own_g, (size_t)n * 4));
     // grid-wide select state for the big nodes of the top levels
     const uint32_t max_big_nodes = n / BIG_NODE + 2, max_chunks = n / BIG_CH + max_big_nodes + 1;
