@@ -289,12 +289,15 @@ def run_ours(args):
     def step_e2e():
         if world > 1:
             return step_e2e_multi()
+        g.set_async_inputs(True)       # pinned buffers: the target copy overlaps the source tree build (onb_set_async_inputs)
         g.timer_start()
         g.set_sources_ptr(N, hx.data_ptr(), hr.data_ptr(), hs.data_ptr())      # pinned host -> device
         g.set_targets_ptr(N, hx.data_ptr(), hr.data_ptr())
         hot_path()
         g.results_into(hu.data_ptr())                                          # device -> pinned host
-        return g.timer_stop_ms()
+        ms = g.timer_stop_ms()
+        g.set_async_inputs(False)
+        return ms
 
     for _ in range(max(args.warmup, 1)):
         step_resident()

@@ -81,6 +81,12 @@ ONB_API void onb_dims(const onb_context* c, int* pd, int* sd, int* od, int* has_
  * speed - or device memory, the copy kind is resolved by unified addressing) ------------------------------ */
 ONB_API int onb_set_sources(onb_context* c, uint64_t n, const float* x, const float* r, const float* s);
 ONB_API int onb_set_targets(onb_context* c, uint64_t n, const float* x, const float* r);
+/* opt-in: with on != 0, set_sources / set_targets return as soon as the copies from PINNED host (or device) buffers
+ * are enqueued; the source copy runs on the context's stream and the target copy on its second stream, so that
+ * onb_make_trees builds the source tree while the targets are still crossing PCIe. The caller must leave the
+ * buffers untouched until the next phase call that consumes them has returned (every phase call blocks). Pageable
+ * buffers are still copied synchronously. Default off: the copies complete before set_* returns. */
+ONB_API int onb_set_async_inputs(onb_context* c, int on);
 /* the drivers' own synthetic initialisation (std::mt19937(12345), Parts.hpp:99-109,169-176), done on the
  * host into caller buffers: x [PD][n], r [n], s [SD][n] (s may be NULL for targets). strength_mode 1 = wave_strengths */
 ONB_API int onb_driver_inputs(int physics, uint64_t n, int strength_mode, float* x, float* r, float* s);

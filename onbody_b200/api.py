@@ -68,6 +68,7 @@ def load_library():
         getattr(L, fn).argtypes = [C.c_void_p, C.c_float, _f32p]
     L.onb_fastsumm.argtypes = [C.c_void_p, C.c_float]
     L.onb_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.onb_set_async_inputs.argtypes = [C.c_void_p, C.c_int]
     L.onb_count.restype = C.c_uint64
     L.onb_count.argtypes = [C.c_void_p, C.c_int]
     L.onb_get_parts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -176,6 +177,9 @@ class GpuSession:
     def set_targets_ptr(self, n, x_ptr, r_ptr):
         self.ntarg = n
         self._chk(self.lib.onb_set_targets(self.h, n, x_ptr, r_ptr))
+
+    def set_async_inputs(self, on):
+        self._chk(self.lib.onb_set_async_inputs(self.h, 1 if on else 0))
 
     def set_shard(self, rank, nranks):
         self._chk(self.lib.onb_set_shard(self.h, rank, nranks))

@@ -95,7 +95,15 @@ cudaError_t onb_dmalloc(onb_context* c, void** p, size_t bytes) {
     *p = s.p;
     return cudaSuccess;
 }
+int onb_join_copies(onb_context* c) {
+    if (c->tgt_copy_pending) {
+        c->tgt_copy_pending = false;
+        ONB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_tgt_ready, 0));
+    }
+    return ONB_OK;
+}
 void onb_scratch_reset(onb_context* c) {
+    onb_join_copies(c);
     if (c->slabs.size() > 1) {          // coalesce what the last call needed into one slab
         cudaStreamSynchronize(c->stream);
         size_t total = 0;
@@ -166,6 +174,8 @@ void onb_destroy(onb_context* c) {
     if (c->d_build_stats) cudaFree(c->d_build_stats);
     for (auto& sl : c->slabs) cudaFree(sl.p);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->ev_tgt_ready) cudaEventDestroy(c->ev_tgt_ready);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -205,14 +215,35 @@ static int set_parts(onb_context* c, int which, uint64_t n, const float* x, cons
     if (p.n != n) { onb_free_parts(c, p); int rc = onb_alloc_parts(c, p, (uint32_t)n, which == 0); if (rc) return rc; }
     if (p.gidx) { p.gidx_spare = p.gidx; p.gidx = nullptr; }      // no cudaFree/cudaMalloc per step: the next build takes it back
     const size_t bytes = (size_t)n * sizeof(float);
-    for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(p.x[d], x + (size_t)d * n, bytes, cudaMemcpyDefault, c->stream));
-    ONB_CUDA(cudaMemcpyAsync(p.r, r, bytes, cudaMemcpyDefault, c->stream));
-    if (which == 0) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(p.s[d], s + (size_t)d * n, bytes, cudaMemcpyDefault, c->stream));
-    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    bool async = false;
+    if (c->async_inputs) {      // only buffers the copy engine reads directly can be left in flight
+        cudaPointerAttributes at;
+        async = true;
+        const float* ptrs[3] = { x, r, which == 0 ? s : x };
+        for (const float* q : ptrs) {
+            if (cudaPointerGetAttributes(&at, q) != cudaSuccess) { cudaGetLastError(); async = false; break; }
+            if (at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) { async = false; break; }
+        }
+    }
+    cudaStream_t st = c->stream;
+    if (async && which == 1) {
+        // targets travel on the second stream, behind whatever the context stream has enqueued so far (the source copy)
+        { int jrc = onb_join_copies(c); if (jrc) return jrc; }
+        if (!c->ev_copy) { ONB_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming)); ONB_CUDA(cudaEventCreateWithFlags(&c->ev_tgt_ready, cudaEventDisableTiming)); }
+        ONB_CUDA(cudaEventRecord(c->ev_copy, c->stream));
+        ONB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_copy, 0));
+        st = c->stream2;
+    }
+    for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(p.x[d], x + (size_t)d * n, bytes, cudaMemcpyDefault, st));
+    ONB_CUDA(cudaMemcpyAsync(p.r, r, bytes, cudaMemcpyDefault, st));
+    if (which == 0) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(p.s[d], s + (size_t)d * n, bytes, cudaMemcpyDefault, st));
+    if (!async) ONB_CUDA(cudaStreamSynchronize(st));
+    else if (which == 1) { ONB_CUDA(cudaEventRecord(c->ev_tgt_ready, c->stream2)); c->tgt_copy_pending = true; }
     p.packed_valid = false;
     c->trees[which].built = false;
     return ONB_OK;
 }
+int onb_set_async_inputs(onb_context* c, int on) { if (!c) return ONB_ERR_ARG; c->async_inputs = on != 0; return ONB_OK; }
 int onb_set_sources(onb_context* c, uint64_t n, const float* x, const float* r, const float* s) { return set_parts(c, 0, n, x, r, s); }
 int onb_set_targets(onb_context* c, uint64_t n, const float* x, const float* r) { return set_parts(c, 1, n, x, r, nullptr); }
 
@@ -253,6 +284,11 @@ int onb_make_tree(onb_context* c, int which) { return onb_make_tree_range(c, whi
 // Both trees at once: the two builds are independent and their top levels are latency bound (grid-wide barriers around
 // short passes), so they are enqueued on two streams and overlap on the device.
 int onb_make_trees_range(onb_context* c, uint64_t slo, uint64_t shi, uint64_t tlo, uint64_t thi) {
+    static const bool seq_builds = std::getenv("ONB_SEQ_BUILDS") != nullptr;      // diagnostics: one build after the other
+    // a pending asynchronous target copy sits on stream2, where the target build is enqueued behind it: the source
+    // build on the context stream need not wait for it (the streams are joined at the end of this call)
+    const bool tgt_in_flight = c->tgt_copy_pending && !seq_builds;
+    if (tgt_in_flight) c->tgt_copy_pending = false;
     onb_scratch_reset(c);
     if (c->parts[0].n == 0 || c->parts[1].n == 0) { c->err = "make_trees: set sources and targets first"; return ONB_ERR_ARG; }
     ONB_CUDA(cudaSetDevice(c->device));
@@ -263,7 +299,6 @@ int onb_make_trees_range(onb_context* c, uint64_t slo, uint64_t shi, uint64_t tl
     ONB_CUDA(cudaEventCreate(&e0)); ONB_CUDA(cudaEventCreate(&e1)); ONB_CUDA(cudaEventCreate(&e2));
     ONB_CUDA(cudaEventRecord(e0, c->stream));
     ONB_CUDA(cudaStreamWaitEvent(c->stream2, e0, 0));
-    static const bool seq_builds = std::getenv("ONB_SEQ_BUILDS") != nullptr;      // diagnostics: one build after the other
     c->concurrent_builds = !seq_builds;
     rc = onb_tree_build(c, c->parts[0], c->trees[0], (uint32_t)slo, (uint32_t)std::min<uint64_t>(shi, c->parts[0].n));
     if (rc == ONB_OK) {
@@ -406,6 +441,7 @@ int onb_get_parts(onb_context* c, int which, float* x, float* r, float* s, float
     DParts& p = c->parts[which];
     const size_t n = p.n, bytes = n * sizeof(float);
     if (n == 0) return ONB_OK;
+    { int jrc = onb_join_copies(c); if (jrc) return jrc; }
     if (x) for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(x + d * n, p.x[d], bytes, cudaMemcpyDefault, c->stream));
     if (r) ONB_CUDA(cudaMemcpyAsync(r, p.r, bytes, cudaMemcpyDeviceToHost, c->stream));
     if (s && p.are_sources) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(s + d * n, p.s[d], bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -424,6 +460,7 @@ int onb_add_results_original_order(onb_context* c, float* u) {
     DParts& p = c->parts[1];
     const size_t n = p.n;
     if (!p.gidx) { c->err = "targets have no tree order yet"; return ONB_ERR_ARG; }
+    { int jrc = onb_join_copies(c); if (jrc) return jrc; }
     std::vector<uint32_t> g(n); std::vector<float> tmp(n);
     ONB_CUDA(cudaStreamSynchronize(c->stream));
     ONB_CUDA(cudaMemcpy(g.data(), p.gidx, n * 4, cudaMemcpyDeviceToHost));
@@ -496,6 +533,7 @@ uint64_t onb_launch_count(const onb_context* c) { return c->launches; }
 
 void* onb_device_ptr(onb_context* c, int which, int field) {
     if (which < 0 || which > 3) return nullptr;
+    onb_join_copies(c);
     DParts& p = c->parts[which];
     if (field >= 0 && field < 3) return p.x[field];
     if (field == 3) return p.r;

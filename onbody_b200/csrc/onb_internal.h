@@ -111,7 +111,11 @@ struct onb_context {
     bool concurrent_builds = false;
     std::vector<uint64_t> dtt_sizes;      // per level: interaction / deferred list sizes of the last dual-tree evaluation
     bool dtt_sizes_valid = false;
+    // opt-in asynchronous input copies (onb_set_async_inputs): the target planes arrive on stream2
+    bool async_inputs = false, tgt_copy_pending = false;
+    cudaEvent_t ev_copy = nullptr, ev_tgt_ready = nullptr;
 };
+int onb_join_copies(onb_context* c);   // make the context stream wait for a pending asynchronous target copy
 
 #define ONB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
     c->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"; \

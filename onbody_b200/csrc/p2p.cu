@@ -314,6 +314,13 @@ template <int PHYS>
 void launch_lists(onb_context* c, const P2PArgs& a, uint32_t nitems) {
     const bool packed = !(g_p2p_tpt & 16);
     int tpt = (g_p2p_tpt & 15) ? (g_p2p_tpt & 15) : (PHYS == ONB_VORTGRAD3D ? 2 : 4);
+    // The top levels of the dual tree have a handful of target nodes: a launch that cannot fill the machine is bound by the
+    // time ONE warp needs for the longest list, so spread each target block over more warps there (fewer targets per
+    // thread). Per-target sums do not depend on the blocking, results stay bit-identical.
+    if (!(g_p2p_tpt & 15) && c->arith != ONB_ARITH_STRICT) {
+        const uint32_t fill = (uint32_t)c->sm_count * 8u;
+        if (nitems <= fill) tpt = 1; else if (nitems <= 4u * fill && tpt > 2) tpt = 2;
+    }
     if (tpt == 1) launch_lists_t<PHYS, 1>(c, a, nitems, packed);
     else if (tpt == 2) launch_lists_t<PHYS, 2>(c, a, nitems, packed);
     else launch_lists_t<PHYS, 4>(c, a, nitems, packed);

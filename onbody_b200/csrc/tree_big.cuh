@@ -31,6 +31,7 @@ struct BigNode {
     uint32_t B, k;
     uint32_t bmin[3], bmax[3];             // order-encoded bounding box atomics
     uint32_t npass, nstall; unsigned long long nscan;
+    uint32_t arrived, expect;              // count-phase ticket: the last chunk of the node to arrive runs the node's scan
 };
 
 struct BigArgs {
@@ -45,33 +46,41 @@ struct BigArgs {
     uint32_t block, big, max_nodes, max_chunks, blo, bhi; int level, PD, pivot_mode;
 };
 
-// one block: list the big nodes of this level (node order) and lay out their chunks
+// one block: list the big nodes of this level (node order) and lay out their chunks - a block-wide exclusive scan of
+// (is big, number of chunks) over the nodes of the level
 __device__ __forceinline__ void big_list(const BigArgs& a) {                         // one CTA
-    __shared__ uint32_t s_n, s_c;
-    if (threadIdx.x == 0) { s_n = 0; s_c = 0; }
+    __shared__ uint32_t s_wn[BIG_T / 32], s_wc[BIG_T / 32], s_bn, s_bc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_bn = 0; s_bc = 0; }
     __syncthreads();
     const uint32_t first = 1u << a.level, last = 2u << a.level;
-    // serial over nodes in order (<= a few thousand), parallel fill of the chunk table afterwards
-    if (threadIdx.x == 0) {
-        uint32_t nb = 0, nc = 0;
-        for (uint32_t node = first; node < last; ++node) {
-            const uint32_t n = a.t.num[node];
-            const uint32_t pf0 = a.t.ioffset[node];
-            if (n > a.big && nb < a.max_nodes && pf0 < a.bhi && pf0 + n > a.blo) {
-                BigNode& b = a.nodes[nb];
-                b.node = node; b.pf = a.t.ioffset[node]; b.pl = b.pf + n; b.chunk0 = nc; b.nchunks = (n + BIG_CH - 1) / BIG_CH;
-                for (int d = 0; d < 3; ++d) { b.bmin[d] = 0xffffffffu; b.bmax[d] = 0u; }
-                b.m = 0; b.mx_enc = 0u; b.mn_enc = 0xffffffffu; b.npass = 0; b.nstall = 0; b.nscan = 0;
-                nc += b.nchunks; ++nb;
-            }
+    for (uint32_t base = first; base < last; base += BIG_T) {
+        const uint32_t node = base + threadIdx.x;
+        uint32_t flag = 0, nch = 0, n = 0, pf0 = 0;
+        if (node < last) {
+            n = a.t.num[node]; pf0 = a.t.ioffset[node];
+            if (n > a.big && pf0 < a.bhi && pf0 + n > a.blo) { flag = 1; nch = (n + BIG_CH - 1) / BIG_CH; }
         }
-        s_n = nb; s_c = nc; a.nbig[0] = nb; a.nbig[1] = nc; a.nbig[2] = nb;
+        uint32_t in = flag, ic = nch;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t tn = __shfl_up_sync(0xffffffffu, in, o), tc = __shfl_up_sync(0xffffffffu, ic, o); if (lane >= o) { in += tn; ic += tc; } }
+        if (lane == 31) { s_wn[warp] = in; s_wc[warp] = ic; }
+        __syncthreads();
+        uint32_t pn = s_bn, pc = s_bc, tn = 0, tc = 0;
+        for (int q = 0; q < BIG_T / 32; ++q) { if (q < warp) { pn += s_wn[q]; pc += s_wc[q]; } tn += s_wn[q]; tc += s_wc[q]; }
+        const uint32_t nb = pn + in - flag, nc = pc + ic - nch;
+        if (flag && nb < a.max_nodes) {
+            BigNode& b = a.nodes[nb];
+            b.node = node; b.pf = pf0; b.pl = pf0 + n; b.chunk0 = nc; b.nchunks = nch;
+            for (int d = 0; d < 3; ++d) { b.bmin[d] = 0xffffffffu; b.bmax[d] = 0u; }
+            b.m = 0; b.mx_enc = 0u; b.mn_enc = 0xffffffffu; b.npass = 0; b.nstall = 0; b.nscan = 0;
+            b.arrived = 0; b.expect = nch;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_bn += tn; s_bc += tc; }
+        __syncthreads();
     }
-    __syncthreads();
-    for (uint32_t b = 0; b < s_n; ++b) {
-        const uint32_t c0 = a.nodes[b].chunk0, nc = a.nodes[b].nchunks;
-        for (uint32_t q = threadIdx.x; q < nc; q += blockDim.x) a.chunk_owner[c0 + q] = b;
-    }
+    if (threadIdx.x == 0) { const uint32_t nb = min(s_bn, a.max_nodes); a.nbig[0] = nb; a.nbig[1] = s_bc; a.nbig[2] = nb; }
 }
 
 __device__ __forceinline__ float bw_min(float v) { for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
@@ -136,8 +145,11 @@ __device__ __forceinline__ bool big_range(const BigNode& b, const BigWin& w, uin
     return i0 < i1;
 }
 
+__device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const uint32_t bi);
+
 __device__ __forceinline__ void big_count(const BigArgs& a, const int it, const uint32_t chunk) {
-    BigNode& b = a.nodes[a.chunk_owner[chunk]];
+    const uint32_t bi = a.chunk_owner[chunk];
+    BigNode& b = a.nodes[bi];
     const BigWin w = b.w[it & 1];
     uint32_t i0, i1;
     if (!big_range(b, w, chunk, i0, i1)) return;
@@ -154,7 +166,9 @@ __device__ __forceinline__ void big_count(const BigArgs& a, const int it, const 
     #pragma unroll
     for (int r = 0; r < BIG_ROUNDS; ++r) if (ok[r]) { if (v[r] < w.pivot) { ++cnt; mx = fmaxf(mx, v[r]); } else mn = fminf(mn, v[r]); }
     __shared__ uint32_t s_c[BIG_T / 32]; __shared__ float s_mx[BIG_T / 32], s_mn[BIG_T / 32];
+    __shared__ uint32_t s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_last = 0u;
     cnt = bw_sum(cnt); mx = bw_max(mx); mn = bw_min(mn);
     if (lane == 0) { s_c[warp] = cnt; s_mx[warp] = mx; s_mn[warp] = mn; }
     __syncthreads();
@@ -166,21 +180,27 @@ __device__ __forceinline__ void big_count(const BigArgs& a, const int it, const 
             if (cnt) atomicAdd(&b.m, cnt);
             if (mx > -INFINITY) atomicMax(&b.mx_enc, f2ord(mx));
             if (mn < INFINITY) atomicMin(&b.mn_enc, f2ord(mn));
+            // ticket: the last chunk of this node's window to arrive runs the node's scan right here (one grid-wide
+            // barrier less per pass). Release our results, take the ticket, acquire everybody else's.
+            __threadfence();
+            s_last = (atomicAdd(&b.arrived, 1u) + 1u == b.expect) ? 1u : 0u;
         }
     }
+    __syncthreads();
+    if (s_last) { __threadfence(); big_scan(a, it, bi); }
 }
 
 // one CTA per big node. The misplaced counts of a chunk follow from its "< pivot" count and its position relative to
 // B = wf + m (left of B: everything not "<" is misplaced; right of B: everything "<" is); only the one chunk that
 // straddles B needs a second look at its keys. Then: exclusive offsets per chunk, k, and the reference's window update
 // and exit rules (barneshut.hpp:565-585).
-__device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const uint32_t bi) {
+__device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const uint32_t bi) {     // one CTA
     BigNode& b = a.nodes[bi];
     const BigWin w = b.w[it & 1];
     if (w.done) { if (threadIdx.x == 0) b.w[(it + 1) & 1] = w; return; }
     __shared__ uint32_t s_wa[8], s_wb[8], s_carry[2], s_ltl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t B = w.wf + b.m;
+    const uint32_t B = w.wf + *(volatile uint32_t*)&b.m;
     // the straddling chunk: #{v < pivot} among its window elements left of B
     {
         const uint32_t qb = (B - b.pf) / BIG_CH;
@@ -204,7 +224,7 @@ __device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const u
             const uint32_t c0 = b.pf + q * BIG_CH;
             const uint32_t i0 = max(c0, w.wf), i1 = min(min(b.pl, c0 + BIG_CH), w.wl + 1);
             if (i0 < i1) {
-                const uint32_t lt = a.cntA[b.chunk0 + q];
+                const uint32_t lt = __ldcg(&a.cntA[b.chunk0 + q]);
                 if (i1 <= B) va = (i1 - i0) - lt;
                 else if (i0 >= B) vb = lt;
                 else { va = (B - i0) - s_ltl; vb = lt - s_ltl; }
@@ -224,7 +244,7 @@ __device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const u
     }
     if (threadIdx.x == 0) {
         b.B = B; b.k = s_carry[0];
-        const float mx_lt = ord2f(b.mx_enc), mn_ge = ord2f(b.mn_enc);
+        const float mx_lt = ord2f(*(volatile uint32_t*)&b.mx_enc), mn_ge = ord2f(*(volatile uint32_t*)&b.mn_enc);
         b.npass += 1; b.nscan += (w.wl - w.wf + 1);
         BigWin nw = w;
         if (B == b.nless) nw.done = 1;
@@ -238,13 +258,13 @@ __device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const u
             }
         }
         b.w[(it + 1) & 1] = nw;
-        b.m = 0; b.mx_enc = 0u; b.mn_enc = 0xffffffffu;
+        b.m = 0; b.mx_enc = 0u; b.mn_enc = 0xffffffffu; b.arrived = 0; b.expect = 0;
         if (nw.done) atomicSub(&a.nbig[2], 1u);
         // the chunks the next pass has to visit
         s_carry[0] = 0; s_carry[1] = 0;
         if (!nw.done) {
             const uint32_t q0 = (nw.wf - b.pf) / BIG_CH, q1 = (nw.wl - b.pf) / BIG_CH;
-            s_carry[0] = q1 - q0 + 1;
+            s_carry[0] = q1 - q0 + 1; b.expect = q1 - q0 + 1;
             s_carry[1] = atomicAdd(&a.nbig[4 + ((it + 1) & 1)], q1 - q0 + 1);
             s_wa[0] = b.chunk0 + q0;
         }
@@ -320,13 +340,18 @@ __device__ __forceinline__ void big_finish(const BigArgs& a, const uint32_t bi) 
 
 // ---- one cooperative launch per level: every phase of every pass, separated by grid-wide barriers -----------------
 // (one launch instead of ~60: at these sizes the passes are short enough that launch latency dominated them)
-__global__ void __launch_bounds__(BIG_T) k_big_level(const BigArgs a) {
+__global__ void __launch_bounds__(BIG_T, 4) k_big_level(const BigArgs a) {
     cg::grid_group grid = cg::this_grid();
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     if (blockIdx.x == 0) big_list(a);
     grid.sync();
     const uint32_t nnodes = a.nbig[0], nchunks = a.nbig[1];
     if (nnodes == 0) return;
+    for (uint32_t bi = blockIdx.x; bi < nnodes; bi += gridDim.x) {
+        const uint32_t c0 = a.nodes[bi].chunk0, nc = a.nodes[bi].nchunks;
+        for (uint32_t q = threadIdx.x; q < nc; q += blockDim.x) a.chunk_owner[c0 + q] = bi;
+    }
+    grid.sync();
     for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_bbox(a, 0, ch); __syncthreads(); }
     grid.sync();
     for (uint32_t bi = gtid; bi < nnodes; bi += gthreads) big_setup(a, bi);
@@ -336,13 +361,12 @@ __global__ void __launch_bounds__(BIG_T) k_big_level(const BigArgs a) {
     for (int it = 0; it < 104; ++it) {
         const uint32_t* wl = a.wl + (size_t)(it & 1) * a.max_chunks;
         const uint32_t nw = a.nbig[4 + (it & 1)];
-        if (gtid == 0) a.nbig[4 + ((it + 1) & 1)] = 0;                            // filled by this pass's scan
+        // count, and per node (last chunk to arrive) the scan: next window, next pivot, next worklist (parity it+1)
         for (uint32_t i = blockIdx.x; i < nw; i += gridDim.x) { big_count(a, it, wl[i]); __syncthreads(); }
-        grid.sync();
-        for (uint32_t bi = blockIdx.x; bi < nnodes; bi += gridDim.x) { big_scan(a, it, bi); __syncthreads(); }
         grid.sync();
         for (uint32_t i = blockIdx.x; i < nw; i += gridDim.x) { big_compact(a, it, wl[i]); __syncthreads(); }
         grid.sync();
+        if (gtid == 0) a.nbig[4 + (it & 1)] = 0;          // this pass's worklist is consumed (everybody holds nw); pass it+1 refills it for it+2
         for (uint32_t i = blockIdx.x; i < nw; i += gridDim.x) { big_swap(a, it, wl[i]); __syncthreads(); }
         grid.sync();
         if (a.nbig[2] == 0) break;        // every node of the level has met one of the reference's exit conditions
