@@ -31,9 +31,14 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-__device__ __forceinline__ float warp_min(float v) { for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
-__device__ __forceinline__ float warp_max(float v) { for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+// order-preserving float <-> uint encoding (min/max of floats as integer min/max: atomics and redux.sync)
+__device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+// warp reductions in ONE instruction each (redux.sync, sm_80+) instead of five shuffle steps: the select passes are
+// chains of short reductions, their latency is what bounds the small-node kernels
+__device__ __forceinline__ float warp_min(float v) { return ord2f(__reduce_min_sync(0xffffffffu, f2ord(v))); }
+__device__ __forceinline__ float warp_max(float v) { return ord2f(__reduce_max_sync(0xffffffffu, f2ord(v))); }
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
 
 __device__ __forceinline__ uint32_t log_2(uint32_t x) { return x == 0 ? 0u : 31u - __clz(x); }   // Tree.hpp:30-33
 
@@ -47,9 +52,6 @@ __device__ __forceinline__ float select_pivot(uint32_t nless, uint32_t wf, uint3
     const float frac = __double2float_rn(__dmul_rn(__fma_rn(9.0, (double)f0, (double)ideal), 0.1));
     return __fmaf_rn(__fsub_rn(hi, lo), frac, lo);
 }
-__device__ __forceinline__ uint32_t f2ord(float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
-__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
-
 struct SplitArgs {
     float* x[3];            // current coordinate planes (the select permutes x[axis] in place)
     TreeView t;
@@ -168,8 +170,9 @@ __global__ void __launch_bounds__(1024) k_node_split(const SplitArgs a) {
             }
             if (lane == 0) { s_cnt[warp] = totA; s_cnt2[warp] = totB; }
             __syncthreads();
-            uint32_t exA = 0, exB = 0, allA = 0, allB = 0;
-            for (int w = 0; w < W; ++w) { const uint32_t ca = s_cnt[w], cb = s_cnt2[w]; if (w < warp) { exA += ca; exB += cb; } allA += ca; allB += cb; }
+            const uint32_t ca = lane < W ? s_cnt[lane] : 0u, cb = lane < W ? s_cnt2[lane] : 0u;
+            const uint32_t allA = warp_sum(ca), allB = warp_sum(cb);
+            const uint32_t exA = warp_sum(lane < warp ? ca : 0u), exB = warp_sum(lane < warp ? cb : 0u);
             uint32_t offA = carryA + exA, offB = carryB + exB;
             const uint32_t lt_mask = (1u << lane) - 1u;
             #pragma unroll
@@ -552,21 +555,29 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
     float* cx[3] = { p.x[0], p.x[1], p.x[2] }; uint32_t* cg = own_g;
     float* ax[3] = { alt_x[0], alt_x[1], alt_x[2] }; uint32_t* ag = alt_g;
 
+    static uint32_t sub_max = 0;     // particles per shared-memory subtree CTA (tree_sub.cuh): 8192 x 1024 threads or 4096 x 512
+    if (!sub_max) { sub_max = 8192; if (const char* e = std::getenv("ONB_SUB")) sub_max = atoi(e) == 4096 ? 4096u : 8192u; }
     uint32_t leftmost = n;     // the leftmost node of a level is its largest
     // the nodes of this level that contain the first / last particle of the build range: [spf, epl) is what this level touches
     uint32_t spf = 0, spl = n, epf = 0, epl = n;
     for (int lev = 0; lev < t.levels; ++lev) {
-        if (leftmost <= SUB_MAX && (t.levels - lev) <= 10) {
+        if (leftmost <= sub_max && (t.levels - lev) <= 10) {
             // every node of this level fits in shared memory: one kernel does all the levels below and writes the
             // final order of the coordinates and the index plane (tree_sub.cuh)
-            static bool attr_set = false;
-            const size_t sub_smem = (size_t)SUB_MAX * (3 * sizeof(float) + 2 * sizeof(uint16_t));
-            if (!attr_set) { ONB_CUDA(cudaFuncSetAttribute(k_subtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sub_smem)); attr_set = true; }
             SubArgs sa;
             for (int d = 0; d < 3; ++d) { sa.x[d] = cx[d]; sa.ox[d] = p.x[d]; }
             sa.g = cg; sa.og = own_g; sa.t = view_of(t); sa.stats = ONB_STATS(c);
             sa.block = c->block; sa.blo = blo; sa.bhi = bhi; sa.level = lev; sa.nsub = t.levels - lev; sa.PD = PD; sa.pivot_mode = onb_pivot_mode;
-            k_subtree<<<1u << lev, SUB_T, sub_smem, ONB_ST(c)>>>(sa); ONB_LAUNCH(c);
+            const size_t sub_smem = (size_t)sub_max * (3 * sizeof(float) + 2 * sizeof(uint16_t));
+            static bool attr_set = false;
+            if (!attr_set) {
+                ONB_CUDA(cudaFuncSetAttribute(k_subtree<1024, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
+                ONB_CUDA(cudaFuncSetAttribute(k_subtree<512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
+                attr_set = true;
+            }
+            if (sub_max == 8192) k_subtree<1024, 8192><<<1u << lev, 1024, sub_smem, ONB_ST(c)>>>(sa);
+            else                 k_subtree<512, 4096><<<1u << lev, 512, sub_smem, ONB_ST(c)>>>(sa);
+            ONB_LAUNCH(c);
             ONB_CUDA(cudaGetLastError());
             break;
         }

@@ -83,9 +83,9 @@ __device__ __forceinline__ void big_list(const BigArgs& a) {                    
     if (threadIdx.x == 0) { const uint32_t nb = min(s_bn, a.max_nodes); a.nbig[0] = nb; a.nbig[1] = s_bc; a.nbig[2] = nb; }
 }
 
-__device__ __forceinline__ float bw_min(float v) { for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
-__device__ __forceinline__ float bw_max(float v) { for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
-__device__ __forceinline__ uint32_t bw_sum(uint32_t v) { for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+__device__ __forceinline__ float bw_min(float v) { return warp_min(v); }
+__device__ __forceinline__ float bw_max(float v) { return warp_max(v); }
+__device__ __forceinline__ uint32_t bw_sum(uint32_t v) { return warp_sum(v); }
 
 // per chunk: bounding box contribution and lidx = iota (barneshut.hpp:621-625, :516)
 __device__ __forceinline__ void big_bbox(const BigArgs& a, const int it, const uint32_t chunk) {

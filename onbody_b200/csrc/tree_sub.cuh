@@ -1,5 +1,5 @@
 /*
- * tree_sub.cuh - the bottom of the k-d tree build: every level below a node of <= 8192 particles in ONE kernel.
+ * tree_sub.cuh - the bottom of the k-d tree build: every level below a node of <= 8192 (or 4096) particles in ONE kernel.
  *
  * Once a node fits in shared memory there is no reason to go back to HBM between levels: one CTA loads the node's
  * coordinates (plus a 16-bit local index), runs ALL remaining levels of splitNode / partialSortIndexes
@@ -16,9 +16,6 @@
  */
 #pragma once
 
-constexpr int SUB_T = 1024;                   // threads per CTA
-constexpr uint32_t SUB_MAX = 8192;            // particles per CTA
-constexpr int SUB_PER_T = SUB_MAX / SUB_T;    // 8
 constexpr int SUB_TAB = 512;                  // max nodes of one sub-level
 constexpr int SUB_ROUNDS = 4;
 
@@ -35,13 +32,16 @@ struct SubArgs {
 
 struct SubGrp { int tig, T, W, w0, id; };     // thread in group, threads, warps, first warp (CTA-wide index), barrier id
 
+template <int SUB_T>
 __device__ __forceinline__ void sub_sync(const SubGrp& g) {
     if (g.W == 1) __syncwarp();
     else if (g.T == SUB_T) __syncthreads();
     else asm volatile("bar.sync %0, %1;" :: "r"(g.id), "r"(g.T) : "memory");
 }
 
-__global__ void __launch_bounds__(SUB_T, 1) k_subtree(const SubArgs a) {
+template <int SUB_T, uint32_t SUB_MAX>
+__global__ void __launch_bounds__(SUB_T, 8192 / SUB_MAX) k_subtree(const SubArgs a) {
+    constexpr int SUB_PER_T = SUB_MAX / SUB_T;
     extern __shared__ __align__(16) unsigned char sub_smem[];
     float* sx[3];
     sx[0] = reinterpret_cast<float*>(sub_smem); sx[1] = sx[0] + SUB_MAX; sx[2] = sx[1] + SUB_MAX;
@@ -128,13 +128,13 @@ __global__ void __launch_bounds__(SUB_T, 1) k_subtree(const SubArgs a) {
                     #pragma unroll
                     for (int d = 0; d < 3; ++d) { s_box[warp][d] = lo[d]; s_box[warp][3 + d] = hi[d]; }
                 }
-                sub_sync(g);
+                sub_sync<SUB_T>(g);
                 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     float l2 = lane < g.W ? s_box[g.w0 + lane][d] : INFINITY, h2 = lane < g.W ? s_box[g.w0 + lane][3 + d] : -INFINITY;
                     lo[d] = warp_min(l2); hi[d] = warp_max(h2);
                 }
-                sub_sync(g);
+                sub_sync<SUB_T>(g);
             }
             if (g.tig == 0) {
                 float bsss = 0.0f;
@@ -175,11 +175,11 @@ __global__ void __launch_bounds__(SUB_T, 1) k_subtree(const SubArgs a) {
                 cnt = warp_sum(cnt); mx_lt = warp_max(mx_lt); mn_ge = warp_min(mn_ge);
                 if (g.W > 1) {
                     if (lane == 0) { s_cnt[warp] = cnt; s_mx[warp] = mx_lt; s_mn[warp] = mn_ge; }
-                    sub_sync(g);
+                    sub_sync<SUB_T>(g);
                     const uint32_t c2 = lane < g.W ? s_cnt[g.w0 + lane] : 0u;
                     const float a2 = lane < g.W ? s_mx[g.w0 + lane] : -INFINITY, b2 = lane < g.W ? s_mn[g.w0 + lane] : INFINITY;
                     cnt = warp_sum(c2); mx_lt = warp_max(a2); mn_ge = warp_min(b2);
-                    sub_sync(g);
+                    sub_sync<SUB_T>(g);
                 }
                 const uint32_t B = wf + cnt;
 
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(SUB_T, 1) k_subtree(const SubArgs a) {
                     uint32_t exA = 0, exB = 0, allA = totA, allB = totB;
                     if (g.W > 1) {
                         if (lane == 0) { s_cnt[warp] = totA; s_cnt2[warp] = totB; }
-                        sub_sync(g);
+                        sub_sync<SUB_T>(g);
                         const uint32_t ca = lane < g.W ? s_cnt[g.w0 + lane] : 0u, cb = lane < g.W ? s_cnt2[g.w0 + lane] : 0u;
                         allA = warp_sum(ca); allB = warp_sum(cb);
                         exA = warp_sum(lane < wig ? ca : 0u); exB = warp_sum(lane < wig ? cb : 0u);
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(SUB_T, 1) k_subtree(const SubArgs a) {
                         offA += __popc(ba[r]); offB += __popc(bb[r]);
                     }
                     carryA += allA; carryB += allB;
-                    sub_sync(g);
+                    sub_sync<SUB_T>(g);
                 }
                 const uint32_t kk = carryA;    // == carryB
                 // pass 3: the swaps :549-556 - coordinates and index move together
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(SUB_T, 1) k_subtree(const SubArgs a) {
                     for (int d = 0; d < 3; ++d) if (d < PD) { const float va = sx[d][pa], vb = sx[d][pb]; sx[d][pa] = vb; sx[d][pb] = va; }
                     const uint16_t ia = sperm[pa], ib = sperm[pb]; sperm[pa] = ib; sperm[pb] = ia;
                 }
-                sub_sync(g);
+                sub_sync<SUB_T>(g);
                 ++n_pass; n_scan += (wl - wf + 1);
                 // :565-583
                 if (B == nless) break;
