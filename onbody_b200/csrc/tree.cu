@@ -22,6 +22,7 @@
  */
 #include "onb_internal.h"
 #include <cstdlib>
+#include <cstdio>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -545,6 +546,10 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
         ONB_CUDA(onb_dmalloc(c, (void**)&bwl, (size_t)max_chunks * 8));
     }
 
+    unsigned long long* big_prof = nullptr;      // diagnostics: ONB_BIG_PROF=1 prints the phase timeline of every big level
+    static const bool want_prof = std::getenv("ONB_BIG_PROF") != nullptr;
+    if (want_prof) { ONB_CUDA(onb_dmalloc(c, (void**)&big_prof, (size_t)t.levels * 512 * 8)); ONB_CUDA(cudaMemsetAsync(big_prof, 0, (size_t)t.levels * 512 * 8, ONB_ST(c))); }
+
     const int TB = 256; const uint32_t GB = (n + TB - 1) / TB;
     k_fill_u32<<<GB, TB, 0, ONB_ST(c)>>>(own_g, n, 0, 1); ONB_LAUNCH(c);                 // gidx = iota :823
     k_fill_u32<<<GB, TB, 0, ONB_ST(c)>>>(owner, n, 1, 0); ONB_LAUNCH(c);
@@ -588,6 +593,7 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
             ba.lidx = lidx; ba.scr = scr; ba.axis_of = axis_of; ba.pmid = pmid; ba.stats = ONB_STATS(c);
             ba.block = c->block; ba.big = BIG_NODE; ba.level = lev; ba.PD = PD; ba.pivot_mode = onb_pivot_mode;
             ba.blo = blo; ba.bhi = bhi;
+            ba.prof = big_prof ? big_prof + (size_t)lev * 512 : nullptr;
             const uint32_t lev_nodes = std::min<uint64_t>(1ull << lev, max_big_nodes);
             ba.max_nodes = lev_nodes; ba.max_chunks = max_chunks;
             const uint32_t chunks_ub = std::min<uint32_t>(max_chunks, n / BIG_CH + lev_nodes + 1);
@@ -645,6 +651,19 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
         ONB_CUDA(cudaGetLastError());
     }
     p.packed_valid = false;
+    if (big_prof) {
+        std::vector<unsigned long long> h((size_t)t.levels * 512);
+        ONB_CUDA(cudaStreamSynchronize(ONB_ST(c)));
+        ONB_CUDA(cudaMemcpy(h.data(), big_prof, h.size() * 8, cudaMemcpyDeviceToHost));
+        for (int lev = 0; lev < t.levels; ++lev) {
+            const unsigned long long* q = h.data() + (size_t)lev * 512;
+            if (!q[0]) continue;
+            fprintf(stderr, "big level %d: %llu stamps, total %.1f us; list+owner %.1f bbox %.1f setup %.1f | passes (count+scan, compact, swap):", lev, q[0],
+                    (q[q[0]] - q[1]) * 1e-3, (q[2] - q[1]) * 1e-3, (q[3] - q[2]) * 1e-3, (q[4] - q[3]) * 1e-3);
+            for (unsigned long long i = 4; i + 3 <= q[0]; i += 3) fprintf(stderr, " [%.1f %.1f %.1f]", (q[i + 1] - q[i]) * 1e-3, (q[i + 2] - q[i + 1]) * 1e-3, (q[i + 3] - q[i + 2]) * 1e-3);
+            fprintf(stderr, "\n");
+        }
+    }
 
     int rc = run_finish(c, p, t);
     if (rc) return rc;

@@ -44,6 +44,7 @@ struct BigArgs {
     uint8_t* axis_of; uint32_t* pmid;
     unsigned long long* stats;
     uint32_t block, big, max_nodes, max_chunks, blo, bhi; int level, PD, pivot_mode;
+    unsigned long long* prof;              // diagnostics (ONB_BIG_PROF): globaltimer at every phase boundary, block 0
 };
 
 // one block: list the big nodes of this level (node order) and lay out their chunks - a block-wide exclusive scan of
@@ -87,30 +88,63 @@ __device__ __forceinline__ float bw_min(float v) { return warp_min(v); }
 __device__ __forceinline__ float bw_max(float v) { return warp_max(v); }
 __device__ __forceinline__ uint32_t bw_sum(uint32_t v) { return warp_sum(v); }
 
-// per chunk: bounding box contribution and lidx = iota (barneshut.hpp:621-625, :516)
-__device__ __forceinline__ void big_bbox(const BigArgs& a, const int it, const uint32_t chunk) {
-    BigNode& b = a.nodes[a.chunk_owner[chunk]];
-    const uint32_t i0 = b.pf + (chunk - b.chunk0) * BIG_CH, i1 = min(b.pl, i0 + BIG_CH);
-    __shared__ float s_lo[BIG_T / 32], s_hi[BIG_T / 32];
+// bounding boxes (barneshut.hpp:621-625) and lidx = iota (:516) over this CTA's contiguous share of the level's chunks:
+// per-thread min/max accumulate across the chunks of a node with no barrier in between (the loads of consecutive
+// chunks overlap); one block reduction + six atomics per (CTA, node)
+__device__ __forceinline__ void big_bbox_flush(const BigArgs& a, const uint32_t bi, float* lo, float* hi) {
+    __shared__ uint32_t s_red[6][BIG_T / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t i = i0 + threadIdx.x; i < i1; i += BIG_T) a.lidx[i] = i;
-    for (int d = 0; d < a.PD; ++d) {
-        float lo = INFINITY, hi = -INFINITY;
-        float v[BIG_ROUNDS];
-        #pragma unroll
-        for (int r = 0; r < BIG_ROUNDS; ++r) { const uint32_t i = i0 + (uint32_t)r * BIG_T + threadIdx.x; v[r] = i < i1 ? a.x[d][i] : NAN; }
-        #pragma unroll
-        for (int r = 0; r < BIG_ROUNDS; ++r) { lo = fminf(lo, v[r]); hi = fmaxf(hi, v[r]); }      // fminf/fmaxf ignore the NaN fillers
-        lo = bw_min(lo); hi = bw_max(hi);
-        if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
-        __syncthreads();
-        if (warp == 0) {
-            lo = lane < BIG_T / 32 ? s_lo[lane] : INFINITY; hi = lane < BIG_T / 32 ? s_hi[lane] : -INFINITY;
-            lo = bw_min(lo); hi = bw_max(hi);
-            if (lane == 0) { atomicMin(&b.bmin[d], f2ord(lo)); atomicMax(&b.bmax[d], f2ord(hi)); }
-        }
-        __syncthreads();
+    #pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const uint32_t l = __reduce_min_sync(0xffffffffu, f2ord(lo[d])), h = __reduce_max_sync(0xffffffffu, f2ord(hi[d]));
+        if (lane == 0) { s_red[d][warp] = l; s_red[3 + d][warp] = h; }
+        lo[d] = INFINITY; hi[d] = -INFINITY;
     }
+    __syncthreads();
+    if (warp < 6 && warp % 3 < a.PD) {
+        const uint32_t v = lane < BIG_T / 32 ? s_red[warp][lane] : (warp < 3 ? 0xffffffffu : 0u);
+        const uint32_t r = warp < 3 ? __reduce_min_sync(0xffffffffu, v) : __reduce_max_sync(0xffffffffu, v);
+        if (lane == 0) { if (warp < 3) atomicMin(&a.nodes[bi].bmin[warp], r); else atomicMax(&a.nodes[bi].bmax[warp - 3], r); }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void big_bbox_phase(const BigArgs& a, const uint32_t nchunks) {
+    __shared__ uint32_t s_owner[64];
+    __shared__ uint32_t s_nd[3];     // pf, pl, chunk0 of the current node
+    const uint32_t i0 = (uint32_t)((unsigned long long)nchunks * blockIdx.x / gridDim.x);
+    const uint32_t i1 = (uint32_t)((unsigned long long)nchunks * (blockIdx.x + 1) / gridDim.x);
+    if (i0 >= i1) return;
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    uint32_t cur = 0xffffffffu;
+    for (uint32_t base = i0; base < i1; base += 64) {
+        const uint32_t m = min(64u, i1 - base);
+        __syncthreads();
+        if (threadIdx.x < m) s_owner[threadIdx.x] = a.chunk_owner[base + threadIdx.x];
+        __syncthreads();
+        for (uint32_t j = 0; j < m; ++j) {
+            const uint32_t bi = s_owner[j], chunk = base + j;
+            if (bi != cur) {
+                if (cur != 0xffffffffu) big_bbox_flush(a, cur, lo, hi);
+                __syncthreads();
+                if (threadIdx.x == 0) { const BigNode& n = a.nodes[bi]; s_nd[0] = n.pf; s_nd[1] = n.pl; s_nd[2] = n.chunk0; }
+                __syncthreads();
+                cur = bi;
+            }
+            const uint32_t c0 = s_nd[0] + (chunk - s_nd[2]) * BIG_CH, c1 = min(s_nd[1], c0 + BIG_CH);
+            #pragma unroll
+            for (int d = 0; d < 3; ++d) if (d < a.PD) {
+                const float* __restrict__ xd = a.x[d];
+                float v[BIG_ROUNDS];
+                #pragma unroll
+                for (int r = 0; r < BIG_ROUNDS; ++r) { const uint32_t i = c0 + (uint32_t)r * BIG_T + threadIdx.x; v[r] = i < c1 ? xd[i] : NAN; }   // 8 loads in flight
+                #pragma unroll
+                for (int r = 0; r < BIG_ROUNDS; ++r) { lo[d] = fminf(lo[d], v[r]); hi[d] = fmaxf(hi[d], v[r]); }      // fminf/fmaxf ignore the NaN fillers
+            }
+            #pragma unroll
+            for (int r = 0; r < BIG_ROUNDS; ++r) { const uint32_t i = c0 + (uint32_t)r * BIG_T + threadIdx.x; if (i < c1) a.lidx[i] = i; }
+        }
+    }
+    if (cur != 0xffffffffu) big_bbox_flush(a, cur, lo, hi);
 }
 
 // per node: node arrays, split axis, first window and pivot (barneshut.hpp:623-663, :519-540)
@@ -137,23 +171,28 @@ __device__ __forceinline__ void big_setup(const BigArgs& a, const uint32_t bi) {
     b.w[0] = w; b.w[1] = w;
 }
 
+// what a chunk phase needs to know about its node, cached in shared memory while consecutive chunks of a CTA's range
+// belong to the same node (the worklist keeps a node's chunks together): one dependent global load chain per node
+// change instead of one per chunk
+struct BigCache { uint32_t pf, pl, chunk0, B, k; int axis; BigWin w; };
+
 // element range of this chunk inside the node's current window; false if empty / node finished
-__device__ __forceinline__ bool big_range(const BigNode& b, const BigWin& w, uint32_t chunk, uint32_t& i0, uint32_t& i1) {
-    if (w.done) return false;
+__device__ __forceinline__ bool big_range(const BigCache& b, uint32_t chunk, uint32_t& i0, uint32_t& i1) {
+    if (b.w.done) return false;
     const uint32_t c0 = b.pf + (chunk - b.chunk0) * BIG_CH;
-    i0 = max(c0, w.wf); i1 = min(min(b.pl, c0 + BIG_CH), w.wl + 1);
+    i0 = max(c0, b.w.wf); i1 = min(min(b.pl, c0 + BIG_CH), b.w.wl + 1);
     return i0 < i1;
 }
 
 __device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const uint32_t bi);
 
-__device__ __forceinline__ void big_count(const BigArgs& a, const int it, const uint32_t chunk) {
-    const uint32_t bi = a.chunk_owner[chunk];
-    BigNode& b = a.nodes[bi];
-    const BigWin w = b.w[it & 1];
+// per chunk: #{v < pivot}, max{v < pivot}, min{v >= pivot}; the chunk count goes to cntA, the node totals are
+// accumulated in shared memory (s_acc) and flushed once per (CTA, node) by big_count_flush
+__device__ __forceinline__ void big_count(const BigArgs& a, const BigCache& b, const uint32_t chunk, uint32_t* s_acc) {
     uint32_t i0, i1;
-    if (!big_range(b, w, chunk, i0, i1)) return;
+    if (!big_range(b, chunk, i0, i1)) return;
     const float* key = a.x[b.axis];
+    const float pivot = b.w.pivot;
     const uint32_t c0 = b.pf + (chunk - b.chunk0) * BIG_CH;
     uint32_t cnt = 0; float mx = -INFINITY, mn = INFINITY;
     float v[BIG_ROUNDS]; bool ok[BIG_ROUNDS];
@@ -164,30 +203,44 @@ __device__ __forceinline__ void big_count(const BigArgs& a, const int it, const 
         v[r] = ok[r] ? key[i] : 0.f;
     }
     #pragma unroll
-    for (int r = 0; r < BIG_ROUNDS; ++r) if (ok[r]) { if (v[r] < w.pivot) { ++cnt; mx = fmaxf(mx, v[r]); } else mn = fminf(mn, v[r]); }
-    __shared__ uint32_t s_c[BIG_T / 32]; __shared__ float s_mx[BIG_T / 32], s_mn[BIG_T / 32];
-    __shared__ uint32_t s_last;
+    for (int r = 0; r < BIG_ROUNDS; ++r) if (ok[r]) { if (v[r] < pivot) { ++cnt; mx = fmaxf(mx, v[r]); } else mn = fminf(mn, v[r]); }
+    __shared__ uint32_t s_c[BIG_T / 32], s_mx[BIG_T / 32], s_mn[BIG_T / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_last = 0u;
-    cnt = bw_sum(cnt); mx = bw_max(mx); mn = bw_min(mn);
-    if (lane == 0) { s_c[warp] = cnt; s_mx[warp] = mx; s_mn[warp] = mn; }
+    cnt = bw_sum(cnt);
+    const uint32_t emx = __reduce_max_sync(0xffffffffu, f2ord(mx)), emn = __reduce_min_sync(0xffffffffu, f2ord(mn));
+    if (lane == 0) { s_c[warp] = cnt; s_mx[warp] = emx; s_mn[warp] = emn; }
     __syncthreads();
     if (warp == 0) {
-        cnt = lane < BIG_T / 32 ? s_c[lane] : 0u; mx = lane < BIG_T / 32 ? s_mx[lane] : -INFINITY; mn = lane < BIG_T / 32 ? s_mn[lane] : INFINITY;
-        cnt = bw_sum(cnt); mx = bw_max(mx); mn = bw_min(mn);
+        const uint32_t c2 = bw_sum(lane < BIG_T / 32 ? s_c[lane] : 0u);
+        const uint32_t x2 = __reduce_max_sync(0xffffffffu, lane < BIG_T / 32 ? s_mx[lane] : 0u);
+        const uint32_t n2 = __reduce_min_sync(0xffffffffu, lane < BIG_T / 32 ? s_mn[lane] : 0xffffffffu);
         if (lane == 0) {
-            a.cntA[chunk] = cnt;                       // elements < pivot in this chunk's part of the window
-            if (cnt) atomicAdd(&b.m, cnt);
-            if (mx > -INFINITY) atomicMax(&b.mx_enc, f2ord(mx));
-            if (mn < INFINITY) atomicMin(&b.mn_enc, f2ord(mn));
-            // ticket: the last chunk of this node's window to arrive runs the node's scan right here (one grid-wide
-            // barrier less per pass). Release our results, take the ticket, acquire everybody else's.
-            __threadfence();
-            s_last = (atomicAdd(&b.arrived, 1u) + 1u == b.expect) ? 1u : 0u;
+            a.cntA[chunk] = c2;                        // elements < pivot in this chunk's part of the window
+            s_acc[0] += c2; s_acc[1] = max(s_acc[1], x2); s_acc[2] = min(s_acc[2], n2); s_acc[3] += 1u;
         }
+    }
+}
+
+// once per (CTA, node): node totals by atomics, then the ticket - the last arrival of the node's window runs the node's
+// scan right here (one grid-wide barrier less per pass). Release our results, take the ticket, acquire everybody else's.
+__device__ __forceinline__ void big_count_flush(const BigArgs& a, const int it, const uint32_t bi, uint32_t* s_acc) {    // one CTA
+    __shared__ uint32_t s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BigNode& b = a.nodes[bi];
+        s_last = 0u;
+        if (s_acc[3]) {
+            if (s_acc[0]) atomicAdd(&b.m, s_acc[0]);
+            if (s_acc[1] > f2ord(-INFINITY)) atomicMax(&b.mx_enc, s_acc[1]);
+            if (s_acc[2] < f2ord(INFINITY)) atomicMin(&b.mn_enc, s_acc[2]);
+            __threadfence();
+            s_last = (atomicAdd(&b.arrived, s_acc[3]) + s_acc[3] == b.expect) ? 1u : 0u;
+        }
+        s_acc[0] = 0u; s_acc[1] = f2ord(-INFINITY); s_acc[2] = f2ord(INFINITY); s_acc[3] = 0u;
     }
     __syncthreads();
     if (s_last) { __threadfence(); big_scan(a, it, bi); }
+    __syncthreads();
 }
 
 // one CTA per big node. The misplaced counts of a chunk follow from its "< pivot" count and its position relative to
@@ -217,10 +270,11 @@ __device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const u
         if (threadIdx.x == 0) { uint32_t t = 0; for (int q = 0; q < 8; ++q) t += s_wa[q]; s_ltl = t; s_carry[0] = 0; s_carry[1] = 0; }
         __syncthreads();
     }
-    for (uint32_t base = 0; base < b.nchunks; base += 256) {
+    const uint32_t wq0 = (w.wf - b.pf) / BIG_CH, wq1 = (w.wl - b.pf) / BIG_CH;      // only the chunks of the window take part
+    for (uint32_t base = wq0; base <= wq1; base += 256) {
         const uint32_t q = base + threadIdx.x;
         uint32_t va = 0, vb = 0;
-        if (q < b.nchunks) {
+        if (q <= wq1) {
             const uint32_t c0 = b.pf + q * BIG_CH;
             const uint32_t i0 = max(c0, w.wf), i1 = min(min(b.pl, c0 + BIG_CH), w.wl + 1);
             if (i0 < i1) {
@@ -237,7 +291,7 @@ __device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const u
         __syncthreads();
         uint32_t pa = s_carry[0], pb = s_carry[1], ta = 0, tb = 0;
         for (int q2 = 0; q2 < 8; ++q2) { if (q2 < warp) { pa += s_wa[q2]; pb += s_wb[q2]; } ta += s_wa[q2]; tb += s_wb[q2]; }
-        if (q < b.nchunks) { a.cntA[b.chunk0 + q] = pa + ia - va; a.cntB[b.chunk0 + q] = pb + ib - vb; }
+        if (q <= wq1) { a.cntA[b.chunk0 + q] = pa + ia - va; a.cntB[b.chunk0 + q] = pb + ib - vb; }
         __syncthreads();
         if (threadIdx.x == 0) { s_carry[0] += ta; s_carry[1] += tb; }
         __syncthreads();
@@ -277,13 +331,12 @@ __device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const u
     }
 }
 
-__device__ __forceinline__ void big_compact(const BigArgs& a, const int it, const uint32_t chunk) {
-    BigNode& b = a.nodes[a.chunk_owner[chunk]];
-    const BigWin w = b.w[it & 1];
+__device__ __forceinline__ void big_compact(const BigArgs& a, const BigCache& b, const uint32_t chunk) {
     uint32_t i0, i1;
-    if (!big_range(b, w, chunk, i0, i1)) return;
+    if (!big_range(b, chunk, i0, i1)) return;
     const uint32_t B = b.B;
     const float* key = a.x[b.axis];
+    const float pivot = b.w.pivot;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t c0 = b.pf + (chunk - b.chunk0) * BIG_CH;
     uint32_t ba[BIG_ROUNDS], bb[BIG_ROUNDS], totA = 0, totB = 0;
@@ -292,7 +345,7 @@ __device__ __forceinline__ void big_compact(const BigArgs& a, const int it, cons
         const uint32_t i = c0 + (uint32_t)warp * 32u * BIG_ROUNDS + (uint32_t)r * 32u + lane;
         const bool valid = i >= i0 && i < i1;
         const float v = valid ? key[i] : 0.f;
-        const bool lt = v < w.pivot;
+        const bool lt = v < pivot;
         ba[r] = __ballot_sync(0xffffffffu, valid && i < B && !lt);
         bb[r] = __ballot_sync(0xffffffffu, valid && i >= B && lt);
         totA += __popc(ba[r]); totB += __popc(bb[r]);
@@ -312,18 +365,58 @@ __device__ __forceinline__ void big_compact(const BigArgs& a, const int it, cons
     }
 }
 
-__device__ __forceinline__ void big_swap(const BigArgs& a, const int it, const uint32_t chunk) {
-    BigNode& b = a.nodes[a.chunk_owner[chunk]];
-    const BigWin w = b.w[it & 1];
-    if (w.done) return;
-    const uint32_t k = b.k, q = (chunk - b.chunk0) - (w.wf - b.pf) / BIG_CH;      // my rank among the chunks of the node's window
+__device__ __forceinline__ void big_swap(const BigArgs& a, const BigCache& b, const uint32_t chunk) {
+    if (b.w.done) return;
+    // the k swap pairs of the node are dealt out evenly over the chunks of its window (a pass misplaces about a quarter
+    // of the window: handing each chunk "its" 2048 pairs would leave three quarters of the CTAs without work)
+    const uint32_t q0 = (b.w.wf - b.pf) / BIG_CH, nq = (b.w.wl - b.pf) / BIG_CH - q0 + 1u;
+    const uint32_t k = b.k, q = (chunk - b.chunk0) - q0;                              // my rank among the chunks of the node's window
     float* key = a.x[b.axis];
-    const uint32_t j1 = min(k, (q + 1) * BIG_CH);
-    for (uint32_t j = q * BIG_CH + threadIdx.x; j < j1; j += BIG_T) {                     // barneshut.hpp:549-556
+    const uint32_t j0 = (uint32_t)((unsigned long long)k * q / nq), j1 = (uint32_t)((unsigned long long)k * (q + 1u) / nq);
+    for (uint32_t j = j0 + threadIdx.x; j < j1; j += BIG_T) {                             // barneshut.hpp:549-556
         const uint32_t pa = a.scr[b.pf + j], pb = a.scr[b.pl - k + j];
         const float va = key[pa], vb = key[pb]; key[pa] = vb; key[pb] = va;
         const uint32_t ia = a.lidx[pa], ib = a.lidx[pb]; a.lidx[pa] = ib; a.lidx[pb] = ia;
     }
+}
+
+// one phase (0 count+scan, 1 compact, 2 swap) of one pass over this CTA's CONTIGUOUS share of the worklist
+constexpr uint32_t BIG_PRE = 64;
+template <int PHASE>
+__device__ __forceinline__ void big_phase(const BigArgs& a, const int it, const uint32_t* wl, const uint32_t nw) {
+    __shared__ uint32_t s_chunk[BIG_PRE], s_owner[BIG_PRE];
+    __shared__ BigCache s_node;
+    __shared__ uint32_t s_acc[4];
+    const uint32_t i0 = (uint32_t)((unsigned long long)nw * blockIdx.x / gridDim.x);
+    const uint32_t i1 = (uint32_t)((unsigned long long)nw * (blockIdx.x + 1) / gridDim.x);
+    if (i0 >= i1) return;
+    if (PHASE == 0 && threadIdx.x == 0) { s_acc[0] = 0u; s_acc[1] = f2ord(-INFINITY); s_acc[2] = f2ord(INFINITY); s_acc[3] = 0u; }
+    uint32_t cur = 0xffffffffu;
+    for (uint32_t base = i0; base < i1; base += BIG_PRE) {
+        const uint32_t m = min(BIG_PRE, i1 - base);
+        __syncthreads();
+        if (threadIdx.x < m) { const uint32_t ch = wl[base + threadIdx.x]; s_chunk[threadIdx.x] = ch; s_owner[threadIdx.x] = a.chunk_owner[ch]; }
+        __syncthreads();
+        for (uint32_t j = 0; j < m; ++j) {
+            const uint32_t bi = s_owner[j], chunk = s_chunk[j];
+            if (bi != cur) {
+                if (PHASE == 0 && cur != 0xffffffffu) big_count_flush(a, it, cur, s_acc);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const BigNode& n = a.nodes[bi];
+                    s_node.pf = n.pf; s_node.pl = n.pl; s_node.chunk0 = n.chunk0; s_node.axis = n.axis; s_node.w = n.w[it & 1];
+                    s_node.B = n.B; s_node.k = n.k;
+                }
+                __syncthreads();
+                cur = bi;
+            }
+            if (PHASE == 0) big_count(a, s_node, chunk, s_acc);
+            else if (PHASE == 1) big_compact(a, s_node, chunk);
+            else big_swap(a, s_node, chunk);
+            __syncthreads();
+        }
+    }
+    if (PHASE == 0 && cur != 0xffffffffu) big_count_flush(a, it, cur, s_acc);
 }
 
 // per node: publish the split (barneshut.hpp:702-704) and the statistics
@@ -343,6 +436,9 @@ __device__ __forceinline__ void big_finish(const BigArgs& a, const uint32_t bi) 
 __global__ void __launch_bounds__(BIG_T, 4) k_big_level(const BigArgs a) {
     cg::grid_group grid = cg::this_grid();
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    int nprof = 0;
+    #define BIG_STAMP() do { if (a.prof && gtid == 0 && nprof < 510) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.prof[1 + nprof++] = t_; a.prof[0] = (unsigned long long)nprof; } } while (0)
+    BIG_STAMP();
     if (blockIdx.x == 0) big_list(a);
     grid.sync();
     const uint32_t nnodes = a.nbig[0], nchunks = a.nbig[1];
@@ -352,23 +448,29 @@ __global__ void __launch_bounds__(BIG_T, 4) k_big_level(const BigArgs a) {
         for (uint32_t q = threadIdx.x; q < nc; q += blockDim.x) a.chunk_owner[c0 + q] = bi;
     }
     grid.sync();
-    for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) { big_bbox(a, 0, ch); __syncthreads(); }
+    BIG_STAMP();
+    big_bbox_phase(a, nchunks);
     grid.sync();
+    BIG_STAMP();
     for (uint32_t bi = gtid; bi < nnodes; bi += gthreads) big_setup(a, bi);
     for (uint32_t i = gtid; i < nchunks; i += gthreads) a.wl[i] = i;            // pass 0 visits every chunk
     if (gtid == 0) { a.nbig[4] = nchunks; a.nbig[5] = 0; }
     grid.sync();
+    BIG_STAMP();
     for (int it = 0; it < 104; ++it) {
         const uint32_t* wl = a.wl + (size_t)(it & 1) * a.max_chunks;
         const uint32_t nw = a.nbig[4 + (it & 1)];
         // count, and per node (last chunk to arrive) the scan: next window, next pivot, next worklist (parity it+1)
-        for (uint32_t i = blockIdx.x; i < nw; i += gridDim.x) { big_count(a, it, wl[i]); __syncthreads(); }
+        big_phase<0>(a, it, wl, nw);
         grid.sync();
-        for (uint32_t i = blockIdx.x; i < nw; i += gridDim.x) { big_compact(a, it, wl[i]); __syncthreads(); }
+        BIG_STAMP();
+        big_phase<1>(a, it, wl, nw);
         grid.sync();
-        if (gtid == 0) a.nbig[4 + (it & 1)] = 0;          // this pass's worklist is consumed (everybody holds nw); pass it+1 refills it for it+2
-        for (uint32_t i = blockIdx.x; i < nw; i += gridDim.x) { big_swap(a, it, wl[i]); __syncthreads(); }
+        BIG_STAMP();
+        if (gtid == 0) a.nbig[4 + (it & 1)] = 0;          // this pass's worklist is consumed (everybody holds nw); pass it+1's scans refill it for pass it+2
+        big_phase<2>(a, it, wl, nw);
         grid.sync();
+        BIG_STAMP();
         if (a.nbig[2] == 0) break;        // every node of the level has met one of the reference's exit conditions
     }
     for (uint32_t bi = gtid; bi < nnodes; bi += gthreads) big_finish(a, bi);
