@@ -217,16 +217,12 @@ def run_ours(args):
     scratch = {"buf": None}
 
     def hot_path_multi():
-        # each rank sorts its share of both trees; NCCL all-gathers over NVLink replicate the particle planes; every rank then
+        # each rank sorts its share of both trees (the two builds concurrently); NCCL all-gathers over NVLink replicate the particle planes; every rank then
         # completes the node arrays bottom-up and runs the (cheap) upward pass in full; evaluation is sharded by target leaves
         from onbody_b200 import multigpu
         t0 = time.perf_counter()
-        scratch["buf"] = multigpu.build_sources_distributed(g, N, rank, world, scratch["buf"], phases)
-        t1 = time.perf_counter()
-        scratch["buf"] = multigpu.build_targets_sharded(g, N, rank, world, scratch["buf"], phases)
-        t2 = time.perf_counter()
-        phases["src_side_wall"] = phases.get("src_side_wall", 0.0) + (t1 - t0) * 1e3
-        phases["tgt_side_wall"] = phases.get("tgt_side_wall", 0.0) + (t2 - t1) * 1e3
+        scratch["buf"] = multigpu.build_both_distributed(g, N, N, rank, world, scratch["buf"], phases)
+        phases["build_side_wall"] = phases.get("build_side_wall", 0.0) + (time.perf_counter() - t0) * 1e3
         g.fastsumm(THETA)
         for k in ("eval", "lists", "p2p", "downward"):
             phases[k] = phases.get(k, 0.0) + g.phase_ms(k)
@@ -350,9 +346,24 @@ def run_ours(args):
     achieved_tf = pairs_local * FLOP_PER_PAIR / (p2p_ms * 1e-3) * 1e-12 if p2p_ms > 0 else 0.0
     peaks, peaks_src = measured_peaks()
     clocks = sampler.summary()
-    tree_ms = (ph_res.get("both_trees", 0) + ph_res.get("src_tree_range", 0) + ph_res.get("tgt_tree_range", 0)) / K
+    tree_ms = (ph_res.get("both_trees", 0) + ph_res.get("both_trees_range", 0)) / K
     # algorithmic bytes of one tree build: every plane read once + written once: sources 6 planes + targets 4 planes + gidx
-    tree_bytes = N * (2 * 4 * (3 + 1 + 1) + 2 * 4 * (3 + 1) + 8)
+    tree_bytes_lb = N * (2 * 4 * (3 + 1 + 1) + 2 * 4 * (3 + 1) + 8)      # lower bound: every plane of both sets read and written once
+    # algorithmic bytes of the level-synchronous partition build the reference's order demands:
+    # per level above the shared-memory subtree 12 B bbox read + 4 B lidx write + 36 B permute (3 coordinates + index
+    # plane read and written, lidx read), the key scans of the select passes (8 B per scanned element: count + compact),
+    # one 32 B read/write of coordinates + index in the subtree kernel, 8 B per deferred plane (r, s) at the end
+    def _tree_bytes(n, sd, scanned):
+        lev, left = 0, n
+        while left > 8192:
+            lev += 1
+            left = 128 * 2 ** int(np.floor(np.log2((left - 1) / 128)))
+        return n * (lev * 52 + 32 + 8 * (1 + sd)) + scanned * 8
+    try:
+        scanned = int(g.build_stats()["scanned"])
+    except Exception:
+        scanned = 26 * N
+    tree_bytes = _tree_bytes(N, 1, scanned) + _tree_bytes(N, 0, scanned)
     rec = {
         "metric": "ongrav3d_dualtree_pair_interactions_per_s", "value": value, "unit": "Ginteractions/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": sec_res * 1e3, "higher_is_better": True,
@@ -373,9 +384,12 @@ def run_ours(args):
                      "flop_per_pair": FLOP_PER_PAIR,
                      "fp32_issue_util": (pairs_local * FP32_SLOTS_PER_PAIR * 2 / (p2p_ms * 1e-3) * 1e-12 / peak_tf) if (peak_tf and p2p_ms > 0) else None,
                      "share_of_step": (p2p_ms / (sec_res * 1e3)) if sec_res > 0 else None},
-        "roofline_tree": {"kernels": "k_node_split + k_gather (both trees)", "bound": "hbm", "achieved": tree_bytes / (tree_ms * 1e-3) * 1e-9 if tree_ms > 0 else None,
+        "roofline_tree": {"kernels": "k_big_level + k_node_split + k_gather + k_subtree + k_apply_perm (both trees)", "bound": "hbm",
+                          "achieved": tree_bytes / (tree_ms * 1e-3) * 1e-9 if (tree_ms > 0 and world == 1) else None,
                           "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "peak_source": peaks_src,
-                          "frac": (tree_bytes / (tree_ms * 1e-3) * 1e-9 / peaks.get("hbm_gbs")) if tree_ms > 0 else None, "traffic": None},
+                          "frac": (tree_bytes / (tree_ms * 1e-3) * 1e-9 / peaks.get("hbm_gbs")) if (tree_ms > 0 and world == 1) else None,
+                          "algorithmic_bytes": tree_bytes, "lower_bound_bytes": tree_bytes_lb, "traffic": None,
+                          "note": "algorithmic bytes = level-synchronous partition build (see bench.py/_tree_bytes and DESIGN.md section 4); lower_bound_bytes = every plane read and written once"},
     }
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference itself on a bounded sample
     if world == 1 and not args.no_cpu_baseline:

@@ -83,3 +83,25 @@ def build_targets_sharded(session, n, rank, world, scratch=None, times=None):
     session.refine(1); t = _tick(times, "refine", t)
     session.upward(1); t = _tick(times, "tgt_equiv", t)
     return scratch
+
+
+def build_both_distributed(session, nsrc, ntarg, rank, world, scratch=None, times=None):
+    """both trees of a multi-GPU step: the two range-restricted builds run concurrently on the device
+    (onb_make_trees_range, two streams), then the source side is completed (exchange, node arrays, upward pass),
+    then the target side (exchange, node arrays, in-leaf refinement of the rank's own leaves, equivalent points)"""
+    import time
+    t = time.perf_counter()
+    slo, shi = session.shard_particle_range(nsrc, rank, world)
+    tlo, thi = session.shard_particle_range(ntarg, rank, world)
+    session.make_trees_range(slo, shi, tlo, thi); t = _tick(times, "both_trees_range", t)
+    scratch = exchange_planes(session, 0, nsrc, rank, world, scratch=scratch); t = _tick(times, "src_allgather", t)
+    if world > 1:
+        session.finish_tree(0); t = _tick(times, "src_finish", t)
+    session.upward(0); t = _tick(times, "upward", t)
+    scratch = exchange_planes(session, 1, ntarg, rank, world, scratch=scratch); t = _tick(times, "tgt_allgather", t)
+    if world > 1:
+        session.finish_tree(1); t = _tick(times, "tgt_finish", t)
+        session.set_build_range(1, tlo, thi)
+    session.refine(1); t = _tick(times, "refine", t)
+    session.upward(1); t = _tick(times, "tgt_equiv", t)
+    return scratch

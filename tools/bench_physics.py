@@ -29,13 +29,13 @@ def step():
     g.set_sources_ptr(N, dx.data_ptr(), dr.data_ptr(), ds.data_ptr()); g.set_targets_ptr(N, dx.data_ptr(), dr.data_ptr())
     g.timer_start()
     if world > 1:
-        scratch = multigpu.build_sources_distributed(g, N, rank, world, scratch)
         if method == "dualtree":
-            scratch = multigpu.build_targets_sharded(g, N, rank, world, scratch)
+            scratch = multigpu.build_both_distributed(g, N, N, rank, world, scratch)
         else:
+            scratch = multigpu.build_sources_distributed(g, N, rank, world, scratch)
             lo, hi = g.shard_particle_range(N, rank, world); g.make_tree_range(1, lo, hi)   # boxwise needs nc/nr of its own leaves only
     else:
-        g.make_tree(0); g.upward(0); g.make_tree(1)
+        g.make_trees(); g.upward(0)
         if method == "dualtree":
             g.refine(1); g.upward(1)
     g.zero_vels()
