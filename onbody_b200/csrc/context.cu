@@ -455,19 +455,29 @@ int onb_get_parts(onb_context* c, int which, float* x, float* r, float* s, float
     return ONB_OK;
 }
 
+// tree order -> the caller's order on the device (one scatter per output plane), so that the host only adds
+// contiguous arrays: out[gidx[i]] = u[i]
+__global__ void k_unsort_plane(const float* __restrict__ u, const uint32_t* __restrict__ g, float* __restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[g[i]] = u[i];
+}
+
 int onb_add_results_original_order(onb_context* c, float* u) {
     ONB_CUDA(cudaSetDevice(c->device));
     DParts& p = c->parts[1];
     const size_t n = p.n;
     if (!p.gidx) { c->err = "targets have no tree order yet"; return ONB_ERR_ARG; }
     { int jrc = onb_join_copies(c); if (jrc) return jrc; }
-    std::vector<uint32_t> g(n); std::vector<float> tmp(n);
-    ONB_CUDA(cudaStreamSynchronize(c->stream));
-    ONB_CUDA(cudaMemcpy(g.data(), p.gidx, n * 4, cudaMemcpyDeviceToHost));
+    onb_scratch_reset(c);
+    float* tmp = nullptr;
+    ONB_CUDA(onb_dmalloc(c, (void**)&tmp, n * sizeof(float)));
+    std::vector<float> h(n);
     for (int d = 0; d < c->OD; ++d) {
-        ONB_CUDA(cudaMemcpy(tmp.data(), p.u[d], n * 4, cudaMemcpyDeviceToHost));
+        k_unsort_plane<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(p.u[d], p.gidx, tmp, (uint32_t)n); ONB_LAUNCH(c);
+        ONB_CUDA(cudaMemcpyAsync(h.data(), tmp, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        ONB_CUDA(cudaStreamSynchronize(c->stream));
         float* ud = u + (size_t)d * n;
-        for (size_t i = 0; i < n; ++i) ud[g[i]] += tmp[i];                                // interface3dvortgrads.cpp:384-395
+        for (size_t i = 0; i < n; ++i) ud[i] += h[i];                                     // interface3dvortgrads.cpp:384-395
     }
     return ONB_OK;
 }

@@ -52,9 +52,8 @@ inline float run(int physics, bool direct, float theta, int ns, const float* con
         if (onb_zero_vels(c) != ONB_OK || onb_naive(c, 1, &flops) != ONB_OK) return fail(c, "naive");
         if (onb_get_parts(c, 1, nullptr, nullptr, nullptr, u.data(), nullptr) != ONB_OK) return fail(c, "get");
     } else {
-        if (onb_make_tree(c, 0) != ONB_OK) return fail(c, "make_tree(sources)");
+        if (onb_make_trees(c) != ONB_OK) return fail(c, "make_trees");         // both builds overlap on the device
         if (onb_upward(c, 0) != ONB_OK) return fail(c, "upward");
-        if (onb_make_tree(c, 1) != ONB_OK) return fail(c, "make_tree(targets)");
         if (onb_zero_vels(c) != ONB_OK || onb_treecode3(c, theta, &flops) != ONB_OK) return fail(c, "treecode3");
         if (onb_add_results_original_order(c, u.data()) != ONB_OK) return fail(c, "results");
     }
