@@ -161,6 +161,63 @@ __global__ void __launch_bounds__(128) k_downward(const DownArgs a) {
     if (tid < cnt) for (int d = 0; d < OD; ++d) tp.u[d][p0 + tid] = acc[d];
 }
 
+// ---------------------------------------------------------------------------------------------
+// calcEquivalents barneshut.hpp:946-1061 - the drivers' default when -o is omitted: every non-leaf node gets
+// ceil(cnt/2) equivalents per child, each the strength-weighted merge of two consecutive points of the child (its real
+// particles if it is a leaf, its own equivalents otherwise); an odd last point is passed up unchanged. One CTA per
+// node per level (deepest first), one thread per equivalent slot; the reference's IEEE operation sequence
+// (std::pow(float,int) and 1.0/(float) evaluate in double) so the result is bit-identical.
+// ---------------------------------------------------------------------------------------------
+struct EqArgs { PartsView p, ep; TreeView t; uint32_t* epnum; uint32_t block, ebs; int level, PD, SD; };
+
+__global__ void __launch_bounds__(128) k_equivalents(const EqArgs a) {
+    const uint32_t node = (1u << a.level) + blockIdx.x;
+    if (a.t.num[node] <= a.block) return;
+    const uint32_t half = a.block / 2;                                                    // ep.blockSize/2 :975
+    const uint32_t side = threadIdx.x >= half ? 1u : 0u, j = threadIdx.x - side * half;
+    const uint32_t child = 2u * node + side;
+    uint32_t cnt[2], first[2]; bool leaf[2];
+    #pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const uint32_t ch = 2u * node + q, cn = a.t.num[ch];
+        leaf[q] = !(cn > a.block);                                                        // :963
+        cnt[q] = leaf[q] ? cn : a.epnum[ch];
+        first[q] = leaf[q] ? a.t.ioffset[ch] : ch * a.ebs;
+    }
+    if (threadIdx.x == 0) a.epnum[node] = (cnt[0] + 1) / 2 + (cnt[1] + 1) / 2;            // :1009, :1056
+    const uint32_t c = cnt[side], numEq = (c + 1) / 2;
+    if (j >= numEq || threadIdx.x >= a.block) return;
+    const PartsView& sp = leaf[side] ? a.p : a.ep;
+    const uint32_t i1 = first[side] + 2u * j, i2 = i1 + 1u;
+    const uint32_t iep = node * a.ebs + side * half + j;                                  // (ep.blockSize/2) * ichild
+    (void)child;
+    if (2u * j + 1u < c) {
+        float str1, str2;
+        if (a.SD == 1) {
+            str1 = fmaxf(1.e-20f, fabsf(sp.s[0][i1])); str2 = fmaxf(1.e-20f, fabsf(sp.s[0][i2]));
+        } else {
+            str1 = 0.0f; str2 = 0.0f;
+            for (int d = 0; d < a.SD; ++d) {
+                const double s1 = (double)sp.s[d][i1], s2 = (double)sp.s[d][i2];
+                str1 = __double2float_rn(__dadd_rn((double)str1, __dmul_rn(s1, s1)));
+                str2 = __double2float_rn(__dadd_rn((double)str2, __dmul_rn(s2, s2)));
+            }
+            str1 = fmaxf(1.e-20f, __fsqrt_rn(str1)); str2 = fmaxf(1.e-20f, __fsqrt_rn(str2));
+        }
+        const float pairm = __double2float_rn(__ddiv_rn(1.0, (double)__fadd_rn(str1, str2)));
+        for (int d = 0; d < a.PD; ++d)
+            a.ep.x[d][iep] = __fmul_rn(__fadd_rn(__fmul_rn(sp.x[d][i1], str1), __fmul_rn(sp.x[d][i2], str2)), pairm);
+        const double r1 = (double)sp.r[i1], r2 = (double)sp.r[i2];
+        const double rr = __dmul_rn(__dadd_rn(__dmul_rn(__dmul_rn(r1, r1), (double)str1), __dmul_rn(__dmul_rn(r2, r2), (double)str2)), (double)pairm);
+        a.ep.r[iep] = __double2float_rn(__dsqrt_rn(rr));
+        for (int d = 0; d < a.SD; ++d) a.ep.s[d][iep] = __fadd_rn(sp.s[d][i1], sp.s[d][i2]);
+    } else {                                                                              // :1003-1008, :1049-1054
+        for (int d = 0; d < a.PD; ++d) a.ep.x[d][iep] = sp.x[d][i1];
+        for (int d = 0; d < a.SD; ++d) a.ep.s[d][iep] = sp.s[d][i1];
+        a.ep.r[iep] = sp.r[i1];
+    }
+}
+
 Cheb make_cheb(int order) {                                                               // set_sk / set_wk :28-48
     Cheb c;
     for (int k = 0; k <= ONB_MAX_ORDER; ++k) { c.sk[k] = 0.f; c.wk[k] = 0.f; }
@@ -207,5 +264,39 @@ int onb_bary_downward_level(onb_context* c, int level) {
     else k_downward<2, 2><<<1u << level, 128, 0, c->stream>>>(a);
     ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
+    return ONB_OK;
+}
+
+int onb_legacy_equivalents(onb_context* c, DParts& p, DParts& ep, DTree& t) {
+    if (!t.built) { c->err = "upward: tree not built"; return ONB_ERR_ARG; }
+    if (!p.are_sources) { c->err = "legacy equivalents exist for sources only (barneshut.hpp:953)"; return ONB_ERR_UNSUPPORTED; }
+    const uint32_t need = (uint32_t)(t.numnodes / 2) * (uint32_t)c->ebs;                  // ongrav3d.cpp:645
+    if (ep.n != need) {
+        onb_free_parts(c, ep);
+        int rc = onb_alloc_parts(c, ep, need, true);
+        if (rc) return rc;
+    }
+    if (c->epnum_cap < (uint32_t)t.numnodes) {
+        if (c->d_epnum) cudaFree(c->d_epnum);
+        c->d_epnum = nullptr; c->epnum_cap = 0;
+        ONB_CUDA(cudaMalloc((void**)&c->d_epnum, (size_t)t.numnodes * 4));
+        c->epnum_cap = (uint32_t)t.numnodes;
+    }
+    ONB_CUDA(cudaMemsetAsync(c->d_epnum, 0, (size_t)t.numnodes * 4, c->stream));
+    // unused slots stay zero like the reference's freshly resized arrays (Parts.hpp resize)
+    const size_t fb = (size_t)ep.cap * sizeof(float);
+    for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemsetAsync(ep.x[d], 0, fb, c->stream));
+    ONB_CUDA(cudaMemsetAsync(ep.r, 0, fb, c->stream));
+    for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemsetAsync(ep.s[d], 0, fb, c->stream));
+    EqArgs a; a.p = view_of(p); a.ep = view_of(ep); a.t = view_of(t); a.epnum = c->d_epnum;
+    a.block = c->block; a.ebs = c->ebs; a.PD = c->PD; a.SD = c->SD;
+    for (int lev = t.levels - 2; lev >= 0; --lev) {      // the last level holds only leaves
+        a.level = lev;
+        k_equivalents<<<1u << lev, 128, 0, c->stream>>>(a); ONB_LAUNCH(c);
+    }
+    ONB_CUDA(cudaGetLastError());
+    ONB_CUDA(cudaMemcpyAsync(&c->root_epnum, c->d_epnum + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    ep.packed_valid = false;
     return ONB_OK;
 }

@@ -172,6 +172,7 @@ void onb_destroy(onb_context* c) {
     cudaStreamSynchronize(c->stream);
     if (c->d_flag) cudaFree(c->d_flag);
     if (c->d_build_stats) cudaFree(c->d_build_stats);
+    if (c->d_epnum) cudaFree(c->d_epnum);
     for (auto& sl : c->slabs) cudaFree(sl.p);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
@@ -188,11 +189,16 @@ int onb_set_params(onb_context* c, int block_size, int order, int arith) {
     if (block_size < 2) { c->err = "block size must be >= 2"; return ONB_ERR_ARG; }
     block_size = 2 * ((block_size + 1) / 2);            // the reference rounds -b up to even (ongrav3d.cpp:522, minBlkSz 2)
     if (block_size > 128) { c->err = "block sizes above 128 are not supported by the GPU build"; return ONB_ERR_UNSUPPORTED; }
-    if (order < 1) { c->err = "order < 1 (the legacy pair-merge equivalents, -o omitted) is not implemented on the GPU"; return ONB_ERR_UNSUPPORTED; }
+    if (order == 0) { c->err = "order 0 is not a valid barycentric order (the drivers reject -o=0, ongrav3d.cpp:516)"; return ONB_ERR_ARG; }
+    if (order < 0) {
+        // the drivers' default when -o is omitted (ongrav3d.cpp:481): hierarchical pair-merge equivalents, up to blockSize per node
+        c->block = block_size; c->order = -1; c->arith = arith; c->ncp = 0; c->num_eqps = block_size; c->ebs = 128; c->legacy = true;
+        return ONB_OK;
+    }
     if (order > ONB_MAX_ORDER) { c->err = "order above 20"; return ONB_ERR_ARG; }
     int ne = 1; for (int d = 0; d < c->PD; ++d) ne *= (order + 1);
     if (ne > 128) { c->err = "(order+1)^PD exceeds the 128-slot equivalent block of the GPU build"; return ONB_ERR_UNSUPPORTED; }
-    c->block = block_size; c->order = order; c->arith = arith; c->ncp = order + 1; c->num_eqps = ne; c->ebs = 128;
+    c->block = block_size; c->order = order; c->arith = arith; c->ncp = order + 1; c->num_eqps = ne; c->ebs = 128; c->legacy = false;
     return ONB_OK;
 }
 
@@ -355,8 +361,13 @@ int onb_upward(onb_context* c, int which) {
     onb_scratch_reset(c);
     if (which < 0 || which > 1) return ONB_ERR_ARG;
     ONB_CUDA(cudaSetDevice(c->device));
+    if (c->legacy && which == 1) {
+        c->err = "legacy equivalents (-o omitted) exist for sources only: the reference's calcEquivalents returns at once for targets (barneshut.hpp:953)";
+        return ONB_ERR_UNSUPPORTED;
+    }
     PhaseTimer tm(c, "upward");
-    int rc = onb_bary_upward(c, c->parts[which], c->parts[which + 2], c->trees[which]);
+    int rc = c->legacy ? onb_legacy_equivalents(c, c->parts[which], c->parts[which + 2], c->trees[which])
+                       : onb_bary_upward(c, c->parts[which], c->parts[which + 2], c->trees[which]);
     if (rc == ONB_OK && which == 0) rc = onb_pack_sources(c, c->parts[2]);
     if (rc == ONB_OK && which == 0 && !c->parts[0].packed_valid) rc = onb_pack_sources(c, c->parts[0]);
     tm.stop();
@@ -396,13 +407,17 @@ int onb_treecode3(onb_context* c, float theta, float* flops) {
     onb_free_worklist(c, wl);
     te.stop();
     if (flops) *flops = (float)c->flops_per_pair * (float)c->block *
-                        ((float)c->stats[0] * (float)c->block + (float)c->stats[1] * (float)c->num_eqps);        // :335-336
+                        ((float)c->stats[0] * (float)c->block + (float)c->stats[1] * (float)(c->legacy ? c->root_epnum : (uint32_t)c->num_eqps));        // :335-336
     return rc;
 }
 int onb_fastsumm(onb_context* c, float theta) {
     onb_scratch_reset(c);
     ONB_CUDA(cudaSetDevice(c->device));
     if (!c->has_fastsumm) { c->err = "this physics has no dual-tree method in the reference (onvortgrad3d.cpp:264)"; return ONB_ERR_UNSUPPORTED; }
+    if (c->legacy) {
+        c->err = "the dual tree needs barycentric equivalent targets (-o=<order>): with -o omitted the reference builds no target equivalents at all (barneshut.hpp:953)";
+        return ONB_ERR_UNSUPPORTED;
+    }
     int rc = need_trees(c, true, true); if (rc) return rc;
     PhaseTimer te(c, "eval");
     rc = onb_run_fastsumm(c, theta);
@@ -416,7 +431,7 @@ int onb_treecode2(onb_context* c, float theta, float* flops) {
     PhaseTimer te(c, "eval");
     rc = onb_run_treecode2(c, theta, 2);
     te.stop();
-    if (flops) *flops = (float)c->flops_per_pair * ((float)c->stats[0] * (float)c->block + (float)c->stats[1] * (float)c->num_eqps);   // :220-221
+    if (flops) *flops = (float)c->flops_per_pair * ((float)c->stats[0] * (float)c->block + (float)c->stats[1] * (float)(c->legacy ? c->root_epnum : (uint32_t)c->num_eqps));   // :220-221
     return rc;
 }
 int onb_treecode1(onb_context* c, float theta, float* flops) {
@@ -507,12 +522,14 @@ int onb_get_tree(onb_context* c, int which, float* x, float* nc, float* ns, floa
     ONB_CUDA(cudaMemcpy(io.data(), t.ioffset, n * 4, cudaMemcpyDeviceToHost));
     ONB_CUDA(cudaMemcpy(nm.data(), t.num, n * 4, cudaMemcpyDeviceToHost));
     const bool have_eq = c->parts[which + 2].n > 0;
+    std::vector<uint32_t> en;
+    if (c->legacy && which == 0 && have_eq && c->d_epnum && epnum) { en.resize(n); ONB_CUDA(cudaMemcpy(en.data(), c->d_epnum, n * 4, cudaMemcpyDeviceToHost)); }
     for (size_t i = 0; i < n; ++i) {
         if (ioffset) ioffset[i] = io[i];
         if (num) num[i] = nm[i];
         const bool nonleaf = have_eq && nm[i] > (uint32_t)c->block;
         if (epoffset) epoffset[i] = nonleaf ? (uint64_t)i * c->ebs : 0;                   // BarycentricLagrange.hpp:289
-        if (epnum) epnum[i] = nonleaf ? c->num_eqps : 0;
+        if (epnum) epnum[i] = nonleaf ? (en.empty() ? (uint64_t)c->num_eqps : (uint64_t)en[i]) : 0;
     }
     return ONB_OK;
 }

@@ -5,8 +5,10 @@
  * "error in fastsumm", "fast total", "onbody naive"), same seeded inputs, same error metric. Host C++ only.
  *
  * Deliberately kept quirks: "-t1=".."-t4=" parse atof(argv+3), i.e. from the '=' sign, get 0 and print the usage
- * (ongrav3d.cpp:491-506); -n goes through atoi. Not available on the GPU: omitting -o (the legacy pair-merge
- * equivalents, order = -1) - the driver says so and exits 1. Extra flag: -strict selects ARITH_STRICT.
+ * (ongrav3d.cpp:491-506); -n goes through atoi. With -o omitted (order = -1, the reference's default) the legacy pair-merge
+ * equivalents are used for treecode2/3 exactly like the reference (refineTree(srcs) + calcEquivalents); the dual tree is
+ * skipped in that mode with a note on stderr, because the reference builds no target equivalents there at all
+ * (calcEquivalents returns at barneshut.hpp:953 for targets). Extra flag: -strict selects ARITH_STRICT.
  * The direct-sum sample uses the divisor of the reference's OpenMP non-Vc build (ongrav3d.cpp:560), the build the oracle uses.
  */
 #pragma once
@@ -64,14 +66,13 @@ static int run_driver(int argc, char* argv[], const DriverSpec& spec) {
         } else if (strncmp(argv[i], "-h", 2) == 0 || strncmp(argv[i], "--h", 3) == 0) usage();
     }
     std::string withwhat;
-    if (order < 0) {
-        std::fprintf(stderr, "%s: the GPU build implements the barycentric path only; pass -o=<order> "
-                             "(the reference's default, order=-1, selects its legacy pair-merge equivalents)\n", spec.progname);
-        return 1;
+    const bool legacy = order < 0;
+    if (legacy) {
+        withwhat = "equivalent particles";                                               // ongrav3d.cpp:543-544
+    } else {
+        withwhat = "a barycentric grid";
+        eqBlockSize = 128;     // the GPU build pads (order+1)^PD to one 128-slot block (the reference pads to its SIMD width)
     }
-    withwhat = "a barycentric grid";
-    size_t ne = 1; for (int d = 0; d < spec.PD; ++d) ne *= (size_t)(order + 1);
-    eqBlockSize = 128;     // the GPU build pads (order+1)^PD to one 128-slot block (the reference pads to its SIMD width)
 
     std::printf("Running %s with %ld sources and %ld targets\n", spec.progname, (long)numSrcs, (long)numTargs);
     std::printf("  source block sizes %ld and %ld, target block size %ld\n\n", (long)blockSize, (long)eqBlockSize, (long)blockSize);
@@ -96,13 +97,18 @@ static int run_driver(int argc, char* argv[], const DriverSpec& spec) {
     start = now_s(); DRV_CHECK(onb_make_tree(ctx, 0)); double dt = now_s() - start;
     std::printf("  build tree time:\t\t[%.4f] seconds\n", dt);
     for (int k = 1; k < 5; ++k) treetime[k] += dt;
+    if (legacy) {                                                                        // ongrav3d.cpp:617-630
+        start = now_s(); DRV_CHECK(onb_refine(ctx, 0)); dt = now_s() - start;
+        std::printf("  refine within leaf nodes:\t[%.4f] seconds\n", dt);
+        for (int k = 2; k < 5; ++k) treetime[k] += dt;
+    }
     std::printf("  add buffer at end of srcs:\t[%.4f] seconds\n", 0.0);
     std::printf("\nCalculating equivalent particles\n");
     int levels = 0, numnodes = 0; onb_tree_shape(ctx, 0, &levels, &numnodes);
     std::printf("  need %ld particles and block size of %ld\n", (long)(numnodes / 2) * (long)eqBlockSize, (long)eqBlockSize);
     std::printf("  allocate eqsrcs structures:\t[%.4f] seconds\n", 0.0);
     start = now_s(); DRV_CHECK(onb_upward(ctx, 0)); dt = now_s() - start;
-    std::printf("  create barylagrange parts:\t[%.4f] seconds\n", dt);
+    std::printf(legacy ? "  create equivalent parts:\t[%.4f] seconds\n" : "  create barylagrange parts:\t[%.4f] seconds\n", dt);
     for (int k = 2; k < 5; ++k) treetime[k] += dt;
 
     std::printf("\nBuilding the target tree\n");
@@ -110,14 +116,20 @@ static int run_driver(int argc, char* argv[], const DriverSpec& spec) {
     start = now_s(); DRV_CHECK(onb_make_tree(ctx, 1)); dt = now_s() - start;
     std::printf("  build tree time:\t\t[%.4f] seconds\n", dt);
     treetime[3] += dt; treetime[4] += dt;
+    const bool run_fast = spec.has_fast && !legacy;
+    if (spec.has_fast && legacy)
+        std::fprintf(stderr, "%s: -o omitted: the dual-tree method is skipped (the reference's legacy path builds no target equivalents, "
+                             "barneshut.hpp:953); pass -o=<order> for it\n", spec.progname);
     if (spec.has_fast) {
+        // (also with -o omitted: the reference refines the target leaves whenever the dual tree is scheduled,
+        // ongrav3d.cpp:686-724, which fixes the target order every method's "particle 0" line refers to)
         std::printf("\nCalculating equivalent targ points\n");
         onb_tree_shape(ctx, 1, &levels, &numnodes);
         std::printf("  need %ld particles and block size of %ld\n", (long)(numnodes / 2) * (long)eqBlockSize, (long)eqBlockSize);
         std::printf("  allocate eqtargs structures:\t[%.4f] seconds\n", 0.0);
         start = now_s(); DRV_CHECK(onb_refine(ctx, 1)); dt = now_s() - start;
         std::printf("  refine within leaf nodes:\t[%.4f] seconds\n", dt); treetime[4] += dt;
-        start = now_s(); DRV_CHECK(onb_upward(ctx, 1)); dt = now_s() - start;
+        start = now_s(); if (run_fast) DRV_CHECK(onb_upward(ctx, 1)); dt = now_s() - start;
         std::printf("  create equivalent parts:\t[%.4f] seconds\n", dt); treetime[4] += dt;
     }
 
@@ -169,7 +181,7 @@ static int run_driver(int argc, char* argv[], const DriverSpec& spec) {
         std::printf("[%s total]:\t\t[%.4f] seconds\n", m.tag, treetime[m.tt] + dt);
         fetch(); echo(); report_err(m.errname);
     }
-    if (spec.has_fast) {
+    if (run_fast) {
         std::printf("\nRun the fast O(N) method with theta %g\n", theta4);
         DRV_CHECK(onb_zero_vels(ctx));
         start = now_s(); DRV_CHECK(onb_fastsumm(ctx, theta4)); dt = now_s() - start;

@@ -86,6 +86,9 @@ struct onb_context {
     bool has_tr = false, has_fastsumm = true;
     int block = 128, order = 4, arith = ONB_ARITH_FAST;
     int ncp = 5, num_eqps = 125, ebs = 128;
+    // legacy equivalents (-o omitted, order = -1, barneshut.hpp:946-1061): per-node counts of pair-merged equivalents
+    bool legacy = false;
+    uint32_t* d_epnum = nullptr; uint32_t epnum_cap = 0, root_epnum = 0;
     int shard_rank = 0, shard_n = 1;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
@@ -180,6 +183,7 @@ int onb_tree_refine(onb_context* c, DParts& p, DTree& t);
 // bary.cu
 int onb_bary_upward(onb_context* c, DParts& p, DParts& ep, DTree& t);
 int onb_bary_downward_level(onb_context* c, int level);
+int onb_legacy_equivalents(onb_context* c, DParts& p, DParts& ep, DTree& t);
 // p2p.cu
 int onb_pack_sources(onb_context* c, DParts& p);
 int onb_p2p_direct(onb_context* c, uint64_t tskip);

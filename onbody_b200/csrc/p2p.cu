@@ -108,13 +108,14 @@ struct P2PArgs {
     const float4* e_pk0; const float4* e_pk1; const float* e_pk2;   // equivalent sources
     const uint32_t* s_ioffset; const uint32_t* s_num;
     const uint32_t* item_node; const uint32_t* start; const uint32_t* entries;
+    const uint32_t* s_epnum;        // legacy equivalents: per source node count (null = num_eqps everywhere)
     uint32_t block, ebs, num_eqps, node_base, nentries;
 };
 
 __device__ __forceinline__ TileRef decode_entry(const P2PArgs& a, uint32_t entry) {
     TileRef t;
     const uint32_t S = entry & 0x7fffffffu;
-    if (entry >> 31) { t.p0 = a.e_pk0; t.p1 = a.e_pk1; t.p2 = a.e_pk2; t.off = S * a.ebs; t.cnt = a.num_eqps; }
+    if (entry >> 31) { t.p0 = a.e_pk0; t.p1 = a.e_pk1; t.p2 = a.e_pk2; t.off = S * a.ebs; t.cnt = a.s_epnum ? a.s_epnum[S] : a.num_eqps; }
     else             { t.p0 = a.s_pk0; t.p1 = a.s_pk1; t.p2 = a.s_pk2; t.off = a.s_ioffset[S]; t.cnt = a.s_num[S]; }
     return t;
 }
@@ -373,6 +374,7 @@ int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tg
     a.s_ioffset = c->trees[0].ioffset; a.s_num = c->trees[0].num;
     a.item_node = wl.tgt_node; a.start = wl.start; a.entries = wl.entries;
     a.block = c->block; a.ebs = c->ebs; a.num_eqps = c->num_eqps; a.node_base = wl.node_base; a.nentries = (uint32_t)wl.nentries;
+    a.s_epnum = c->legacy ? c->d_epnum : nullptr;
     switch (c->physics) {
         case ONB_GRAV3D:     launch_lists<ONB_GRAV3D>(c, a, wl.nitems); break;
         case ONB_VORT3D:     launch_lists<ONB_VORT3D>(c, a, wl.nitems); break;

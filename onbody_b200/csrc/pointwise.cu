@@ -26,6 +26,7 @@ struct PwArgs {
     const float4* s_pk0; const float4* s_pk1; const float* s_pk2;
     const float4* e_pk0; const float4* e_pk1; const float* e_pk2;
     unsigned long long* stats;     // [0] sltp [1] sbtp [9] pairs
+    const uint32_t* s_epnum;       // legacy equivalents: per source node count (null = num_eqps everywhere)
     uint32_t t_lo, t_hi, block, ebs, num_eqps; float theta;
 };
 
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32) k_pointwise(const __grid_consta
         const uint32_t am = __ballot_sync(0xffffffffu, accept);
         if (am) {
             if (VARIANT == 2) {                                                           // :177 equivalent particles of the node
-                const uint32_t off = S * a.ebs, cnt = a.num_eqps;
+                const uint32_t off = S * a.ebs, cnt = a.s_epnum ? a.s_epnum[S] : a.num_eqps;
                 for (uint32_t j = lane; j < cnt; j += 32) {
                     sA[wib][j] = a.e_pk0[off + j];
                     if (Phys<PHYS>::NF4 > 1) sB[wib][j] = a.e_pk1[off + j];
@@ -175,6 +176,7 @@ int onb_run_treecode2(onb_context* c, float theta, int variant) {
     a.t_lo = (uint32_t)(n * (uint64_t)c->shard_rank / (uint64_t)c->shard_n);
     a.t_hi = (uint32_t)(n * (uint64_t)(c->shard_rank + 1) / (uint64_t)c->shard_n);
     a.block = c->block; a.ebs = c->ebs; a.num_eqps = c->num_eqps; a.theta = theta;
+    a.s_epnum = c->legacy ? c->d_epnum : nullptr;
     const uint32_t nt = a.t_hi - a.t_lo;
     if (nt > 0) {
         const uint32_t blocks = (nt + PW_WARPS * 32 - 1) / (PW_WARPS * 32);

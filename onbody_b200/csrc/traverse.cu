@@ -40,6 +40,7 @@ struct BoxArgs {
     const uint32_t* start;          // per leaf (fill pass)
     uint32_t* entries;
     unsigned long long* stats;      // [0] sltp [1] sbtp [9] pairs
+    const uint32_t* s_epnum;        // legacy equivalents: per source node count (null = num_eqps everywhere)
     uint32_t block, num_eqps; int PD; float theta;
 };
 
@@ -68,7 +69,7 @@ __global__ void k_boxwise(const BoxArgs a) {
         const float snr = a.st.nr[S];
         const float testrad = __fadd_rn(fmaxf(snr, tnr), __fmul_rn(0.25f, fminf(snr, tnr)));          // :280
         if (__fdiv_rn(dist, __fmul_rn(2.0f, testrad)) > a.theta) {                                     // :283
-            if (FILL) { out[n] = S | 0x80000000u; pairs += (unsigned long long)a.num_eqps * tcnt; }
+            if (FILL) { out[n] = S | 0x80000000u; pairs += (unsigned long long)(a.s_epnum ? a.s_epnum[S] : a.num_eqps) * tcnt; }
             ++n; ++nb;
         } else {
             if (sp + 2 > 64) { continue; }      // cannot happen: depth <= levels <= 32
@@ -248,6 +249,7 @@ int onb_lists_boxwise(onb_context* c, float theta, WorkList& wl) {
     BoxArgs a; a.st = view_of(st); a.tt = view_of(tt); a.leaf_nodes = wl.tgt_node; a.nleaves = nl;
     a.counts = wl.start; a.start = wl.start; a.entries = nullptr; a.stats = d_stats;
     a.block = c->block; a.num_eqps = c->num_eqps; a.PD = c->PD; a.theta = theta;
+    a.s_epnum = c->legacy ? c->d_epnum : nullptr;
     const int TB = 128;
     k_boxwise<false><<<(nl + TB - 1) / TB, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());

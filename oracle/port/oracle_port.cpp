@@ -465,6 +465,56 @@ void bary_upward_node(Session& S, const PParts& p, PParts& ep, PTree& t, const C
     }
 }
 
+// calcEquivalents barneshut.hpp:946-1061 - the drivers' default when -o is omitted (order = -1): every non-leaf node
+// gets ceil(cnt/2) equivalents per child, each the strength-weighted merge of two consecutive points of the child
+// (its real particles if it is a leaf, its own equivalents otherwise), an odd last point is passed up unchanged.
+// The recursion only orders children before parents, so it is restated level by level, deepest first.
+void legacy_merge(const PParts& sp, size_t i1, size_t i2, PParts& ep, size_t iep) {         // :985-1001 == :1031-1043
+    const int PD = sp.PD, SD = sp.SD;
+    float str1, str2;
+    if (SD == 1) {
+        str1 = std::max(1.e-20f, std::abs(sp.s[0][i1]));
+        str2 = std::max(1.e-20f, std::abs(sp.s[0][i2]));
+    } else {
+        str1 = 0.0f; for (int d = 0; d < SD; ++d) str1 += std::pow(sp.s[d][i1], 2);
+        str1 = std::max(1.e-20f, std::sqrt(str1));
+        str2 = 0.0f; for (int d = 0; d < SD; ++d) str2 += std::pow(sp.s[d][i2], 2);
+        str2 = std::max(1.e-20f, std::sqrt(str2));
+    }
+    const float pairm = 1.0 / (str1 + str2);
+    for (int d = 0; d < PD; ++d) ep.x[d][iep] = (sp.x[d][i1]*str1 + sp.x[d][i2]*str2) * pairm;
+    ep.r[iep] = std::sqrt((std::pow(sp.r[i1],2)*str1 + std::pow(sp.r[i2],2)*str2) * pairm);
+    for (int d = 0; d < SD; ++d) ep.s[d][iep] = sp.s[d][i1] + sp.s[d][i2];
+}
+void legacy_equivalents(Session& S, PParts& p, PParts& ep, PTree& t) {
+    (void)S;
+    ep.resize((size_t)(t.numnodes / 2) * ep.blockSize);                                  // ongrav3d.cpp:645
+    if (!p.are_sources || !ep.are_sources) return;                                       // :953
+    const size_t ebs = ep.blockSize;
+    for (int lev = t.levels - 1; lev >= 0; --lev)
+        for (size_t node = (size_t)1 << lev; node < ((size_t)2 << lev); ++node) {
+            if (!(t.num[node] > p.blockSize)) continue;
+            t.epoffset[node] = node * ebs; t.epnum[node] = 0;                            // :955-956
+            for (size_t child = 2*node; child < 2*node + 2; ++child) {
+                const bool leaf = !(t.num[child] > p.blockSize);                         // :963
+                const PParts& sp = leaf ? p : ep;
+                const size_t first = leaf ? t.ioffset[child] : t.epoffset[child];
+                const size_t cnt = leaf ? t.num[child] : t.epnum[child];
+                const size_t numEqps = (cnt + 1) / 2, istart = (ebs / 2) * child;        // :974-975, :1020-1021
+                for (size_t j = 0; j < numEqps; ++j) {
+                    const size_t i1 = first + 2*j, iep = istart + j;
+                    if (2*j + 1 < cnt) legacy_merge(sp, i1, i1 + 1, ep, iep);
+                    else {                                                               // :1003-1008, :1049-1054
+                        for (int d = 0; d < p.PD; ++d) ep.x[d][iep] = sp.x[d][i1];
+                        for (int d = 0; d < p.SD; ++d) ep.s[d][iep] = sp.s[d][i1];
+                        ep.r[iep] = sp.r[i1];
+                    }
+                }
+                t.epnum[node] += numEqps;
+            }
+        }
+}
+
 void bary_upward(Session& S, PParts& p, PParts& ep, PTree& t) {                          // :255-417, post-order == deepest level first
     ep.resize((size_t)(t.numnodes / 2) * ep.blockSize);                                  // ongrav3d.cpp:645
     const Cheb c = make_cheb(S.order);
@@ -636,7 +686,11 @@ static PTree& tree_of(Session* S, int which) { return which == 0 ? S->stree : S-
 
 void oport_make_tree(void* h, int which) { Session* S = (Session*)h; make_tree(*S, parts_of(S, which), tree_of(S, which)); }
 void oport_refine(void* h, int which) { Session* S = (Session*)h; refine_tree(*S, parts_of(S, which), tree_of(S, which)); }
-void oport_upward(void* h, int which) { Session* S = (Session*)h; bary_upward(*S, parts_of(S, which), parts_of(S, which+2), tree_of(S, which)); }
+void oport_upward(void* h, int which) {
+    Session* S = (Session*)h;
+    if (S->order < 0) legacy_equivalents(*S, parts_of(S, which), parts_of(S, which+2), tree_of(S, which));
+    else bary_upward(*S, parts_of(S, which), parts_of(S, which+2), tree_of(S, which));
+}
 void oport_zero_vels(void* h) { Session* S = (Session*)h; for (int d = 0; d < S->OD; ++d) std::fill(S->targs.u[d].begin(), S->targs.u[d].end(), 0.0f); }
 
 float oport_naive(void* h, uint64_t tskip) {                                             // barneshut.hpp:46-53

@@ -93,6 +93,11 @@ OREF_API void oref_upward(void* h, int which) {
     OrefParts& ep = oref_parts(s, which+2);
     OrefTree& t = oref_tree(s, which);
     ep.resize((t.numnodes/2) * ep.blockSize);
+    if (s->order < 0) {
+        // the drivers' default (-o omitted): hierarchical pair-merge equivalents, ongrav3d.cpp:654-659
+        (void) calcEquivalents(p, ep, t, 1);
+        return;
+    }
     #pragma omp parallel
     #pragma omp single
     (void) calcBarycentricLagrange(p, ep, t, s->order, 1);

@@ -57,7 +57,28 @@ def one(physics, n, theta):
     return out
 
 
+def legacy(physics="grav3d", n=20000, theta=1.2):
+    """-o omitted (order = -1): refineTree(srcs) + calcEquivalents (barneshut.hpp:946-1061), treecode2/3 over them"""
+    out = {"physics": physics, "n": n, "theta": theta}
+    s = RefSession(physics, n, n, order=-1, build="strict")
+    s.init_driver(); s.make_tree(0); s.refine(0); s.upward(0); s.make_tree(1)
+    e, t = s.parts(2), s.tree(0)
+    out["srcs.x"] = h(s.parts(0)["x"]); out["eqsrcs.x"] = h(e["x"]); out["eqsrcs.r"] = h(e["r"]); out["eqsrcs.s"] = h(e["s"])
+    out["stree.epnum"] = h(t["epnum"]); out["stree.epoffset"] = h(t["epoffset"])
+    for name in ("treecode2", "treecode3"):
+        s.zero_vels(); out[name + ".flops"] = getattr(s, name)(theta); out[name + ".u"] = h(s.parts(1)["u"])
+    return out
+
+
 if __name__ == "__main__":
+    if "--legacy-only" in sys.argv:      # add the legacy case to the existing file without touching the others
+        with open(os.path.join(HERE, "golden.json")) as f:
+            g = json.load(f)
+        g["legacy"] = legacy()
+        with open(os.path.join(HERE, "golden.json"), "w") as f:
+            json.dump(g, f, indent=1)
+        print("wrote the legacy case")
+        sys.exit(0)
     res = [one(*c) for c in CASES]
     # SURVEY.md section 4 golden values, generated independently by the survey from the same reference (N=1e5)
     survey = {"grav3d_100000": {"targs.gidx": "4dabb0d8b604b1af", "srcs.x0": "fc790cc62bf536c0", "stree.nr": "d236dfc82c723b6a",
@@ -65,5 +86,5 @@ if __name__ == "__main__":
               "dtt_counts_1e5_t1.4": {"sltl": 52086, "sbtl": 3988, "sltb": 3989, "sbtb": 17570, "tlc": 782, "bpc": 780},
               "dtt_counts_1e6_t1.4": {"sltl": 612957, "sbtl": 57780, "sltb": 57774, "sbtb": 297403, "tlc": 7813}}
     with open(os.path.join(HERE, "golden.json"), "w") as f:
-        json.dump({"cases": res, "survey": survey}, f, indent=1)
+        json.dump({"cases": res, "survey": survey, "legacy": legacy()}, f, indent=1)
     print("wrote", len(res), "cases")

@@ -326,3 +326,48 @@ def test_fastsumm_size_cache_hit_and_miss():
     h.init_driver(); h.make_tree(0); h.upward(0); h.make_tree(1); h.refine(1); h.upward(1)
     h.zero_vels(); h.fastsumm(1.1)
     assert bits_equal(h.parts(1, ("u",))["u"], res[1.1][0]) and h.stats() == res[1.1][1]
+
+
+def _run_legacy(s, theta):
+    out = {}
+    s.init_driver(); s.make_tree(0); s.refine(0); s.upward(0); s.make_tree(1)
+    e, t = s.parts(2), s.tree(0)
+    out.update({"srcs.x": s.parts(0)["x"], "eqsrcs.x": e["x"], "eqsrcs.r": e["r"], "eqsrcs.s": e["s"], "stree.epnum": t["epnum"]})
+    for name in ("treecode2", "treecode3"):
+        s.zero_vels(); out[name + ".flops"] = getattr(s, name)(theta); out[name + ".u"] = s.parts(1)["u"]
+    return out
+
+
+@pytest.mark.parametrize("physics,n,block", [("grav3d", 20000, 128), ("vort3d", 9000, 128), ("vort2d", 7001, 128), ("vortgrad3d", 5000, 128), ("grav3d", 6000, 64)])
+def test_legacy_equivalents_strict_bit_exact(physics, n, block):
+    """-o omitted (order = -1, the drivers' default): refineTree(srcs) + pair-merge equivalents (barneshut.hpp:946-1061)
+    and treecode2/3 over them, every array and every result bit-identical to the oracle"""
+    from onbody_b200.api import GpuSession, ARITH_STRICT
+    from oracle.refapi import PortSession
+    a = _run_legacy(PortSession(physics, n, n, block=block, order=-1, eq_block=block), 1.2)
+    b = _run_legacy(GpuSession(physics, n, n, block=block, order=-1, arith=ARITH_STRICT), 1.2)
+    for k in ("srcs.x", "stree.epnum", "treecode2.u", "treecode3.u"):
+        assert bits_equal(a[k], b[k]), k
+    # equivalent arrays: the reference strides node blocks by blockSize, the GPU build by 128 - compare node by node
+    ep = a["stree.epnum"]
+    for node in np.nonzero(ep)[0][:4000]:
+        cnt = int(ep[node])
+        for key in ("eqsrcs.x", "eqsrcs.r", "eqsrcs.s"):
+            ra = a[key][..., node * block: node * block + cnt]; rb = b[key][..., node * 128: node * 128 + cnt]
+            assert bits_equal(np.ascontiguousarray(ra), np.ascontiguousarray(rb)), (key, node)
+    assert a["treecode2.flops"] == b["treecode2.flops"] and a["treecode3.flops"] == b["treecode3.flops"]
+
+
+def test_legacy_equivalents_fast_arithmetic_and_refusals():
+    from onbody_b200.api import GpuSession, ARITH_FAST, OnbodyError
+    from oracle.refapi import PortSession
+    n = 30000
+    a = _run_legacy(PortSession("grav3d", n, n, order=-1), 1.2)
+    g = GpuSession("grav3d", n, n, order=-1, arith=ARITH_FAST)
+    b = _run_legacy(g, 1.2)
+    for k in ("treecode2.u", "treecode3.u"):
+        assert rel_rms(b[k], a[k]) < 1e-6, (k, rel_rms(b[k], a[k]))
+    with pytest.raises(OnbodyError):
+        g.fastsumm(1.2)          # no target equivalents in the legacy mode (barneshut.hpp:953)
+    with pytest.raises(OnbodyError):
+        g.upward(1)

@@ -85,3 +85,42 @@ def test_reference_cli_binary_matches_golden_stdout():
         pytest.skip("reference driver binary not built")
     out = subprocess.run([exe, "-n=20000", "-t=1.2", "-o=4", "-b=128"], stdout=subprocess.PIPE, text=True, timeout=300).stdout
     assert "error in fastsumm (max/rms)" in out and "[fast total]" in out and "[onbody naive]" in out
+
+
+def _run_legacy(s, theta):
+    """the drivers' sequence when -o is omitted (order = -1): refineTree(srcs) + calcEquivalents, then treecode2/3
+    (ongrav3d.cpp:617-659); the dual tree has no target equivalents in that mode (barneshut.hpp:953)"""
+    out = {}
+    s.init_driver(); s.make_tree(0); s.refine(0); s.upward(0); s.make_tree(1)
+    e, t = s.parts(2), s.tree(0)
+    out.update({"srcs.x": s.parts(0)["x"], "eqsrcs.x": e["x"], "eqsrcs.r": e["r"], "eqsrcs.s": e["s"], "stree.epnum": t["epnum"], "stree.epoffset": t["epoffset"]})
+    for name in ("treecode2", "treecode3"):
+        s.zero_vels(); out[name + ".flops"] = getattr(s, name)(theta); out[name + ".u"] = s.parts(1)["u"]
+    return out
+
+
+@pytest.mark.skipif(not ref_available("grav3d"), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("physics,n", [("grav3d", 6100), ("vort3d", 5000), ("vort2d", 7001), ("vortgrad3d", 3000)])
+def test_port_legacy_equivalents_equal_compiled_reference(physics, n):
+    """-o omitted: pair-merge equivalents (barneshut.hpp:946-1061) of the restatement against the reference itself"""
+    a = _run_legacy(RefSession(physics, n, n, order=-1), 1.2)
+    b = _run_legacy(PortSession(physics, n, n, order=-1), 1.2)
+    for k, v in a.items():
+        if isinstance(v, np.ndarray):
+            assert bits_equal(v, b[k]), k
+        else:
+            assert v == b[k], k
+    assert 0 < int(a["stree.epnum"][1]) <= 128
+
+
+def test_port_legacy_golden(golden):
+    """known answers of the legacy path generated from the compiled reference (tests/golden/make_golden.py)"""
+    case = golden.get("legacy")
+    if not case:
+        pytest.skip("golden.json has no legacy case")
+    out = _run_legacy(PortSession(case["physics"], case["n"], case["n"], order=-1), case["theta"])
+    for k, v in case.items():
+        if k in out and isinstance(out[k], np.ndarray):
+            assert "%016x" % fnv1a64(out[k]) == v, k
+        elif k in out:
+            assert float(out[k]) == v, k
