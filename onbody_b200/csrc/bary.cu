@@ -45,7 +45,11 @@ __device__ __forceinline__ float bary_row(int PD, int ncp, const float* wk, cons
     return __fdiv_rn(1.0f, denom);
 }
 
-template <int PD, int SD>
+// NCP > 0 (3-D, order+1 == NCP <= 5): every contributor also stores the NCP x NCP products (den*a0[k0])*a1[k1] - exactly
+// the intermediate of the reference's wgt = ((den*a0)*a1)*a2 - so that the accumulation loop needs one multiplication per
+// weight instead of three and two shared-memory reads instead of four. Same rounding sequence: results stay bit-identical.
+constexpr int W01_STRIDE = 27;
+template <int PD, int SD, int NCP>
 __global__ void __launch_bounds__(128) k_upward(const UpArgs a) {
     const uint32_t node = (1u << a.level) + blockIdx.x;
     if (a.t.num[node] <= a.block) return;                                                 // :266 leaves have no equivalents
@@ -54,6 +58,7 @@ __global__ void __launch_bounds__(128) k_upward(const UpArgs a) {
     __shared__ float s_am[128 * AM_STRIDE];
     __shared__ float s_den[128];
     __shared__ float s_str[3][128];
+    __shared__ float s_w01[NCP > 0 ? 128 * W01_STRIDE : 1];
     const uint32_t e0 = node * a.ebs;                                                     // :289
     if (tid < PD * ncp) {
         const int d = tid / ncp, k = tid % ncp;
@@ -86,12 +91,32 @@ __global__ void __launch_bounds__(128) k_upward(const UpArgs a) {
             float px[3];
             #pragma unroll
             for (int d = 0; d < PD; ++d) px[d] = sp.x[d][is + tid];
-            s_den[tid] = bary_row(PD, ncp, a.ch.wk, px, lsk, &s_am[tid * AM_STRIDE]);
+            const float den = bary_row(PD, ncp, a.ch.wk, px, lsk, &s_am[tid * AM_STRIDE]);
+            s_den[tid] = den;
+            if (NCP > 0) {
+                const float* row = &s_am[tid * AM_STRIDE];
+                #pragma unroll
+                for (int k0 = 0; k0 < NCP; ++k0) {
+                    const float w0 = __fmul_rn(den, row[k0]);
+                    #pragma unroll
+                    for (int k1 = 0; k1 < NCP; ++k1) s_w01[tid * W01_STRIDE + k1 * NCP + k0] = __fmul_rn(w0, row[NCP + k1]);
+                }
+            }
             #pragma unroll
             for (int d = 0; d < SD; ++d) s_str[d][tid] = sp.s[d][is + tid];
         }
         __syncthreads();
-        if (tid < numEqps) {
+        if (NCP > 0) {
+            if (tid < numEqps) {
+                const int o01 = kd[1] * NCP + kd[0];
+                #pragma unroll 4
+                for (int j = 0; j < cnt; ++j) {                                           // :190, :228-241
+                    const float wgt = __fmul_rn(s_w01[j * W01_STRIDE + o01], s_am[j * AM_STRIDE + o2]);
+                    #pragma unroll
+                    for (int d = 0; d < SD; ++d) acc[d] = __fadd_rn(acc[d], __fmul_rn(wgt, s_str[d][j]));
+                }
+            }
+        } else if (tid < numEqps) {
             #pragma unroll 4
             for (int j = 0; j < cnt; ++j) {                                               // :190, :228-241
                 const float* row = &s_am[j * AM_STRIDE];
@@ -116,7 +141,11 @@ struct DownArgs {
     uint32_t block, ebs, shard_lo, shard_hi; int level, PD, OD, ncp, numEqps;
 };
 
-template <int PD, int OD>
+// NCP > 0 (3-D, OD == 3, order+1 == NCP): the point's weights live in registers as (den*a0[k0])*a1[k1], the loops over the
+// parent's equivalent points are fully unrolled and the parent's values are read as one float4 broadcast per point: one
+// multiplication + three accumulations per equivalent point. The multiplication order is the reference's, so STRICT
+// (separate multiply and add) stays bit-identical; FAST contracts the accumulation into FMAs.
+template <int PD, int OD, int NCP, bool FAST>
 __global__ void __launch_bounds__(128) k_downward(const DownArgs a) {
     const uint32_t T = (1u << a.level) + blockIdx.x;
     const uint32_t tn = a.t.num[T];
@@ -131,6 +160,7 @@ __global__ void __launch_bounds__(128) k_downward(const DownArgs a) {
     __shared__ float lsk[3 * (ONB_MAX_ORDER + 1)];
     __shared__ float s_am[128 * AM_STRIDE];
     __shared__ float s_pu[3][128];
+    __shared__ float4 s_pu4[NCP > 0 ? 128 : 1];
     float acc[3] = {0.0f, 0.0f, 0.0f};                                                    // :232 / :270 zero fill
     if (T > 1) {
         const uint32_t pe0 = (T >> 1) * a.ebs;                                            // parent's equivalent points
@@ -139,13 +169,38 @@ __global__ void __launch_bounds__(128) k_downward(const DownArgs a) {
             int stride = 1; for (int q = 0; q < d; ++q) stride *= ncp;
             lsk[tid] = a.tb.x[d][pe0 + stride * k];
         }
-        if (tid < numEqps) for (int d = 0; d < OD; ++d) s_pu[d][tid] = a.tb.u[d][pe0 + tid];
+        if (NCP > 0) { if (tid < numEqps) s_pu4[tid] = make_float4(a.tb.u[0][pe0 + tid], a.tb.u[1][pe0 + tid], a.tb.u[2][pe0 + tid], 0.0f); }
+        else if (tid < numEqps) for (int d = 0; d < OD; ++d) s_pu[d][tid] = a.tb.u[d][pe0 + tid];
         __syncthreads();
         if (tid < cnt) {
             float px[3];
             for (int d = 0; d < PD; ++d) px[d] = tp.x[d][p0 + tid];
             float* row = &s_am[tid * AM_STRIDE];
             const float denom = bary_row(PD, ncp, a.ch.wk, px, lsk, row);
+            if (NCP > 0) {
+                float r01[NCP > 0 ? NCP : 1][NCP > 0 ? NCP : 1], a2[NCP > 0 ? NCP : 1];
+                #pragma unroll
+                for (int k0 = 0; k0 < NCP; ++k0) {
+                    const float w0 = __fmul_rn(denom, row[k0]);
+                    #pragma unroll
+                    for (int k1 = 0; k1 < NCP; ++k1) r01[k1][k0] = __fmul_rn(w0, row[NCP + k1]);
+                }
+                #pragma unroll
+                for (int k2 = 0; k2 < NCP; ++k2) a2[k2] = row[2 * NCP + k2];
+                #pragma unroll
+                for (int k2 = 0; k2 < NCP; ++k2) {
+                    #pragma unroll
+                    for (int k1 = 0; k1 < NCP; ++k1) {
+                        #pragma unroll
+                        for (int k0 = 0; k0 < NCP; ++k0) {                                // :140-156, i = (k2*ncp + k1)*ncp + k0
+                            const float wgt = __fmul_rn(r01[k1][k0], a2[k2]);
+                            const float4 pu = s_pu4[(k2 * NCP + k1) * NCP + k0];
+                            if (FAST) { acc[0] = fmaf(wgt, pu.x, acc[0]); acc[1] = fmaf(wgt, pu.y, acc[1]); acc[2] = fmaf(wgt, pu.z, acc[2]); }
+                            else { acc[0] = __fadd_rn(acc[0], __fmul_rn(wgt, pu.x)); acc[1] = __fadd_rn(acc[1], __fmul_rn(wgt, pu.y)); acc[2] = __fadd_rn(acc[2], __fmul_rn(wgt, pu.z)); }
+                        }
+                    }
+                }
+            } else {
             int k0 = 0, k1 = 0, k2 = 0;
             #pragma unroll 5
             for (int i = 0; i < numEqps; ++i) {                                           // :140-156
@@ -155,6 +210,7 @@ __global__ void __launch_bounds__(128) k_downward(const DownArgs a) {
                 #pragma unroll
                 for (int d = 0; d < OD; ++d) acc[d] = __fadd_rn(acc[d], __fmul_rn(wgt, s_pu[d][i]));
                 if (++k0 == ncp) { k0 = 0; if (++k1 == ncp) { k1 = 0; ++k2; } }
+            }
             }
         }
     }
@@ -244,9 +300,9 @@ int onb_bary_upward(onb_context* c, DParts& p, DParts& ep, DTree& t) {
     for (int lev = t.levels - 2; lev >= 0; --lev) {      // the last level holds only leaves
         a.level = lev;
         const uint32_t G = 1u << lev;
-        if (c->PD == 3 && c->SD == 1) k_upward<3, 1><<<G, 128, 0, c->stream>>>(a);
-        else if (c->PD == 3) k_upward<3, 3><<<G, 128, 0, c->stream>>>(a);
-        else k_upward<2, 1><<<G, 128, 0, c->stream>>>(a);
+        if (c->PD == 3 && c->SD == 1) { if (c->ncp == 5) k_upward<3, 1, 5><<<G, 128, 0, c->stream>>>(a); else k_upward<3, 1, 0><<<G, 128, 0, c->stream>>>(a); }
+        else if (c->PD == 3) { if (c->ncp == 5) k_upward<3, 3, 5><<<G, 128, 0, c->stream>>>(a); else k_upward<3, 3, 0><<<G, 128, 0, c->stream>>>(a); }
+        else k_upward<2, 1, 0><<<G, 128, 0, c->stream>>>(a);
         ONB_LAUNCH(c);
     }
     ONB_CUDA(cudaGetLastError());
@@ -260,8 +316,11 @@ int onb_bary_downward_level(onb_context* c, int level) {
     a.block = c->block; a.ebs = c->ebs; a.level = level; a.PD = c->PD; a.OD = c->OD; a.ncp = c->ncp; a.numEqps = c->num_eqps;
     // shard range in particle indices (contiguous target leaves)
     onb_shard_range(c, &a.shard_lo, &a.shard_hi);
-    if (c->PD == 3) k_downward<3, 3><<<1u << level, 128, 0, c->stream>>>(a);
-    else k_downward<2, 2><<<1u << level, 128, 0, c->stream>>>(a);
+    const bool fast = c->arith != ONB_ARITH_STRICT;
+    const dim3 G(1u << level);
+    if (c->PD == 3 && c->ncp == 5) { if (fast) k_downward<3, 3, 5, true><<<G, 128, 0, c->stream>>>(a); else k_downward<3, 3, 5, false><<<G, 128, 0, c->stream>>>(a); }
+    else if (c->PD == 3) k_downward<3, 3, 0, false><<<G, 128, 0, c->stream>>>(a);
+    else k_downward<2, 2, 0, false><<<G, 128, 0, c->stream>>>(a);
     ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
     return ONB_OK;
