@@ -371,3 +371,64 @@ def test_legacy_equivalents_fast_arithmetic_and_refusals():
         g.fastsumm(1.2)          # no target equivalents in the legacy mode (barneshut.hpp:953)
     with pytest.raises(OnbodyError):
         g.upward(1)
+
+
+def test_full_size_invariants_1e7():
+    """BASELINE configs[1] at its full size (N = 1e7, -t=1.4 -o=4 -b=128), where the CPU oracle would take minutes:
+    size-independent properties of every stage, plus the numbers the reference run of the same command prints"""
+    from onbody_b200.api import GpuSession, ARITH_FAST
+    n, block = 10000000, 128
+    g = GpuSession("grav3d", n, n, arith=ARITH_FAST)
+    g.init_driver(); g.make_trees()
+    bs = g.build_stats()
+    assert bs["selects"] == 78124 and bs["stalls"] == 39 and bs["passes"] == 338547      # SURVEY App. A: the reference's own pass statistics at N = 1e7
+    ts, tt = g.tree(0), g.tree(1)
+    for t in (ts, tt):
+        num, io = t["num"].astype(np.int64), t["ioffset"].astype(np.int64)
+        assert num[1] == n and io[1] == 0
+        nonleaf = np.nonzero(num > block)[0]
+        assert np.all(num[2 * nonleaf] + num[2 * nonleaf + 1] == num[nonleaf])            # children partition the parent
+        assert np.all(io[2 * nonleaf] == io[nonleaf]) and np.all(io[2 * nonleaf + 1] == io[nonleaf] + num[2 * nonleaf])
+        assert np.all(num[2 * nonleaf] == block * 2 ** np.floor(np.log2((num[nonleaf] - 1) // block)).astype(np.int64))   # barneshut.hpp:663
+        leaves = np.nonzero((num > 0) & (num <= block))[0]
+        assert leaves.size == 78125 and num[leaves].sum() == n
+    p = g.parts(0, ("x", "s"))
+    # every particle lies inside the tight box of its leaf and of the root; the split axis separates the children
+    num, io = ts["num"].astype(np.int64), ts["ioffset"].astype(np.int64)
+    for node in (1, 2, 3, 77, 1000, 70001, 131072, 150000, 200000):
+        if num[node] == 0:
+            continue
+        seg = p["x"][:, io[node]: io[node] + num[node]]
+        lo, hi = seg.min(axis=1), seg.max(axis=1)
+        assert np.array_equal((hi - lo).astype(np.float32), ts["ns"][:, node]) and np.array_equal((0.5 * (hi + lo)).astype(np.float32), ts["nc"][:, node])
+        if num[node] > block:
+            ax = int(np.argmax(ts["ns"][:, node])); m = num[2 * node]
+            assert seg[ax, :m].max() <= seg[ax, m:].min()
+    # the reordering is a permutation of the input (multiset of strengths and of every coordinate is preserved)
+    from onbody_b200.api import driver_inputs
+    xi, ri, si = driver_inputs("grav3d", n, True)
+    assert np.array_equal(np.sort(p["s"][0]), np.sort(si[0])) and np.array_equal(np.sort(p["x"][2]), np.sort(xi[2]))
+    gi = g.parts(1, ("gidx",))["gidx"].astype(np.int64)
+    assert np.array_equal(np.sort(gi), np.arange(n))                                      # targets: gidx is a permutation ...
+    tx = g.parts(1, ("x",))["x"]
+    assert np.array_equal(tx[1], xi[1][gi])                                               # ... that maps tree order back to the input
+    # upward pass: barycentric weights sum to one, so every node's equivalent strengths sum to its particles' strengths
+    g.upward(0); g.refine(1); g.upward(1)
+    es = g.parts(2, ("s",))["s"][0].astype(np.float64).reshape(-1, 128).sum(axis=1)
+    tot = float(si[0].astype(np.float64).sum())
+    assert abs(es[1] - tot) <= 2e-5 * np.abs(si[0]).astype(np.float64).sum()
+    for node in (2, 3, 500, 40000):
+        want = p["s"][0][io[node]: io[node] + num[node]].astype(np.float64).sum()
+        assert abs(es[node] - want) <= 2e-5 * np.abs(p["s"][0][io[node]: io[node] + num[node]]).astype(np.float64).sum()
+    # dual tree: exact pair count of the lists (tests/golden/dtt_pairs.json, measured once and pinned) and the reference's
+    # accuracy against the direct sum on its own sample (every 5000th target, ongrav3d.cpp:556-561)
+    g.zero_vels(); g.fastsumm(1.4)
+    import json, os
+    from conftest import ROOT
+    with open(os.path.join(ROOT, "tests", "golden", "dtt_pairs.json")) as f:
+        assert g.last_pairs() == int(json.load(f)[str(n)])
+    u = g.parts(1, ("u",))["u"]
+    g.zero_vels(); g.naive(5000); un = g.parts(1, ("u",))["u"]
+    a, b = u[:, ::5000].astype(np.float64), un[:, ::5000].astype(np.float64)
+    rms = np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum())
+    assert 3e-5 < rms < 2e-4, rms              # the reference's README: ~1e-4 at -t=1.4 -o=4

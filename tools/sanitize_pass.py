@@ -15,3 +15,8 @@ for phys, n in (("grav3d", 40000), ("vortgrad3d", 3000), ("vort2dtr", 5000)):
         g.zero_vels(); g.fastsumm(1.3)
     print(phys, "ok", g.stats(), flush=True)
     g.close()
+# concurrent builds + the legacy (-o omitted) equivalents
+g = GpuSession("grav3d", 50000, 50000, order=-1)
+g.init_driver(); g.make_trees(); g.refine(0); g.upward(0); g.zero_vels(); g.treecode2(1.2); g.zero_vels(); g.treecode3(1.2)
+print("legacy ok", g.stats(), flush=True)
+g.close()
