@@ -20,6 +20,8 @@
  * and divide correctly rounded), which makes whole-pipeline results bit-comparable with the strict oracle.
  */
 #include "onb_internal.h"
+#include <cstdlib>
+#include <algorithm>
 #include "ptx.cuh"
 #include "pair.cuh"
 
@@ -319,8 +321,13 @@ void launch_lists(onb_context* c, const P2PArgs& a, uint32_t nitems) {
     // time ONE warp needs for the longest list, so spread each target block over more warps there (fewer targets per
     // thread). Per-target sums do not depend on the blocking, results stay bit-identical.
     if (!(g_p2p_tpt & 15) && c->arith != ONB_ARITH_STRICT) {
-        const uint32_t fill = (uint32_t)c->sm_count * 8u;
-        if (nitems <= fill) tpt = 1; else if (nitems <= 4u * fill && tpt > 2) tpt = 2;
+        static uint32_t t1 = 0, t2 = 0;      // launch sizes up to which TPT = 1 / TPT = 2 are used (tunable: ONB_TPT1_MAX, ONB_TPT2_MAX)
+        if (!t1) {
+            t1 = (uint32_t)c->sm_count * 8u; t2 = 4u * t1;
+            if (const char* e = std::getenv("ONB_TPT1_MAX")) t1 = (uint32_t)std::max(1, atoi(e));
+            if (const char* e = std::getenv("ONB_TPT2_MAX")) t2 = (uint32_t)std::max(1, atoi(e));
+        }
+        if (nitems <= t1) tpt = 1; else if (nitems <= t2 && tpt > 2) tpt = 2;
     }
     if (tpt == 1) launch_lists_t<PHYS, 1>(c, a, nitems, packed);
     else if (tpt == 2) launch_lists_t<PHYS, 2>(c, a, nitems, packed);

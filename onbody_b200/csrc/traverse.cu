@@ -21,6 +21,8 @@
  * "push_back onto the list being iterated" order of the reference.
  */
 #include "onb_internal.h"
+#include <cstdlib>
+#include <cstdio>
 
 namespace {
 
@@ -289,6 +291,9 @@ static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cach
     ONB_CUDA(onb_dmalloc(c, (void**)&d_totals, (size_t)2 * L * 4));
     std::vector<uint64_t> sizes(2 * L, 0);
     if (use_cache) sizes = c->dtt_sizes;
+    static const bool want_prof = std::getenv("ONB_DTT_PROF") != nullptr;      // diagnostics: pairs and pair-kernel time per level
+    unsigned long long* d_lvl = nullptr;
+    if (want_prof) ONB_CUDA(onb_dmalloc(c, (void**)&d_lvl, (size_t)L * 8));
 
     uint32_t *pc_start = nullptr, *pc_entries = nullptr;     // previous level's deferred lists
     std::vector<cudaEvent_t> ev((size_t)4 * L);
@@ -329,6 +334,7 @@ static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cach
         a.icap = (uint32_t)itotal; a.ccap = (uint32_t)ctotal;
         k_dtt<true><<<blocks, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
+        if (d_lvl) ONB_CUDA(cudaMemcpyAsync(d_lvl + lev, d_stats + 9, 8, cudaMemcpyDeviceToDevice, c->stream));
         cudaEventRecord(ev[4 * lev + 1], c->stream);
         // node entry: zero + interpolate from the parent (ongrav3d.cpp:232-304)
         if ((rc = onb_bary_downward_level(c, lev))) break;
@@ -345,7 +351,14 @@ static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cach
         std::vector<uint32_t> h_tot(2 * L);
         ONB_CUDA(cudaMemcpyAsync(h_tot.data(), d_totals, (size_t)2 * L * 4, cudaMemcpyDeviceToHost, c->stream));
         ONB_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<unsigned long long> h_lvl(L, 0);
+        if (d_lvl) ONB_CUDA(cudaMemcpy(h_lvl.data(), d_lvl, (size_t)L * 8, cudaMemcpyDeviceToHost));
         for (int lev = 0; lev < L; ++lev) {
+            if (d_lvl) {
+                float tp = 0; cudaEventElapsedTime(&tp, ev[4 * lev + 2], ev[4 * lev + 3]);
+                const unsigned long long pr = h_lvl[lev] - (lev ? h_lvl[lev - 1] : 0ull);
+                fprintf(stderr, "dtt level %2d: entries %10llu pairs %14llu p2p %8.3f ms -> %7.1f Gpairs/s\n", lev, (unsigned long long)sizes[2 * lev], pr, tp, tp > 0 ? pr / tp * 1e-6 : 0.0);
+            }
             float t01 = 0, t12 = 0, t23 = 0;
             cudaEventElapsedTime(&t01, ev[4 * lev], ev[4 * lev + 1]); cudaEventElapsedTime(&t12, ev[4 * lev + 1], ev[4 * lev + 2]); cudaEventElapsedTime(&t23, ev[4 * lev + 2], ev[4 * lev + 3]);
             ms_lists += t01; ms_down += t12; ms_p2p += t23;

@@ -6,6 +6,9 @@ import torch
 import torch.distributed as dist
 
 
+_UNEVEN = {"ok": True}
+
+
 def shard_ranges(session, n, world):
     return [session.shard_particle_range(n, r, world) for r in range(world)]
 
@@ -16,6 +19,15 @@ def allgather_ranges(plane, ranges, rank, world, scratch=None, group=None):
     Works on CUDA tensors over NCCL and on CPU tensors over gloo (tests)."""
     if world == 1:
         return scratch
+    if dist.get_backend(group) != "gloo" and _UNEVEN["ok"]:
+        # NCCL: every rank's range goes straight to its final place on every other rank (torch issues one grouped
+        # ncclBroadcast per rank for unequal sizes) - no padding, no staging buffer, no unpack copies
+        lo, hi = ranges[rank]
+        try:
+            dist.all_gather([plane[a:b] for a, b in ranges], plane[lo:hi], group=group)
+            return scratch
+        except Exception:          # older torch: fall back to the padded collective below, once and for all
+            _UNEVEN["ok"] = False
     chunk = max(hi - lo for lo, hi in ranges)
     lo, hi = ranges[rank]
     if scratch is None or scratch.numel() < world * chunk or scratch.device != plane.device:
