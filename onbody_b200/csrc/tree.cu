@@ -53,89 +53,20 @@ __device__ __forceinline__ float select_pivot(uint32_t nless, uint32_t wf, uint3
     const float frac = __double2float_rn(__dmul_rn(__fma_rn(9.0, (double)f0, (double)ideal), 0.1));
     return __fmaf_rn(__fsub_rn(hi, lo), frac, lo);
 }
-struct SplitArgs {
-    float* x[3];            // current coordinate planes (the select permutes x[axis] in place)
-    TreeView t;
-    uint8_t* axis_of;       // per node: split axis
-    uint32_t* pmid;         // per node: first index of the right child
-    uint32_t* lidx;         // per particle: position before this level's select (barneshut.hpp:516)
-    uint32_t* scr;          // per particle scratch for the ordered compactions
-    unsigned long long* stats;   // selects, passes, stalls, scanned
-    uint32_t block, big;    // nodes with more than `big` particles are split by the grid-wide kernels below
-    uint32_t blo, bhi;      // build range: only nodes overlapping particles [blo,bhi) are split (multi-GPU: each rank its share)
-    int level, PD, pivot_mode;
-};
-
 constexpr int SPLIT_ROUNDS = 4;   // each warp handles 4 x 32 consecutive elements per chunk
 
-// ---- one CTA = one node of this level -----------------------------------------------------
-__global__ void __launch_bounds__(1024) k_node_split(const SplitArgs a) {
-    const uint32_t node = (1u << a.level) + blockIdx.x;
-    const uint32_t n = a.t.num[node];
-    if (n == 0) return;
-    const uint32_t pf = a.t.ioffset[node], pl = pf + n;
-    if (!(pf < a.bhi && pl > a.blo)) {
-        // outside this rank's build range: not sorted here, but the shape of the tree below it is data independent
-        if (threadIdx.x == 0 && n > a.block) {
-            const uint32_t pm = pf + a.block * (1u << log_2((n - 1) / a.block));
-            a.t.ioffset[2 * node] = pf;     a.t.num[2 * node] = pm - pf;
-            a.t.ioffset[2 * node + 1] = pm; a.t.num[2 * node + 1] = pl - pm;
-        }
-        return;
-    }
-    if (n > a.big) return;
+// ---- the select passes of ONE node by ONE CTA, from any window state (barneshut.hpp:527-586) ----
+// Used by k_node_split from the full window, and by the big-level kernel to finish a node locally once its window has
+// become small (tree_big.cuh). Every thread tracks the (identical) window state in registers.
+struct SelStats { uint32_t n_pass, n_stall; unsigned long long n_scan; };
+__device__ __forceinline__ SelStats cta_select(float* key, uint32_t* lidx, uint32_t* scr, const uint32_t pf, const uint32_t pl, const uint32_t nless,
+                                               uint32_t wf, uint32_t wl, float lo, float hi, const float ideal, int iters, const int pivot_mode) {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
-
-    __shared__ float s_min[32], s_max[32];
     __shared__ uint32_t s_cnt[32], s_cnt2[32];
-    __shared__ float s_lo[3], s_hi[3];
-
-    // bounding box :621-625 (exact, order independent)
-    for (int d = 0; d < a.PD; ++d) {
-        const float* xd = a.x[d];
-        float lo = INFINITY, hi = -INFINITY;
-        for (uint32_t i = pf + tid; i < pl; i += T) { const float v = xd[i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
-        lo = warp_min(lo); hi = warp_max(hi);
-        if (lane == 0) { s_min[warp] = lo; s_max[warp] = hi; }
-        __syncthreads();
-        if (warp == 0) {
-            lo = lane < W ? s_min[lane] : INFINITY; hi = lane < W ? s_max[lane] : -INFINITY;
-            lo = warp_min(lo); hi = warp_max(hi);
-            if (lane == 0) { s_lo[d] = lo; s_hi[d] = hi; }
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        float bsss = 0.0f;
-        for (int d = 0; d < a.PD; ++d) {
-            const float ns = __fsub_rn(s_hi[d], s_lo[d]);
-            a.t.ns[d][node] = ns;
-            a.t.nc[d][node] = __fmul_rn(0.5f, __fadd_rn(s_hi[d], s_lo[d]));
-            bsss = __double2float_rn(__dadd_rn((double)bsss, __dmul_rn((double)ns, (double)ns)));   // std::pow(float,int) is double :638
-        }
-        a.t.nr[node] = __fmul_rn(0.5f, __fsqrt_rn(bsss));
-    }
-    if (n <= a.block) return;                                                            // :644 leaf
-
-    // longest axis :652-659 (first strict maximum)
-    int axis = 0; float axsz = -1.0f;
-    for (int d = 0; d < a.PD; ++d) { const float ns = __fsub_rn(s_hi[d], s_lo[d]); if (ns > axsz) { axsz = ns; axis = d; } }
-    const uint32_t nless = pf + a.block * (1u << log_2((n - 1) / a.block));              // :663
-    float* key = a.x[axis];
-    uint32_t* lidx = a.lidx;
-    uint32_t* scr = a.scr;
-
-    for (uint32_t i = pf + tid; i < pl; i += T) lidx[i] = i;                             // :516
-    __syncthreads();
-
-    // partial select :519-586; every thread tracks the (identical) window state in registers
-    uint32_t wf = pf, wl = pl - 1;
-    float lo = s_lo[axis], hi = s_hi[axis];
-    const float ideal = __fdiv_rn(__uint2float_rn(nless - pf), __uint2float_rn(pl - pf));     // :522
-    int iters = 0;
+    __shared__ float s_max[32], s_min[32];
     uint32_t n_pass = 0, n_stall = 0; unsigned long long n_scan = 0;
     while (wl > wf && iters < 100) {
-        const float pivot = select_pivot(nless, wf, wl, lo, hi, ideal, a.pivot_mode);                // :538-540
+        const float pivot = select_pivot(nless, wf, wl, lo, hi, ideal, pivot_mode);                  // :538-540
         // pass 1: m = #{v < pivot}, and the min/max the two possible next windows will have
         uint32_t cnt = 0; float mx_lt = -INFINITY, mn_ge = INFINITY;
         for (uint32_t i = wf + tid; i <= wl; i += T) {
@@ -202,6 +133,88 @@ __global__ void __launch_bounds__(1024) k_node_split(const SplitArgs a) {
         if (wf == owf && wl == owl) { ++n_stall; break; }
         ++iters;
     }
+    SelStats st; st.n_pass = n_pass; st.n_stall = n_stall; st.n_scan = n_scan;
+    return st;
+}
+
+struct SplitArgs {
+    float* x[3];            // current coordinate planes (the select permutes x[axis] in place)
+    TreeView t;
+    uint8_t* axis_of;       // per node: split axis
+    uint32_t* pmid;         // per node: first index of the right child
+    uint32_t* lidx;         // per particle: position before this level's select (barneshut.hpp:516)
+    uint32_t* scr;          // per particle scratch for the ordered compactions
+    unsigned long long* stats;   // selects, passes, stalls, scanned
+    uint32_t block, big;    // nodes with more than `big` particles are split by the grid-wide kernels below
+    uint32_t blo, bhi;      // build range: only nodes overlapping particles [blo,bhi) are split (multi-GPU: each rank its share)
+    int level, PD, pivot_mode;
+};
+
+
+// ---- one CTA = one node of this level -----------------------------------------------------
+__global__ void __launch_bounds__(1024) k_node_split(const SplitArgs a) {
+    const uint32_t node = (1u << a.level) + blockIdx.x;
+    const uint32_t n = a.t.num[node];
+    if (n == 0) return;
+    const uint32_t pf = a.t.ioffset[node], pl = pf + n;
+    if (!(pf < a.bhi && pl > a.blo)) {
+        // outside this rank's build range: not sorted here, but the shape of the tree below it is data independent
+        if (threadIdx.x == 0 && n > a.block) {
+            const uint32_t pm = pf + a.block * (1u << log_2((n - 1) / a.block));
+            a.t.ioffset[2 * node] = pf;     a.t.num[2 * node] = pm - pf;
+            a.t.ioffset[2 * node + 1] = pm; a.t.num[2 * node + 1] = pl - pm;
+        }
+        return;
+    }
+    if (n > a.big) return;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+
+    __shared__ float s_min[32], s_max[32];
+    __shared__ uint32_t s_cnt[32], s_cnt2[32];
+    __shared__ float s_lo[3], s_hi[3];
+
+    // bounding box :621-625 (exact, order independent)
+    for (int d = 0; d < a.PD; ++d) {
+        const float* xd = a.x[d];
+        float lo = INFINITY, hi = -INFINITY;
+        for (uint32_t i = pf + tid; i < pl; i += T) { const float v = xd[i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        lo = warp_min(lo); hi = warp_max(hi);
+        if (lane == 0) { s_min[warp] = lo; s_max[warp] = hi; }
+        __syncthreads();
+        if (warp == 0) {
+            lo = lane < W ? s_min[lane] : INFINITY; hi = lane < W ? s_max[lane] : -INFINITY;
+            lo = warp_min(lo); hi = warp_max(hi);
+            if (lane == 0) { s_lo[d] = lo; s_hi[d] = hi; }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        float bsss = 0.0f;
+        for (int d = 0; d < a.PD; ++d) {
+            const float ns = __fsub_rn(s_hi[d], s_lo[d]);
+            a.t.ns[d][node] = ns;
+            a.t.nc[d][node] = __fmul_rn(0.5f, __fadd_rn(s_hi[d], s_lo[d]));
+            bsss = __double2float_rn(__dadd_rn((double)bsss, __dmul_rn((double)ns, (double)ns)));   // std::pow(float,int) is double :638
+        }
+        a.t.nr[node] = __fmul_rn(0.5f, __fsqrt_rn(bsss));
+    }
+    if (n <= a.block) return;                                                            // :644 leaf
+
+    // longest axis :652-659 (first strict maximum)
+    int axis = 0; float axsz = -1.0f;
+    for (int d = 0; d < a.PD; ++d) { const float ns = __fsub_rn(s_hi[d], s_lo[d]); if (ns > axsz) { axsz = ns; axis = d; } }
+    const uint32_t nless = pf + a.block * (1u << log_2((n - 1) / a.block));              // :663
+    float* key = a.x[axis];
+    uint32_t* lidx = a.lidx;
+    uint32_t* scr = a.scr;
+
+    for (uint32_t i = pf + tid; i < pl; i += T) lidx[i] = i;                             // :516
+    __syncthreads();
+
+    // partial select :519-586
+    const float ideal = __fdiv_rn(__uint2float_rn(nless - pf), __uint2float_rn(pl - pf));     // :522
+    const SelStats st = cta_select(key, lidx, scr, pf, pl, nless, pf, pl - 1, s_lo[axis], s_hi[axis], ideal, 0, a.pivot_mode);
+    const uint32_t n_pass = st.n_pass, n_stall = st.n_stall; const unsigned long long n_scan = st.n_scan;
     if (tid == 0) {
         a.axis_of[node] = (uint8_t)axis; a.pmid[node] = nless;
         a.t.ioffset[2 * node] = pf;        a.t.num[2 * node] = nless - pf;               // :702-704

@@ -22,8 +22,9 @@
 constexpr int BIG_T = 256;                 // threads per chunk CTA
 constexpr int BIG_ROUNDS = 8;              // 8 warps x 8 rounds x 32 lanes
 constexpr uint32_t BIG_CH = BIG_T * BIG_ROUNDS;   // 2048 particles per chunk
+constexpr uint32_t BIG_LOCAL = 4096;       // a window this small is finished by ONE CTA with block barriers only (cta_select)
 
-struct BigWin { uint32_t wf, wl; float lo, hi, pivot; int done, iters, pad; };
+struct BigWin { uint32_t wf, wl; float lo, hi, pivot; int done, iters, local; };   // local: finish in one CTA (big_local_finish)
 struct BigNode {
     uint32_t node, pf, pl, nless, chunk0, nchunks; int axis; float ideal;
     BigWin w[2];
@@ -166,7 +167,7 @@ __device__ __forceinline__ void big_setup(const BigArgs& a, const uint32_t bi) {
     b.axis = axis;
     b.nless = b.pf + a.block * (1u << (31 - __clz((n - 1) / a.block)));
     b.ideal = __fdiv_rn(__uint2float_rn(b.nless - b.pf), __uint2float_rn(n));
-    BigWin w; w.wf = b.pf; w.wl = b.pl - 1; w.lo = lo[axis]; w.hi = hi[axis]; w.done = 0; w.iters = 0; w.pad = 0;
+    BigWin w; w.wf = b.pf; w.wl = b.pl - 1; w.lo = lo[axis]; w.hi = hi[axis]; w.done = 0; w.iters = 0; w.local = 0;
     w.pivot = select_pivot(b.nless, w.wf, w.wl, w.lo, w.hi, b.ideal, a.pivot_mode);
     b.w[0] = w; b.w[1] = w;
 }
@@ -308,7 +309,12 @@ __device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const u
             else {
                 nw.iters = w.iters + 1;
                 if (!(nw.wl > nw.wf) || nw.iters >= 100) nw.done = 1;                      // loop condition :527
-                else nw.pivot = select_pivot(b.nless, nw.wf, nw.wl, nw.lo, nw.hi, b.ideal, a.pivot_mode);
+                else {
+                    nw.pivot = select_pivot(b.nless, nw.wf, nw.wl, nw.lo, nw.hi, b.ideal, a.pivot_mode);
+                    // the remaining passes of a small window cost three grid-wide barriers each for a few microseconds of
+                    // work: hand the node to one CTA instead (first chunk of the window, next count phase)
+                    if (nw.wl - nw.wf + 1u <= BIG_LOCAL) nw.local = 1;
+                }
             }
         }
         b.w[(it + 1) & 1] = nw;
@@ -317,7 +323,7 @@ __device__ __forceinline__ void big_scan(const BigArgs& a, const int it, const u
         // the chunks the next pass has to visit
         s_carry[0] = 0; s_carry[1] = 0;
         if (!nw.done) {
-            const uint32_t q0 = (nw.wf - b.pf) / BIG_CH, q1 = (nw.wl - b.pf) / BIG_CH;
+            const uint32_t q0 = (nw.wf - b.pf) / BIG_CH, q1 = nw.local ? q0 : (nw.wl - b.pf) / BIG_CH;
             s_carry[0] = q1 - q0 + 1; b.expect = q1 - q0 + 1;
             s_carry[1] = atomicAdd(&a.nbig[4 + ((it + 1) & 1)], q1 - q0 + 1);
             s_wa[0] = b.chunk0 + q0;
@@ -380,6 +386,21 @@ __device__ __forceinline__ void big_swap(const BigArgs& a, const BigCache& b, co
     }
 }
 
+// all remaining passes of a node whose window has become small, by this CTA alone (same passes, pivots and exit rules:
+// cta_select is the loop k_node_split runs). Publishes the node as done in both window slots.
+__device__ __forceinline__ void big_local_finish(const BigArgs& a, const int it, const uint32_t bi) {     // one CTA
+    BigNode& b = a.nodes[bi];
+    const BigWin w = b.w[it & 1];
+    const SelStats st = cta_select(a.x[b.axis], a.lidx, a.scr, b.pf, b.pl, b.nless, w.wf, w.wl, w.lo, w.hi, b.ideal, w.iters, a.pivot_mode);
+    if (threadIdx.x == 0) {
+        b.npass += st.n_pass; b.nstall += st.n_stall; b.nscan += st.n_scan;
+        BigWin d = w; d.done = 1;
+        b.w[0] = d; b.w[1] = d;
+        atomicSub(&a.nbig[2], 1u);
+    }
+    __syncthreads();
+}
+
 // one phase (0 count+scan, 1 compact, 2 swap) of one pass over this CTA's CONTIGUOUS share of the worklist
 constexpr uint32_t BIG_PRE = 64;
 template <int PHASE>
@@ -410,7 +431,8 @@ __device__ __forceinline__ void big_phase(const BigArgs& a, const int it, const 
                 __syncthreads();
                 cur = bi;
             }
-            if (PHASE == 0) big_count(a, s_node, chunk, s_acc);
+            if (PHASE == 0 && s_node.w.local) big_local_finish(a, it, bi);        // (its single worklist entry; phases 1 and 2 then see done)
+            else if (PHASE == 0) big_count(a, s_node, chunk, s_acc);
             else if (PHASE == 1) big_compact(a, s_node, chunk);
             else big_swap(a, s_node, chunk);
             __syncthreads();
