@@ -198,7 +198,7 @@ struct WorkList {
     uint32_t* entries = nullptr;
     uint64_t nentries = 0;
 };
-int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tgt_which_box, bool accumulate);
+int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tgt_which_box, bool accumulate, uint32_t nsplit = 1);
 void onb_free_worklist(onb_context* c, WorkList& wl);
 // traverse.cu
 int onb_lists_boxwise(onb_context* c, float theta, WorkList& wl);

@@ -111,7 +111,8 @@ struct P2PArgs {
     const uint32_t* s_ioffset; const uint32_t* s_num;
     const uint32_t* item_node; const uint32_t* start; const uint32_t* entries;
     const uint32_t* s_epnum;        // legacy equivalents: per source node count (null = num_eqps everywhere)
-    uint32_t block, ebs, num_eqps, node_base, nentries;
+    float* partial;                 // nsplit > 1: [item][segment][OD][128] partial sums, reduced in segment order by k_p2p_reduce
+    uint32_t block, ebs, num_eqps, node_base, nentries, nsplit;
 };
 
 __device__ __forceinline__ TileRef decode_entry(const P2PArgs& a, uint32_t entry) {
@@ -134,9 +135,16 @@ __global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__
     static_assert(!PK || (TPT % 2 == 0 && !STRICT), "packed arithmetic needs an even TPT and the fast mode");
     __shared__ TileSmem<PHYS> sm;
     const int tid = threadIdx.x;
-    const uint32_t w = blockIdx.x;
-    const uint32_t e0 = min(a.start[w], a.nentries), e1 = min(a.start[w + 1], a.nentries);   // never read past the allocated list
+    // nsplit > 1 (under-filled launches of the upper dual-tree levels, fast arithmetic only): the item's list is cut into
+    // nsplit contiguous segments, one CTA each, partial sums go to a[].partial and are added in segment order afterwards
+    const uint32_t w = blockIdx.x / a.nsplit, seg = blockIdx.x - w * a.nsplit;
+    uint32_t e0 = min(a.start[w], a.nentries), e1 = min(a.start[w + 1], a.nentries);   // never read past the allocated list
     if (e0 >= e1) return;
+    if (a.nsplit > 1) {
+        const uint32_t len = e1 - e0;
+        const uint32_t s0 = e0 + (uint32_t)((unsigned long long)len * seg / a.nsplit), s1 = e0 + (uint32_t)((unsigned long long)len * (seg + 1u) / a.nsplit);
+        e0 = s0; e1 = s1;
+    }
     const uint32_t T = a.item_node ? a.item_node[w] : a.node_base + w;
     const uint32_t tn = a.t_num[T];
     const bool leaf = tn <= a.block;
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__
         tg[q].r2 = 0.f;
         if (Phys<PHYS>::TR) { const float r = leaf ? a.tr[ti] : a.br[ti]; tg[q].r2 = __fmul_rn(r, r); }
         #pragma unroll
-        for (int d = 0; d < OD; ++d) acc[q][d] = valid ? (leaf ? a.tu[d][ti] : a.bu[d][ti]) : 0.f;
+        for (int d = 0; d < OD; ++d) acc[q][d] = (valid && a.nsplit == 1) ? (leaf ? a.tu[d][ti] : a.bu[d][ti]) : 0.f;
     }
     Tgt2 tg2[G];
     f2 acc2[G][OD];
@@ -173,8 +181,8 @@ __global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__
 
     if (tid == 0) { ptx::mbar_init(&sm.bar[0], 1); ptx::mbar_init(&sm.bar[1], 1); ptx::fence_mbar_init(); }
     __syncthreads();
-    TileRef cur = decode_entry(a, a.entries[e0]);
-    if (tid == 0) tile_issue<PHYS>(sm, 0, cur);
+    TileRef cur = decode_entry(a, a.entries[min(e0, a.nentries - 1u)]);
+    if (tid == 0 && e0 < e1) tile_issue<PHYS>(sm, 0, cur);
     for (uint32_t e = e0; e < e1; ++e) {
         const int buf = (e - e0) & 1;
         const uint32_t par = ((e - e0) >> 1) & 1;
@@ -218,9 +226,35 @@ __global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__
         const uint32_t slot = (uint32_t)tid + (uint32_t)q * NT;
         if (slot < tcnt) {
             const uint32_t ti = toff + slot;
-            #pragma unroll
-            for (int d = 0; d < OD; ++d) { if (leaf) a.tu[d][ti] = acc[q][d]; else a.bu[d][ti] = acc[q][d]; }
+            if (a.nsplit == 1) {
+                #pragma unroll
+                for (int d = 0; d < OD; ++d) { if (leaf) a.tu[d][ti] = acc[q][d]; else a.bu[d][ti] = acc[q][d]; }
+            } else {
+                float* __restrict__ part = a.partial + ((size_t)blockIdx.x * OD) * 128u;
+                #pragma unroll
+                for (int d = 0; d < OD; ++d) part[d * 128 + slot] = acc[q][d];
+            }
         }
+    }
+}
+
+// nsplit > 1: acc(target) = ((stored + partial_0) + partial_1) + ... in segment order (deterministic for a given nsplit)
+template <int OD>
+__global__ void __launch_bounds__(128) k_p2p_reduce(const __grid_constant__ P2PArgs a) {
+    const uint32_t w = blockIdx.x, slot = threadIdx.x;
+    const uint32_t e0 = min(a.start[w], a.nentries), e1 = min(a.start[w + 1], a.nentries);
+    if (e0 >= e1) return;
+    const uint32_t T = a.item_node ? a.item_node[w] : a.node_base + w;
+    const uint32_t tn = a.t_num[T];
+    const bool leaf = tn <= a.block;
+    const uint32_t toff = leaf ? a.t_ioffset[T] : T * a.ebs, tcnt = leaf ? tn : a.num_eqps;
+    if (slot >= tcnt) return;
+    const uint32_t ti = toff + slot;
+    #pragma unroll
+    for (int d = 0; d < OD; ++d) {
+        float v = leaf ? a.tu[d][ti] : a.bu[d][ti];
+        for (uint32_t k = 0; k < a.nsplit; ++k) v += a.partial[(((size_t)w * a.nsplit + k) * OD + d) * 128u + slot];
+        if (leaf) a.tu[d][ti] = v; else a.bu[d][ti] = v;
     }
 }
 
@@ -309,9 +343,11 @@ int g_p2p_tpt = 0;     // 0 = per-physics default; 1, 2 or 4 forces the register
 
 template <int PHYS, int TPT>
 void launch_lists_t(onb_context* c, const P2PArgs& a, uint32_t nitems, bool packed) {
-    if (c->arith == ONB_ARITH_STRICT) k_p2p_lists<PHYS, true, TPT, false><<<nitems, 128 / TPT, 0, c->stream>>>(a);
-    else if (packed && TPT > 1)       k_p2p_lists<PHYS, false, TPT, (TPT > 1)><<<nitems, 128 / TPT, 0, c->stream>>>(a);
-    else                              k_p2p_lists<PHYS, false, TPT, false><<<nitems, 128 / TPT, 0, c->stream>>>(a);
+    const uint32_t grid = nitems * a.nsplit;
+    if (c->arith == ONB_ARITH_STRICT) k_p2p_lists<PHYS, true, TPT, false><<<grid, 128 / TPT, 0, c->stream>>>(a);
+    else if (packed && TPT > 1)       k_p2p_lists<PHYS, false, TPT, (TPT > 1)><<<grid, 128 / TPT, 0, c->stream>>>(a);
+    else                              k_p2p_lists<PHYS, false, TPT, false><<<grid, 128 / TPT, 0, c->stream>>>(a);
+    if (a.nsplit > 1) { k_p2p_reduce<Phys<PHYS>::OD><<<nitems, 128, 0, c->stream>>>(a); ONB_LAUNCH(c); }
 }
 template <int PHYS>
 void launch_lists(onb_context* c, const P2PArgs& a, uint32_t nitems) {
@@ -327,7 +363,8 @@ void launch_lists(onb_context* c, const P2PArgs& a, uint32_t nitems) {
             if (const char* e = std::getenv("ONB_TPT1_MAX")) t1 = (uint32_t)std::max(1, atoi(e));
             if (const char* e = std::getenv("ONB_TPT2_MAX")) t2 = (uint32_t)std::max(1, atoi(e));
         }
-        if (nitems <= t1) tpt = 1; else if (nitems <= t2 && tpt > 2) tpt = 2;
+        const uint32_t ncta = nitems * a.nsplit;
+        if (ncta <= t1) tpt = 1; else if (ncta <= t2 && tpt > 2) tpt = 2;
     }
     if (tpt == 1) launch_lists_t<PHYS, 1>(c, a, nitems, packed);
     else if (tpt == 2) launch_lists_t<PHYS, 2>(c, a, nitems, packed);
@@ -364,9 +401,10 @@ int onb_pack_sources(onb_context* c, DParts& p) {
     return ONB_OK;
 }
 
-int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tgt_which_box, bool accumulate) {
+int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tgt_which_box, bool accumulate, uint32_t nsplit) {
     (void)accumulate;   // the kernel always starts from the stored value, i.e. "+=" like ppinter
     if (wl.nitems == 0) return ONB_OK;
+    if (nsplit < 1 || c->arith == ONB_ARITH_STRICT) nsplit = 1;     // the strict mode keeps the reference's summation order
     DParts& srcs = c->parts[0]; DParts& eqs = c->parts[2];
     DParts& tl = c->parts[tgt_which_leaf]; DParts& tb = c->parts[tgt_which_box];
     if (!srcs.packed_valid) { int rc = onb_pack_sources(c, srcs); if (rc) return rc; }
@@ -382,6 +420,8 @@ int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tg
     a.item_node = wl.tgt_node; a.start = wl.start; a.entries = wl.entries;
     a.block = c->block; a.ebs = c->ebs; a.num_eqps = c->num_eqps; a.node_base = wl.node_base; a.nentries = (uint32_t)wl.nentries;
     a.s_epnum = c->legacy ? c->d_epnum : nullptr;
+    a.nsplit = nsplit; a.partial = nullptr;
+    if (nsplit > 1) ONB_CUDA(onb_dmalloc(c, (void**)&a.partial, (size_t)wl.nitems * nsplit * c->OD * 128u * sizeof(float)));
     switch (c->physics) {
         case ONB_GRAV3D:     launch_lists<ONB_GRAV3D>(c, a, wl.nitems); break;
         case ONB_VORT3D:     launch_lists<ONB_VORT3D>(c, a, wl.nitems); break;

@@ -22,6 +22,7 @@
  */
 #include "onb_internal.h"
 #include <cstdlib>
+#include <algorithm>
 #include <cstdio>
 
 namespace {
@@ -341,7 +342,17 @@ static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cach
         cudaEventRecord(ev[4 * lev + 2], c->stream);
         // then this level's interactions, in list order, on top of the interpolated values (:315-402)
         WorkList wl; wl.nitems = nn; wl.tgt_node = nullptr; wl.node_base = nn; wl.start = istart; wl.entries = ientries; wl.nentries = itotal;
-        if (itotal > 0) if ((rc = onb_p2p_lists(c, wl, 1, 3, true))) break;
+        // Upper levels have too few target nodes to fill the machine with one warp per node. Cutting every list into nsplit
+        // segments (ONB_P2P_SPLIT_TARGET=<CTAs per launch to aim for>) makes the pair kernel 4 % faster at N = 1e7 (79.5 ->
+        // 76.1 ms), but it is OFF by default: adding the far-field partial sums in another order than the reference moves
+        // the result 2.1e-6 (relative rms) away from the reference treecode - the noise of its own float summation -
+        // where the same order stays within 4.4e-7, and the contract is 1e-6. nsplit depends on the LEVEL only (not on
+        // this rank's share of it), so a multi-GPU run would still add in exactly the order of the single-GPU run.
+        uint32_t nsplit = 1;
+        { static int target = -1;
+          if (target < 0) { target = 0; if (const char* e = std::getenv("ONB_P2P_SPLIT_TARGET")) target = std::max(0, atoi(e)); }
+          while (nsplit < 16u && (unsigned long long)nn * nsplit < (unsigned long long)target) nsplit <<= 1; }
+        if (itotal > 0) if ((rc = onb_p2p_lists(c, wl, 1, 3, true, nsplit))) break;
         cudaEventRecord(ev[4 * lev + 3], c->stream);
         pc_start = cstart; pc_entries = centries;
     }
