@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(128) k_refine(const RefineArgs a) {
     __shared__ int perm[128];
     __shared__ int segtie[128];
     __shared__ float keys[128];
+    __shared__ float s_wb[4][6];
     const bool act = tid < n;
     if (act) { for (int d = 0; d < a.PD; ++d) sx[d][tid] = a.p.x[d][pf + tid]; perm[tid] = tid; }
     int sa = 0, sb = n;             // my segment [sa, sb)
@@ -390,13 +391,48 @@ __global__ void __launch_bounds__(128) k_refine(const RefineArgs a) {
         if (!__syncthreads_or(work ? 1 : 0)) break;
         int axis = 0; int rank = 0; bool tie = false;
         if (act) segtie[tid] = 0;
-        if (work) {
-            float bs[3];
+        float bs[3] = {0.f, 0.f, 0.f};
+        if (n == 128) {
+            // a full leaf (all but the last one): every segment of this recursion level is an aligned block of w = sb - sa
+            // threads, so the boxes come from warp reductions / xor shuffles instead of one loop over the segment per thread
+            const int w = sb - sa, lane = tid & 31, warp = tid >> 5;
+            if (w >= 3) {
+                float lo[3], hi[3];
+                #pragma unroll
+                for (int d = 0; d < 3; ++d) { const float v = d < a.PD ? sx[d][tid] : 0.f; lo[d] = v; hi[d] = v; }
+                if (w >= 32) {
+                    #pragma unroll
+                    for (int d = 0; d < 3; ++d) { lo[d] = warp_min(lo[d]); hi[d] = warp_max(hi[d]); }
+                    if (w > 32) {
+                        if (lane == 0) {
+                            #pragma unroll
+                            for (int d = 0; d < 3; ++d) { s_wb[warp][d] = lo[d]; s_wb[warp][3 + d] = hi[d]; }
+                        }
+                        __syncthreads();
+                        const int w0 = sa >> 5, nw = w >> 5;
+                        #pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            lo[d] = s_wb[w0][d]; hi[d] = s_wb[w0][3 + d];
+                            for (int q = 1; q < nw; ++q) { lo[d] = fminf(lo[d], s_wb[w0 + q][d]); hi[d] = fmaxf(hi[d], s_wb[w0 + q][3 + d]); }
+                        }
+                    }
+                } else {
+                    for (int o = w >> 1; o; o >>= 1) {
+                        #pragma unroll
+                        for (int d = 0; d < 3; ++d) { lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o)); hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o)); }
+                    }
+                }
+                #pragma unroll
+                for (int d = 0; d < 3; ++d) bs[d] = __fsub_rn(hi[d], lo[d]);
+            }
+        } else if (work) {
             for (int d = 0; d < a.PD; ++d) {
                 float lo = sx[d][sa], hi = lo;
                 for (int j = sa; j < sb; ++j) { const float v = sx[d][j]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
                 bs[d] = __fsub_rn(hi, lo);
             }
+        }
+        if (work) {
             for (int d = 1; d < a.PD; ++d) if (bs[axis] < bs[d]) axis = d;                // std::max_element :878
             const float key = sx[axis][tid];
             for (int j = sa; j < sb; ++j) { const float v = sx[axis][j]; rank += (v < key); tie |= (v == key && j != tid); }
