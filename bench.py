@@ -381,9 +381,9 @@ def run_ours(args):
         "roofline": {"kernel": "k_p2p_lists<grav3d,fast>", "bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved_tf / peak_tf) if peak_tf else None,
                      # DRAM bytes per launch of the packed pair kernel at this workload, from the ncu launch list of the same
-                     # step (profiles/r1_launch_list_summary_v2.txt: 1673.8 MB read + 179.1 MB written over 5 launches)
-                     "traffic": 370.6e6 if (N == 10000000 and world == 1) else None,
-                     "traffic_source": "profiles/r1_launch_list_summary_v2.txt (dram__bytes_read.sum + dram__bytes_write.sum, k_p2p_lists<grav3d,fast,TPT=4,packed>, per launch)" if (N == 10000000 and world == 1) else None,
+                     # step (profiles/r1_launch_list_summary_v3.txt: 1672.3 MB read + 180.3 MB written over 5 launches)
+                     "traffic": 370.5e6 if (N == 10000000 and world == 1) else None,
+                     "traffic_source": "profiles/r1_launch_list_summary_v3.txt (dram__bytes_read.sum + dram__bytes_write.sum, k_p2p_lists<grav3d,fast,TPT=4,packed>, per launch)" if (N == 10000000 and world == 1) else None,
                      "peak_source": "FP32 FMA issue microbenchmark run in this process (onb_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 SIMT figure",
                      "flop_per_pair": FLOP_PER_PAIR,
                      "fp32_issue_util": (pairs_local * FP32_SLOTS_PER_PAIR * 2 / (p2p_ms * 1e-3) * 1e-12 / peak_tf) if (peak_tf and p2p_ms > 0) else None,

@@ -7,4 +7,5 @@ $TR --master-port 29523 tools/bench_physics.py vort3d dualtree 10000000 1.4 2>gp
 for f in gpurun_out/bench8_grav3d_1e7_v2.json gpurun_out/bench8_grav3d_1e8_v2.json; do python -c "
 import json,sys
 d=json.load(open('$f')); print(d['n_gpus'], d['config']['n_particles'], 'ms/step', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['ms_per_step'],2), {k: round(v,2) for k,v in d['phases_ms'].items()}, d['ms_steps'], d['e2e_ms_steps'])"; done
-cat gpurun_out/bench8_vort3d_dtt_v2.json; tail -3 gpurun_out/b8_*.err
+cat gpurun_out/bench8_vort3d_dtt_v2.json
+$TR --master-port 29524 tools/check_multi.py 1000000 2>/dev/null | grep -c "True"; $TR --master-port 29525 tools/check_multi.py 1000000 2>/dev/null | grep CHECK_MULTI
