@@ -6,7 +6,13 @@ import torch
 import torch.distributed as dist
 
 
-_UNEVEN = {"ok": True}
+import os
+# Two ways to replicate unequal, leaf-aligned ranges (both bit-identical, tools/check_multi.py):
+#   uneven : every rank's range straight into place (torch issues one grouped ncclBroadcast per rank, no staging buffer)
+#   padded : one ncclAllGather of equal padded chunks + unpack copies
+# Measured on B200s at N=1e7 (5 source planes): 2 GPUs uneven 1.34 ms / padded 1.59 ms; 8 GPUs uneven 2.8 ms / padded 2.2 ms.
+# ONB_ALLGATHER=auto (default: uneven up to 2 ranks, padded above) | uneven | padded
+_UNEVEN = {"ok": True, "mode": os.environ.get("ONB_ALLGATHER", "auto")}
 
 
 def shard_ranges(session, n, world):
@@ -19,7 +25,8 @@ def allgather_ranges(plane, ranges, rank, world, scratch=None, group=None):
     Works on CUDA tensors over NCCL and on CPU tensors over gloo (tests)."""
     if world == 1:
         return scratch
-    if dist.get_backend(group) != "gloo" and _UNEVEN["ok"]:
+    want_uneven = _UNEVEN["mode"] == "uneven" or (_UNEVEN["mode"] == "auto" and world <= 2)
+    if dist.get_backend(group) != "gloo" and _UNEVEN["ok"] and want_uneven:
         # NCCL: every rank's range goes straight to its final place on every other rank (torch issues one grouped
         # ncclBroadcast per rank for unequal sizes) - no padding, no staging buffer, no unpack copies
         lo, hi = ranges[rank]

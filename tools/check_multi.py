@@ -32,5 +32,5 @@ if True:
     print("rank %d equivalent strengths identical: %s" % (rank, same), flush=True)
 t = torch.tensor([1.0 if ok else 0.0], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("CHECK_MULTI", "PASS" if t.item() == 1.0 else "FAIL", "world", world, "uneven all-gather path:", multigpu._UNEVEN["ok"], flush=True)
+    print("CHECK_MULTI", "PASS" if t.item() == 1.0 else "FAIL", "world", world, "all-gather mode:", multigpu._UNEVEN["mode"], flush=True)
 dist.destroy_process_group()
