@@ -64,9 +64,14 @@ __device__ __forceinline__ SelStats cta_select(float* key, uint32_t* lidx, uint3
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
     __shared__ uint32_t s_cnt[32], s_cnt2[32];
     __shared__ float s_max[32], s_min[32];
+    __shared__ float s_piv;
     uint32_t n_pass = 0, n_stall = 0; unsigned long long n_scan = 0;
-    while (wl > wf && iters < 100) {
-        const float pivot = select_pivot(nless, wf, wl, lo, hi, ideal, pivot_mode);                  // :538-540
+    // the pivot (:538-540: double arithmetic, software division) is evaluated by warp 0 alone and published across a barrier
+    bool go = wl > wf && iters < 100;
+    if (warp == 0 && go) { const float pv = select_pivot(nless, wf, wl, lo, hi, ideal, pivot_mode); if (lane == 0) s_piv = pv; }
+    __syncthreads();
+    float pivot = go ? s_piv : 0.f;
+    while (go) {
         // pass 1: m = #{v < pivot}, and the min/max the two possible next windows will have
         uint32_t cnt = 0; float mx_lt = -INFINITY, mn_ge = INFINITY;
         for (uint32_t i = wf + tid; i <= wl; i += T) {
@@ -124,14 +129,18 @@ __device__ __forceinline__ SelStats cta_select(float* key, uint32_t* lidx, uint3
             const float va = key[pa], vb = key[pb]; key[pa] = vb; key[pb] = va;
             const uint32_t ia = lidx[pa], ib = lidx[pb]; lidx[pa] = ib; lidx[pb] = ia;
         }
-        __syncthreads();
         ++n_pass; n_scan += (wl - wf + 1);
-        // :565-583
-        if (B == nless) break;
-        const uint32_t owf = wf, owl = wl;
-        if (B < nless) { wf = B; lo = mn_ge; } else { wl = B - 1; hi = mx_lt; }
-        if (wf == owf && wl == owl) { ++n_stall; break; }
-        ++iters;
+        // :565-583 - the next window follows from B and the two extrema, all known since the count
+        if (B == nless) go = false;
+        else {
+            const uint32_t owf = wf, owl = wl;
+            if (B < nless) { wf = B; lo = mn_ge; } else { wl = B - 1; hi = mx_lt; }
+            if (wf == owf && wl == owl) { ++n_stall; go = false; }
+            else { ++iters; go = wl > wf && iters < 100; }                                        // loop condition :527
+        }
+        if (go && warp == 0) { const float pv = select_pivot(nless, wf, wl, lo, hi, ideal, pivot_mode); if (lane == 0) s_piv = pv; }
+        __syncthreads();                             // swaps done; next pivot published
+        if (go) pivot = s_piv;
     }
     SelStats st; st.n_pass = n_pass; st.n_stall = n_stall; st.n_scan = n_scan;
     return st;

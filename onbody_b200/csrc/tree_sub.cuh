@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(SUB_T, 8192 / SUB_MAX) k_subtree(const SubArgs
     __shared__ uint16_t s_pf[2][SUB_TAB], s_n[2][SUB_TAB];
     __shared__ float s_box[32][6];
     __shared__ uint32_t s_cnt[32], s_cnt2[32];
-    __shared__ float s_mx[32], s_mn[32];
+    __shared__ float s_mx[32], s_mn[32], s_piv[32];
     __shared__ unsigned long long s_stats[4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -164,8 +164,17 @@ __global__ void __launch_bounds__(SUB_T, 8192 / SUB_MAX) k_subtree(const SubArgs
             const float ideal = __fdiv_rn(__uint2float_rn(nless - pf), __uint2float_rn(pl - pf));     // :522
             int iters = 0;
             uint32_t n_pass = 0, n_stall = 0, n_scan = 0;
-            while (wl > wf && iters < 100) {
-                const float pivot = select_pivot(nless, wf, wl, wlo, whi, ideal, a.pivot_mode);  // :538-540 (index differences only)
+            // The pivot (:538-540, double arithmetic with a software division; index differences only) is evaluated by the
+            // group's first warp alone and published through shared memory across a barrier the pass needs anyway: the
+            // kernel is issue-bound and every warp repeating those ~200 instructions per pass was a quarter of its work.
+            bool go = wl > wf;
+            float pivot = 0.f;
+            if (g.W > 1) {
+                if (wig == 0 && go) { const float pv = select_pivot(nless, wf, wl, wlo, whi, ideal, a.pivot_mode); if (lane == 0) s_piv[g.w0] = pv; }
+                sub_sync<SUB_T>(g);
+                if (go) pivot = s_piv[g.w0];
+            } else if (go) pivot = select_pivot(nless, wf, wl, wlo, whi, ideal, a.pivot_mode);
+            while (go) {
                 // pass 1: m = #{v < pivot}, and the min/max the two possible next windows will have
                 uint32_t cnt = 0; float mx_lt = -INFINITY, mn_ge = INFINITY;
                 for (uint32_t i = wf + g.tig; i <= wl; i += g.T) {
@@ -189,15 +198,19 @@ __global__ void __launch_bounds__(SUB_T, 8192 / SUB_MAX) k_subtree(const SubArgs
                 for (uint32_t base = wf; base <= wl; base += chunk) {
                     uint32_t ba[SUB_ROUNDS], bb[SUB_ROUNDS];
                     uint32_t totA = 0, totB = 0;
+                    const bool warp_in = base + (uint32_t)wig * 32u * SUB_ROUNDS <= wl;       // (warp-uniform) anything of the window here?
                     #pragma unroll
                     for (int r = 0; r < SUB_ROUNDS; ++r) {
-                        const uint32_t i = base + (uint32_t)wig * 32u * SUB_ROUNDS + (uint32_t)r * 32u + lane;
-                        const bool valid = i <= wl;
-                        const float v = valid ? key[i] : 0.f;
-                        const bool lt = v < pivot;
-                        ba[r] = __ballot_sync(0xffffffffu, valid && i < B && !lt);
-                        bb[r] = __ballot_sync(0xffffffffu, valid && i >= B && lt);
-                        totA += __popc(ba[r]); totB += __popc(bb[r]);
+                        ba[r] = 0u; bb[r] = 0u;
+                        if (warp_in) {
+                            const uint32_t i = base + (uint32_t)wig * 32u * SUB_ROUNDS + (uint32_t)r * 32u + lane;
+                            const bool valid = i <= wl;
+                            const float v = valid ? key[i] : 0.f;
+                            const bool lt = v < pivot;
+                            ba[r] = __ballot_sync(0xffffffffu, valid && i < B && !lt);
+                            bb[r] = __ballot_sync(0xffffffffu, valid && i >= B && lt);
+                            totA += __popc(ba[r]); totB += __popc(bb[r]);
+                        }
                     }
                     uint32_t exA = 0, exB = 0, allA = totA, allB = totB;
                     if (g.W > 1) {
@@ -227,14 +240,18 @@ __global__ void __launch_bounds__(SUB_T, 8192 / SUB_MAX) k_subtree(const SubArgs
                     for (int d = 0; d < 3; ++d) if (d < PD) { const float va = sx[d][pa], vb = sx[d][pb]; sx[d][pa] = vb; sx[d][pb] = va; }
                     const uint16_t ia = sperm[pa], ib = sperm[pb]; sperm[pa] = ib; sperm[pb] = ia;
                 }
-                sub_sync<SUB_T>(g);
                 ++n_pass; n_scan += (wl - wf + 1);
-                // :565-583
-                if (B == nless) break;
-                const uint32_t owf = wf, owl = wl;
-                if (B < nless) { wf = B; wlo = mn_ge; } else { wl = B - 1; whi = mx_lt; }
-                if (wf == owf && wl == owl) { ++n_stall; break; }
-                ++iters;
+                // :565-583 - the next window follows from B and the two extrema, all known since the count
+                if (B == nless) go = false;
+                else {
+                    const uint32_t owf = wf, owl = wl;
+                    if (B < nless) { wf = B; wlo = mn_ge; } else { wl = B - 1; whi = mx_lt; }
+                    if (wf == owf && wl == owl) { ++n_stall; go = false; }
+                    else { ++iters; go = wl > wf && iters < 100; }                                // loop condition :527
+                }
+                if (go && g.W > 1 && wig == 0) { const float pv = select_pivot(nless, wf, wl, wlo, whi, ideal, a.pivot_mode); if (lane == 0) s_piv[g.w0] = pv; }
+                sub_sync<SUB_T>(g);                      // swaps done; next pivot published
+                if (go) pivot = g.W > 1 ? s_piv[g.w0] : select_pivot(nless, wf, wl, wlo, whi, ideal, a.pivot_mode);
             }
             if (g.tig == 0) {
                 a.t.ioffset[2 * node] = pf0 + pf;        a.t.num[2 * node] = nless - pf;           // :702-704
