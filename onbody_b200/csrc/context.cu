@@ -103,6 +103,7 @@ int onb_join_copies(onb_context* c) {
     return ONB_OK;
 }
 void onb_scratch_reset(onb_context* c) {
+    c->cur_stream = nullptr;          // (an error return may have left a phase's secondary stream selected)
     onb_join_copies(c);
     if (c->slabs.size() > 1) {          // coalesce what the last call needed into one slab
         cudaStreamSynchronize(c->stream);

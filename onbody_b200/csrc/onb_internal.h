@@ -125,6 +125,10 @@ int onb_join_copies(onb_context* c);   // make the context stream wait for a pen
     return ONB_ERR_CUDA; } } while (0)
 
 #define ONB_LAUNCH(c) ((c)->launches++)
+// the stream / statistics slot of the work being enqueued: onb_make_trees enqueues two builds on two streams, the dual
+// tree builds its interaction lists on the second stream ahead of the pair kernels
+#define ONB_ST(c) ((c)->cur_stream ? (c)->cur_stream : (c)->stream)
+#define ONB_STATS(c) ((c)->d_build_stats + (c)->cur_stats_off)
 
 // scratch (per-call) device memory: bump allocation from the context's arena; "free" is a no-op, the arena is reset by
 // onb_scratch_reset() at the start of every public phase call. Persistent arrays use onb_pmalloc / onb_pfree.

@@ -42,23 +42,23 @@ int onb_exclusive_scan_u32(onb_context* c, const uint32_t* in, uint32_t* out, ui
     if (n == 0) { if (total) *total = 0; return ONB_OK; }
     unsigned long long* d_total = nullptr;
     uint32_t last_in = 0;
-    if (total) ONB_CUDA(cudaMemcpyAsync(&last_in, in + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    if (total) ONB_CUDA(cudaMemcpyAsync(&last_in, in + (n - 1), 4, cudaMemcpyDeviceToHost, ONB_ST(c)));
     (void)d_total;
     const uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t* sums = nullptr;
     if (ntiles > 1) ONB_CUDA(onb_dmalloc(c, (void**)&sums, (size_t)ntiles * 4));
-    k_scan_tiles<<<ntiles, SCAN_T, 0, c->stream>>>(in, out, sums, n); ONB_LAUNCH(c);
+    k_scan_tiles<<<ntiles, SCAN_T, 0, ONB_ST(c)>>>(in, out, sums, n); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
     if (ntiles > 1) {
         int rc = onb_exclusive_scan_u32(c, sums, sums, ntiles, nullptr);
         if (rc) { onb_dfree(c, sums); return rc; }
-        k_scan_add<<<(n + 255) / 256, 256, 0, c->stream>>>(out, sums, n); ONB_LAUNCH(c);
+        k_scan_add<<<(n + 255) / 256, 256, 0, ONB_ST(c)>>>(out, sums, n); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
     }
     if (total) {
         uint32_t last_out = 0;
-        ONB_CUDA(cudaMemcpyAsync(&last_out, out + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
-        ONB_CUDA(cudaStreamSynchronize(c->stream));
+        ONB_CUDA(cudaMemcpyAsync(&last_out, out + (n - 1), 4, cudaMemcpyDeviceToHost, ONB_ST(c)));
+        ONB_CUDA(cudaStreamSynchronize(ONB_ST(c)));
         *total = (uint64_t)last_out + (uint64_t)last_in;
     }
     (void)sums;      // arena scratch: released at the next phase

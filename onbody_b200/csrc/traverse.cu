@@ -297,12 +297,22 @@ static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cach
     if (want_prof) ONB_CUDA(onb_dmalloc(c, (void**)&d_lvl, (size_t)L * 8));
 
     uint32_t *pc_start = nullptr, *pc_entries = nullptr;     // previous level's deferred lists
-    std::vector<cudaEvent_t> ev((size_t)4 * L);
+    std::vector<cudaEvent_t> ev((size_t)4 * L), ev_d0((size_t)L);
     for (auto& e : ev) cudaEventCreate(&e);
+    for (auto& e : ev_d0) cudaEventCreate(&e);
+    static const bool no_ahead = std::getenv("ONB_DTT_ONE_STREAM") != nullptr;
+    const bool ahead = use_cache && !no_ahead;
+    if (ahead) {      // the list stream starts behind everything enqueued so far (statistics reset, earlier phases)
+        cudaEventRecord(ev_d0[0], c->stream);
+        ONB_CUDA(cudaStreamWaitEvent(c->stream2, ev_d0[0], 0));
+    }
     int rc = ONB_OK;
     for (int lev = 0; lev < L && rc == ONB_OK; ++lev) {
         const uint32_t nn = 1u << lev;
-        cudaEventRecord(ev[4 * lev + 0], c->stream);
+        // With cached list sizes nothing below needs the host: the traversal of level lev+1 depends only on the deferred
+        // lists of level lev, not on the pair kernels, so it is enqueued on the second stream and runs underneath them.
+        if (ahead) c->cur_stream = c->stream2;
+        cudaEventRecord(ev[4 * lev + 0], ONB_ST(c));
         uint32_t *istart = nullptr, *cstart = nullptr, *ientries = nullptr, *centries = nullptr;
         ONB_CUDA(onb_dmalloc(c, (void**)&istart, (size_t)(nn + 1) * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&cstart, (size_t)(nn + 1) * 4));
         DttArgs a; a.st = view_of(st); a.tt = view_of(tt); a.level = lev; a.nnodes = nn;
@@ -311,9 +321,9 @@ static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cach
         a.queue = queue; a.qcap = qcap; a.stats = d_stats; a.flag = c->d_flag;
         a.block = c->block; a.num_eqps = c->num_eqps; a.shard_lo = lo; a.shard_hi = hi; a.PD = c->PD; a.theta = theta;
         const uint32_t blocks = std::min<uint32_t>(max_blocks, (nn + WPB - 1) / WPB);
-        k_dtt<false><<<blocks, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
+        k_dtt<false><<<blocks, TB, 0, ONB_ST(c)>>>(a); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
-        ONB_CUDA(cudaMemsetAsync(istart + nn, 0, 4, c->stream)); ONB_CUDA(cudaMemsetAsync(cstart + nn, 0, 4, c->stream));
+        ONB_CUDA(cudaMemsetAsync(istart + nn, 0, 4, ONB_ST(c))); ONB_CUDA(cudaMemsetAsync(cstart + nn, 0, 4, ONB_ST(c)));
         uint64_t itotal = 0, ctotal = 0;
         if (use_cache) {
             if ((rc = onb_exclusive_scan_u32(c, istart, istart, nn + 1, nullptr))) break;
@@ -327,16 +337,17 @@ static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cach
             sizes[2 * lev] = itotal; sizes[2 * lev + 1] = ctotal;
         }
         // after the exclusive scan the appended last element holds the total
-        ONB_CUDA(cudaMemcpyAsync(d_totals + 2 * lev, istart + nn, 4, cudaMemcpyDeviceToDevice, c->stream));
-        ONB_CUDA(cudaMemcpyAsync(d_totals + 2 * lev + 1, cstart + nn, 4, cudaMemcpyDeviceToDevice, c->stream));
+        ONB_CUDA(cudaMemcpyAsync(d_totals + 2 * lev, istart + nn, 4, cudaMemcpyDeviceToDevice, ONB_ST(c)));
+        ONB_CUDA(cudaMemcpyAsync(d_totals + 2 * lev + 1, cstart + nn, 4, cudaMemcpyDeviceToDevice, ONB_ST(c)));
         ONB_CUDA(onb_dmalloc(c, (void**)&ientries, std::max<size_t>(4, (size_t)itotal * 4)));
         ONB_CUDA(onb_dmalloc(c, (void**)&centries, std::max<size_t>(4, (size_t)ctotal * 4)));
         a.ientries = ientries; a.centries = centries;
         a.icap = (uint32_t)itotal; a.ccap = (uint32_t)ctotal;
-        k_dtt<true><<<blocks, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
+        k_dtt<true><<<blocks, TB, 0, ONB_ST(c)>>>(a); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
-        if (d_lvl) ONB_CUDA(cudaMemcpyAsync(d_lvl + lev, d_stats + 9, 8, cudaMemcpyDeviceToDevice, c->stream));
-        cudaEventRecord(ev[4 * lev + 1], c->stream);
+        if (d_lvl) ONB_CUDA(cudaMemcpyAsync(d_lvl + lev, d_stats + 9, 8, cudaMemcpyDeviceToDevice, ONB_ST(c)));
+        cudaEventRecord(ev[4 * lev + 1], ONB_ST(c));
+        if (ahead) { c->cur_stream = nullptr; ONB_CUDA(cudaStreamWaitEvent(c->stream, ev[4 * lev + 1], 0)); cudaEventRecord(ev_d0[lev], c->stream); }
         // node entry: zero + interpolate from the parent (ongrav3d.cpp:232-304)
         if ((rc = onb_bary_downward_level(c, lev))) break;
         cudaEventRecord(ev[4 * lev + 2], c->stream);
@@ -356,6 +367,7 @@ static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cach
         cudaEventRecord(ev[4 * lev + 3], c->stream);
         pc_start = cstart; pc_entries = centries;
     }
+    c->cur_stream = nullptr;
     double ms_lists = 0.0, ms_p2p = 0.0, ms_down = 0.0;
     *cache_ok = true;
     if (rc == ONB_OK) {
@@ -371,7 +383,7 @@ static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cach
                 fprintf(stderr, "dtt level %2d: entries %10llu pairs %14llu p2p %8.3f ms -> %7.1f Gpairs/s\n", lev, (unsigned long long)sizes[2 * lev], pr, tp, tp > 0 ? pr / tp * 1e-6 : 0.0);
             }
             float t01 = 0, t12 = 0, t23 = 0;
-            cudaEventElapsedTime(&t01, ev[4 * lev], ev[4 * lev + 1]); cudaEventElapsedTime(&t12, ev[4 * lev + 1], ev[4 * lev + 2]); cudaEventElapsedTime(&t23, ev[4 * lev + 2], ev[4 * lev + 3]);
+            cudaEventElapsedTime(&t01, ev[4 * lev], ev[4 * lev + 1]); cudaEventElapsedTime(&t12, ahead ? ev_d0[lev] : ev[4 * lev + 1], ev[4 * lev + 2]); cudaEventElapsedTime(&t23, ev[4 * lev + 2], ev[4 * lev + 3]);
             ms_lists += t01; ms_down += t12; ms_p2p += t23;
             if (h_tot[2 * lev] != (uint32_t)sizes[2 * lev] || h_tot[2 * lev + 1] != (uint32_t)sizes[2 * lev + 1]) *cache_ok = false;
         }
@@ -379,6 +391,7 @@ static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cach
         if (!use_cache) { c->dtt_sizes = sizes; c->dtt_sizes_valid = true; }
     }
     for (auto& e : ev) cudaEventDestroy(e);
+    for (auto& e : ev_d0) cudaEventDestroy(e);
     if (rc == ONB_OK && *cache_ok) rc = fetch_stats(c, d_stats);
     c->phase_ms["lists"] = ms_lists; c->phase_ms["downward"] = ms_down; c->phase_ms["p2p"] = ms_p2p;
     return rc;

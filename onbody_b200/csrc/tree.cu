@@ -26,9 +26,6 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-// the stream / statistics slot of the build being enqueued (onb_make_trees enqueues two builds on two streams)
-#define ONB_ST(c) ((c)->cur_stream ? (c)->cur_stream : (c)->stream)
-#define ONB_STATS(c) ((c)->d_build_stats + (c)->cur_stats_off)
 
 namespace {
 
