@@ -1,4 +1,4 @@
-"""Phase-by-phase GPU-vs-oracle diagnostic (run on a B200: `python tests/gpu_diag.py [physics] [N] [theta]`).
+"""Phase-by-phase GPU-vs-oracle diagnostic (run on a B200: `python tools/gpu_diag.py [physics] [N] [theta]`).
 
 Not a pytest file: it prints, for every phase of the hot path, whether the CUDA result is bit-identical to the
 oracle's, and when a phase differs it re-runs the downstream phases from the ORACLE's state so that one GPU
