@@ -231,9 +231,8 @@ def run_ours(args):
         if world > 1:
             return hot_path_multi()
         g.make_trees(); phases["both_trees"] = phases.get("both_trees", 0.0) + g.phase_ms("tree")    # two streams, overlapped
-        g.upward(0); phases["upward"] = phases.get("upward", 0.0) + g.phase_ms("upward")
-        g.refine(1); phases["refine"] = phases.get("refine", 0.0) + g.phase_ms("refine")
-        g.upward(1); phases["tgt_equiv"] = phases.get("tgt_equiv", 0.0) + g.phase_ms("upward")
+        # source side (upward pass + packing) and target side (in-leaf refinement + equivalent points) on two streams
+        g.prepare_eval(); phases["upward_refine_tgt_equiv"] = phases.get("upward_refine_tgt_equiv", 0.0) + g.phase_ms("prepare")
         g.fastsumm(THETA)
         for k in ("eval", "lists", "p2p", "downward"):
             phases[k] = phases.get(k, 0.0) + g.phase_ms(k)

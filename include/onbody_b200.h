@@ -104,6 +104,12 @@ ONB_API int onb_finish_tree(onb_context* c, int which);
  * results are identical to two onb_make_tree[_range] calls */
 ONB_API int onb_make_trees(onb_context* c);
 ONB_API int onb_make_trees_range(onb_context* c, uint64_t src_lo, uint64_t src_hi, uint64_t tgt_lo, uint64_t tgt_hi);
+/* everything between the tree builds and onb_fastsumm in one call, source side and target side overlapped on two streams:
+ * [onb_finish_tree(0)] onb_upward(0)  |  [onb_finish_tree(1)] onb_refine(1) onb_upward(1)
+ * (ongrav3d.cpp:636-724 runs the two independent chains one after the other). finish != 0: the multi-GPU variant after the
+ * plane exchange, with the in-leaf refinement restricted to the target range [tgt_lo, tgt_hi). Results are identical to
+ * the separate calls. */
+ONB_API int onb_prepare_eval(onb_context* c, int finish, uint64_t tgt_lo, uint64_t tgt_hi);
 /* restrict the following onb_refine to the leaves of [lo,hi) again (onb_finish_tree resets the range to the whole set) */
 ONB_API int onb_set_build_range(onb_context* c, int which, uint64_t lo, uint64_t hi);
 /* the tree-order particle range of shard `rank` of `nranks` for a set of n particles (contiguous leaves) */

@@ -59,6 +59,7 @@ def load_library():
     L.onb_make_trees.argtypes = [C.c_void_p]
     L.onb_make_trees_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]
     L.onb_set_build_range.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
+    L.onb_prepare_eval.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
     L.onb_shard_particle_range.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, _u64p, _u64p]
     L.onb_device_ptr.restype = C.c_void_p
     L.onb_device_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -190,6 +191,7 @@ class GpuSession:
     def finish_tree(self, which): self._chk(self.lib.onb_finish_tree(self.h, which))
     def make_trees(self): self._chk(self.lib.onb_make_trees(self.h))
     def make_trees_range(self, slo, shi, tlo, thi): self._chk(self.lib.onb_make_trees_range(self.h, slo, shi, tlo, thi))
+    def prepare_eval(self, finish=False, tgt_lo=0, tgt_hi=2**63): self._chk(self.lib.onb_prepare_eval(self.h, 1 if finish else 0, tgt_lo, tgt_hi))
     def set_build_range(self, which, lo, hi): self._chk(self.lib.onb_set_build_range(self.h, which, lo, hi))
 
     def shard_particle_range(self, n, rank, nranks):

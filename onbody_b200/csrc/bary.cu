@@ -300,9 +300,9 @@ int onb_bary_upward(onb_context* c, DParts& p, DParts& ep, DTree& t) {
     for (int lev = t.levels - 2; lev >= 0; --lev) {      // the last level holds only leaves
         a.level = lev;
         const uint32_t G = 1u << lev;
-        if (c->PD == 3 && c->SD == 1) { if (c->ncp == 5) k_upward<3, 1, 5><<<G, 128, 0, c->stream>>>(a); else k_upward<3, 1, 0><<<G, 128, 0, c->stream>>>(a); }
-        else if (c->PD == 3) { if (c->ncp == 5) k_upward<3, 3, 5><<<G, 128, 0, c->stream>>>(a); else k_upward<3, 3, 0><<<G, 128, 0, c->stream>>>(a); }
-        else k_upward<2, 1, 0><<<G, 128, 0, c->stream>>>(a);
+        if (c->PD == 3 && c->SD == 1) { if (c->ncp == 5) k_upward<3, 1, 5><<<G, 128, 0, ONB_ST(c)>>>(a); else k_upward<3, 1, 0><<<G, 128, 0, ONB_ST(c)>>>(a); }
+        else if (c->PD == 3) { if (c->ncp == 5) k_upward<3, 3, 5><<<G, 128, 0, ONB_ST(c)>>>(a); else k_upward<3, 3, 0><<<G, 128, 0, ONB_ST(c)>>>(a); }
+        else k_upward<2, 1, 0><<<G, 128, 0, ONB_ST(c)>>>(a);
         ONB_LAUNCH(c);
     }
     ONB_CUDA(cudaGetLastError());

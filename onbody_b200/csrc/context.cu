@@ -374,6 +374,48 @@ int onb_upward(onb_context* c, int which) {
     tm.stop();
     return rc;
 }
+// Everything between the tree builds and the dual-tree evaluation in one call, the source side and the target side on
+// two streams: [finish_tree(0)] -> upward(0) -> pack | [finish_tree(1)] -> refine(1) -> upward(1). The two chains are
+// independent (ongrav3d.cpp:636-724 runs them one after the other) and each is a sequence of small, latency-bound
+// launches, so they overlap almost perfectly. finish != 0 is the multi-GPU variant (node arrays completed bottom-up
+// after the plane exchange; the refinement is restricted to the target build range [tgt_lo, tgt_hi)).
+int onb_prepare_eval(onb_context* c, int finish, uint64_t tgt_lo, uint64_t tgt_hi) {
+    onb_scratch_reset(c);
+    ONB_CUDA(cudaSetDevice(c->device));
+    if (c->legacy) { c->err = "prepare_eval: the dual tree needs barycentric equivalents (-o=<order>)"; return ONB_ERR_UNSUPPORTED; }
+    if (!c->trees[0].built || !c->trees[1].built) { c->err = "prepare_eval: build both trees first"; return ONB_ERR_ARG; }
+    cudaEvent_t e0, e1, e2;
+    ONB_CUDA(cudaEventCreate(&e0)); ONB_CUDA(cudaEventCreate(&e1)); ONB_CUDA(cudaEventCreate(&e2));
+    ONB_CUDA(cudaEventRecord(e0, c->stream));
+    ONB_CUDA(cudaStreamWaitEvent(c->stream2, e0, 0));
+    // source side on the context stream
+    int rc = ONB_OK;
+    if (finish) rc = onb_tree_finish_from_particles(c, c->parts[0], c->trees[0]);
+    if (rc == ONB_OK) rc = onb_bary_upward(c, c->parts[0], c->parts[2], c->trees[0]);
+    if (rc == ONB_OK) rc = onb_pack_sources(c, c->parts[2]);
+    if (rc == ONB_OK && !c->parts[0].packed_valid) rc = onb_pack_sources(c, c->parts[0]);
+    // target side on the second stream
+    if (rc == ONB_OK) {
+        c->cur_stream = c->stream2;
+        if (finish) {
+            rc = onb_tree_finish_from_particles(c, c->parts[1], c->trees[1]);
+            DParts& p = c->parts[1];
+            p.build_lo = (uint32_t)std::min<uint64_t>(tgt_lo, p.n); p.build_hi = (uint32_t)std::min<uint64_t>(tgt_hi, p.n);
+        }
+        if (rc == ONB_OK) rc = onb_tree_refine(c, c->parts[1], c->trees[1], false);
+        if (rc == ONB_OK) rc = onb_bary_upward(c, c->parts[1], c->parts[3], c->trees[1]);
+        c->cur_stream = nullptr;
+    }
+    ONB_CUDA(cudaEventRecord(e1, c->stream2));
+    ONB_CUDA(cudaStreamWaitEvent(c->stream, e1, 0));
+    ONB_CUDA(cudaEventRecord(e2, c->stream));
+    ONB_CUDA(cudaEventSynchronize(e2));
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e2);
+    c->phase_ms["prepare"] = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (rc == ONB_OK) rc = onb_check_flag(c, "refine (introsort depth limit: libstdc++ heapsort fallback is not restated)");
+    return rc;
+}
 int onb_zero_vels(onb_context* c) {
     DParts& t = c->parts[1];
     for (int d = 0; d < c->OD; ++d) if (t.u[d]) ONB_CUDA(cudaMemsetAsync(t.u[d], 0, (size_t)t.cap * sizeof(float), c->stream));

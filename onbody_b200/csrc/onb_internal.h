@@ -183,7 +183,7 @@ void onb_shard_range(const onb_context* c, uint32_t* lo, uint32_t* hi);   // par
 // tree.cu
 int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t bhi);
 int onb_tree_finish_from_particles(onb_context* c, DParts& p, DTree& t);
-int onb_tree_refine(onb_context* c, DParts& p, DTree& t);
+int onb_tree_refine(onb_context* c, DParts& p, DTree& t, bool check_now = true);
 // bary.cu
 int onb_bary_upward(onb_context* c, DParts& p, DParts& ep, DTree& t);
 int onb_bary_downward_level(onb_context* c, int level);

@@ -389,11 +389,11 @@ int onb_pack_sources(onb_context* c, DParts& p) {
     const int T = 256; const uint32_t G = (cap + T - 1) / T;
     PartsView v = view_of(p);
     switch (c->physics) {
-        case ONB_GRAV3D:     k_pack<ONB_GRAV3D><<<G, T, 0, c->stream>>>(v, p.pk0, p.pk1, p.pk2, p.n, cap); break;
-        case ONB_VORT3D:     k_pack<ONB_VORT3D><<<G, T, 0, c->stream>>>(v, p.pk0, p.pk1, p.pk2, p.n, cap); break;
-        case ONB_VORTGRAD3D: k_pack<ONB_VORTGRAD3D><<<G, T, 0, c->stream>>>(v, p.pk0, p.pk1, p.pk2, p.n, cap); break;
-        case ONB_VORT2D:     k_pack<ONB_VORT2D><<<G, T, 0, c->stream>>>(v, p.pk0, p.pk1, p.pk2, p.n, cap); break;
-        default:             k_pack<ONB_VORT2DTR><<<G, T, 0, c->stream>>>(v, p.pk0, p.pk1, p.pk2, p.n, cap); break;
+        case ONB_GRAV3D:     k_pack<ONB_GRAV3D><<<G, T, 0, ONB_ST(c)>>>(v, p.pk0, p.pk1, p.pk2, p.n, cap); break;
+        case ONB_VORT3D:     k_pack<ONB_VORT3D><<<G, T, 0, ONB_ST(c)>>>(v, p.pk0, p.pk1, p.pk2, p.n, cap); break;
+        case ONB_VORTGRAD3D: k_pack<ONB_VORTGRAD3D><<<G, T, 0, ONB_ST(c)>>>(v, p.pk0, p.pk1, p.pk2, p.n, cap); break;
+        case ONB_VORT2D:     k_pack<ONB_VORT2D><<<G, T, 0, ONB_ST(c)>>>(v, p.pk0, p.pk1, p.pk2, p.n, cap); break;
+        default:             k_pack<ONB_VORT2DTR><<<G, T, 0, ONB_ST(c)>>>(v, p.pk0, p.pk1, p.pk2, p.n, cap); break;
     }
     ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());

@@ -746,7 +746,7 @@ int onb_tree_finish_from_particles(onb_context* c, DParts& p, DTree& t) {
     return run_finish(c, p, t);
 }
 
-int onb_tree_refine(onb_context* c, DParts& p, DTree& t) {
+int onb_tree_refine(onb_context* c, DParts& p, DTree& t, bool check_now) {
     if (!t.built) { c->err = "refine: tree not built"; return ONB_ERR_ARG; }
     if (c->block > 128) { c->err = "refine: block size > 128 not supported by the GPU build"; return ONB_ERR_UNSUPPORTED; }
     ONB_CUDA(cudaMemsetAsync(ONB_STATS(c) + 4, 0, sizeof(unsigned long long), ONB_ST(c)));
@@ -758,5 +758,6 @@ int onb_tree_refine(onb_context* c, DParts& p, DTree& t) {
     k_refine<<<leaf1 - leaf0, 128, 0, ONB_ST(c)>>>(ra); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
     p.packed_valid = false;
+    if (!check_now) return ONB_OK;      // the caller checks the flag after joining its streams (onb_prepare_eval)
     return onb_check_flag(c, "refine (introsort depth limit: libstdc++ heapsort fallback is not restated)");
 }

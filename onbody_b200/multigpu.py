@@ -114,13 +114,8 @@ def build_both_distributed(session, nsrc, ntarg, rank, world, scratch=None, time
     tlo, thi = session.shard_particle_range(ntarg, rank, world)
     session.make_trees_range(slo, shi, tlo, thi); t = _tick(times, "both_trees_range", t)
     scratch = exchange_planes(session, 0, nsrc, rank, world, scratch=scratch); t = _tick(times, "src_allgather", t)
-    if world > 1:
-        session.finish_tree(0); t = _tick(times, "src_finish", t)
-    session.upward(0); t = _tick(times, "upward", t)
     scratch = exchange_planes(session, 1, ntarg, rank, world, scratch=scratch); t = _tick(times, "tgt_allgather", t)
-    if world > 1:
-        session.finish_tree(1); t = _tick(times, "tgt_finish", t)
-        session.set_build_range(1, tlo, thi)
-    session.refine(1); t = _tick(times, "refine", t)
-    session.upward(1); t = _tick(times, "tgt_equiv", t)
+    # node arrays of both trees, upward pass + packing | in-leaf refinement of the rank's own leaves + equivalent points:
+    # the two sides on two streams in one call (onb_prepare_eval)
+    session.prepare_eval(world > 1, tlo, thi); t = _tick(times, "finish_upward_refine", t)
     return scratch

@@ -432,3 +432,24 @@ def test_full_size_invariants_1e7():
     a, b = u[:, ::5000].astype(np.float64), un[:, ::5000].astype(np.float64)
     rms = np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum())
     assert 3e-5 < rms < 2e-4, rms              # the reference's README: ~1e-4 at -t=1.4 -o=4
+
+
+def test_prepare_eval_equals_separate_calls():
+    """onb_prepare_eval (source side and target side overlapped on two streams) against the separate phase calls, plain and
+    in the multi-GPU variant (node arrays completed bottom-up, refinement restricted to a range)"""
+    n = 300000
+    a = _gpu("grav3d", n); a.init_driver(); a.make_trees(); a.upward(0); a.refine(1); a.upward(1); a.zero_vels(); a.fastsumm(1.4)
+    b = _gpu("grav3d", n); b.init_driver(); b.make_trees(); b.prepare_eval(); b.zero_vels(); b.fastsumm(1.4)
+    lo, hi = a.shard_particle_range(n, 1, 3)
+    c = _gpu("grav3d", n); c.init_driver(); c.make_trees(); c.finish_tree(0); c.upward(0); c.finish_tree(1); c.set_build_range(1, lo, hi); c.refine(1); c.upward(1)
+    d = _gpu("grav3d", n); d.init_driver(); d.make_trees(); d.prepare_eval(True, lo, hi)
+    for x, y, evald in ((a, b, True), (c, d, False)):
+        for which, keys in ((1, ("x", "gidx") + (("u",) if evald else ())), (2, ("x", "r", "s")), (3, ("x",))):
+            px, py = x.parts(which, keys), y.parts(which, keys)
+            for k in keys:
+                assert bits_equal(px[k], py[k]), (which, k, evald)
+        assert x.build_stats() == y.build_stats()
+        for which in (0, 1):
+            tx, ty = x.tree(which), y.tree(which)
+            for k in ("num", "ioffset", "nc", "ns", "nr", "x", "pr"):
+                assert bits_equal(tx[k], ty[k]), (which, k)
