@@ -291,7 +291,10 @@ int onb_make_tree(onb_context* c, int which) { return onb_make_tree_range(c, whi
 // Both trees at once: the two builds are independent and their top levels are latency bound (grid-wide barriers around
 // short passes), so they are enqueued on two streams and overlap on the device.
 int onb_make_trees_range(onb_context* c, uint64_t slo, uint64_t shi, uint64_t tlo, uint64_t thi) {
-    static const bool seq_builds = std::getenv("ONB_SEQ_BUILDS") != nullptr;      // diagnostics: one build after the other
+    // one build after the other: on request (diagnostics), and above 5e8 particles, where two concurrent builds would hold
+    // 2 x 36 B per particle of scratch at once
+    static const bool seq_env = std::getenv("ONB_SEQ_BUILDS") != nullptr;
+    const bool seq_builds = seq_env || std::max(c->parts[0].n, c->parts[1].n) > 500000000u;
     // a pending asynchronous target copy sits on stream2, where the target build is enqueued behind it: the source
     // build on the context stream need not wait for it (the streams are joined at the end of this call)
     const bool tgt_in_flight = c->tgt_copy_pending && !seq_builds;
