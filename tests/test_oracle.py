@@ -100,17 +100,19 @@ def _run_legacy(s, theta):
 
 
 @pytest.mark.skipif(not ref_available("grav3d"), reason="compiled reference (oracle/_ref) not present")
-@pytest.mark.parametrize("physics,n", [("grav3d", 6100), ("vort3d", 5000), ("vort2d", 7001), ("vortgrad3d", 3000)])
-def test_port_legacy_equivalents_equal_compiled_reference(physics, n):
-    """-o omitted: pair-merge equivalents (barneshut.hpp:946-1061) of the restatement against the reference itself"""
-    a = _run_legacy(RefSession(physics, n, n, order=-1), 1.2)
-    b = _run_legacy(PortSession(physics, n, n, order=-1), 1.2)
+@pytest.mark.parametrize("physics,n,block", [("grav3d", 6100, 128), ("vort3d", 5000, 128), ("vort2d", 7001, 128), ("vortgrad3d", 3000, 128),
+                                             ("grav3d", 5003, 64), ("vort2dtr", 4001, 32), ("grav3d", 300, 128), ("grav3d", 129, 128)])
+def test_port_legacy_equivalents_equal_compiled_reference(physics, n, block):
+    """-o omitted: pair-merge equivalents (barneshut.hpp:946-1061) of the restatement against the reference itself,
+    including block sizes other than 128 (odd counts on the right spine) and trees of one or two levels"""
+    a = _run_legacy(RefSession(physics, n, n, block=block, order=-1, eq_block=block), 1.2)
+    b = _run_legacy(PortSession(physics, n, n, block=block, order=-1, eq_block=block), 1.2)
     for k, v in a.items():
         if isinstance(v, np.ndarray):
             assert bits_equal(v, b[k]), k
         else:
             assert v == b[k], k
-    assert 0 < int(a["stree.epnum"][1]) <= 128
+    assert 0 < int(a["stree.epnum"][1]) <= block
 
 
 def test_port_legacy_golden(golden):
