@@ -338,7 +338,8 @@ def _run_legacy(s, theta):
     return out
 
 
-@pytest.mark.parametrize("physics,n,block", [("grav3d", 20000, 128), ("vort3d", 9000, 128), ("vort2d", 7001, 128), ("vortgrad3d", 5000, 128), ("grav3d", 6000, 64)])
+@pytest.mark.parametrize("physics,n,block", [("grav3d", 20000, 128), ("vort3d", 9000, 128), ("vort2d", 7001, 128), ("vortgrad3d", 5000, 128), ("grav3d", 6000, 64),
+                                             ("vort2dtr", 4001, 32), ("grav3d", 300, 128), ("grav3d", 129, 128)])
 def test_legacy_equivalents_strict_bit_exact(physics, n, block):
     """-o omitted (order = -1, the drivers' default): refineTree(srcs) + pair-merge equivalents (barneshut.hpp:946-1061)
     and treecode2/3 over them, every array and every result bit-identical to the oracle"""
