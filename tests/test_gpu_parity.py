@@ -415,6 +415,16 @@ def test_full_size_invariants_1e7():
     assert np.array_equal(tx[1], xi[1][gi])                                               # ... that maps tree order back to the input
     # upward pass: barycentric weights sum to one, so every node's equivalent strengths sum to its particles' strengths
     g.upward(0); g.refine(1); g.upward(1)
+    # the hashes SURVEY.md section 4 obtained independently from the reference at N = 1e7 (FNV-1a-64 over the raw bytes):
+    # final target order, target coordinates, every source-node array, and the strict (-O2) build's intra-leaf source order
+    from oracle.refapi import fnv1a64
+    h = lambda a: "%016x" % fnv1a64(np.ascontiguousarray(a))
+    pt = g.parts(1, ("gidx", "x"))
+    assert h(pt["gidx"]) == "957a1ab3437a7eeb" and [int(v) for v in pt["gidx"][:8]] == [8089804, 7138819, 7371734, 6685117, 5734885, 1392952, 2924730, 1050990]
+    assert h(pt["x"][0]) == "b647a1c4491c5fe3"
+    assert ts["levels"] == 18 and ts["numnodes"] == 262144
+    assert h(ts["nr"]) == "54cb79fc9521bd9d" and h(ts["nc"][0]) == "1b16678759bcf79e" and h(ts["x"][0]) == "8951e8b417150f7e" and h(ts["num"]) == "822a73b6b72f92bf"
+    assert h(p["x"][0]) == "f1fd8ca55ae2d837"
     es = g.parts(2, ("s",))["s"][0].astype(np.float64).reshape(-1, 128).sum(axis=1)
     tot = float(si[0].astype(np.float64).sum())
     assert abs(es[1] - tot) <= 2e-5 * np.abs(si[0]).astype(np.float64).sum()

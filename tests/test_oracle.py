@@ -75,6 +75,12 @@ def test_port_equals_reference_tree_1e6():
     for k in ("num", "ioffset", "nc", "ns", "nr", "x", "s", "pr"):
         assert bits_equal(tr[k], tp[k]), k
     assert p.build_stats()["stalls"] == 2 and p.refine_tie_sorts() > 0
+    # the hashes SURVEY.md section 4 obtained independently from the reference at this size (FNV-1a-64 over the raw bytes)
+    h = lambda a: "%016x" % fnv1a64(np.ascontiguousarray(a))
+    assert h(p.parts(1)["gidx"]) == "502bae5161063bf7" and h(p.parts(1)["x"][0]) == "f6c62a65e19a00c1"
+    assert tp["levels"] == 14 and tp["numnodes"] == 16384
+    assert h(tp["nr"]) == "16e0e91d02b96887" and h(tp["nc"][0]) == "f5df6737c4298b86" and h(tp["x"][0]) == "0b659ba5898c0aa6" and h(tp["num"]) == "ccbcffa83332a668"
+    assert h(p.parts(0)["x"][0]) == "5b0b68d776e49dc5"          # intra-leaf source order of the strict (-O2) build
 
 
 def test_reference_cli_binary_matches_golden_stdout():
