@@ -81,6 +81,10 @@ ONB_API void onb_dims(const onb_context* c, int* pd, int* sd, int* od, int* has_
  * speed - or device memory, the copy kind is resolved by unified addressing) ------------------------------ */
 ONB_API int onb_set_sources(onb_context* c, uint64_t n, const float* x, const float* r, const float* s);
 ONB_API int onb_set_targets(onb_context* c, uint64_t n, const float* x, const float* r);
+/* the same with one pointer per plane (x[PD], s[SD]): the Fortran-style entry points hand over separate arrays
+ * (interface3dvortgrads.cpp:247-254), which then need no re-packing on the host */
+ONB_API int onb_set_sources_planes(onb_context* c, uint64_t n, const float* const* x, const float* r, const float* const* s);
+ONB_API int onb_set_targets_planes(onb_context* c, uint64_t n, const float* const* x, const float* r);
 /* opt-in: with on != 0, set_sources / set_targets return as soon as the copies from PINNED host (or device) buffers
  * are enqueued; the source copy runs on the context's stream and the target copy on its second stream, so that
  * onb_make_trees builds the source tree while the targets are still crossing PCIe. The caller must leave the
@@ -126,8 +130,44 @@ ONB_API int onb_treecode3(onb_context* c, float theta, float* flops);
 ONB_API int onb_fastsumm(onb_context* c, float theta);
 
 /* target sharding for multi-GPU runs: this context evaluates only the targets of shard `rank` of `nranks`
- * (contiguous tree-order ranges of target leaves); the trees themselves are built in full. */
+ * (contiguous tree-order ranges of target leaves, ceil(leaves/nranks) each); without a communicator the trees themselves
+ * are built in full (or by the explicit *_range calls above). */
 ONB_API int onb_set_shard(onb_context* c, int rank, int nranks);
+
+/* multi-GPU communicator ---------------------------------------------------------------------------------------
+ * (the reference has no multi-device path; north_star: targets sharded, source tree + equivalent particles replicated by
+ * NCCL all-gathers over NVLink.) One context per GPU. With a communicator attached the SAME phase calls run distributed:
+ * onb_make_tree(s) sorts only this rank's leaf range and completes the node arrays from exchanged per-leaf records,
+ * onb_upward(0) / onb_prepare_eval anterpolate the rank's own nodes and exchange the strengths, onb_refine / onb_upward(1) /
+ * every evaluation method work on the rank's target shard; results are bit-identical to the single-GPU run. Every context
+ * must be given the same inputs and must make the same calls in the same order. NCCL is loaded with dlopen at first use
+ * (ONB_NCCL_LIB overrides "libnccl.so.2").
+ *   one process per GPU : rank 0 calls onb_comm_unique_id, ships the 128 bytes to the others, all call onb_comm_init_rank
+ *   one process, n GPUs : onb_comm_init_all(ctxs, n), then one host thread per context makes the phase calls
+ *   onb_comm_init_loopback: contexts of one process joined by device copies instead of NCCL - on ANY devices, also all on
+ *   the same one; exists so that the distributed path can be verified on a single GPU, one host thread per context. */
+ONB_API int onb_comm_unique_id(void* id, uint64_t bytes);
+ONB_API int onb_comm_init_rank(onb_context* c, int rank, int nranks, const void* id, uint64_t bytes);
+ONB_API int onb_comm_init_all(onb_context** ctxs, int n);
+ONB_API int onb_comm_init_loopback(onb_context** ctxs, int n);
+ONB_API int onb_comm_destroy(onb_context* c);
+/* transport: 0 none, 1 NCCL, 2 loopback */
+ONB_API int onb_comm_info(const onb_context* c, int* rank, int* nranks, int* transport, int* nccl_version);
+/* the partition arithmetic, pure host code (no GPU needed): particles per rank, and per tree level the node-id intervals
+ * [own_lo, own_hi) inside / [need_lo, need_hi) overlapping the rank's range plus the nodes straddling rank boundaries
+ * (shared[level * nranks + k], k < nshared[level]). Returns the number of levels, or a negative error code. */
+ONB_API uint64_t onb_shard_chunk_for(uint64_t n, int block, int nranks);
+ONB_API int onb_plan_query(uint64_t n, int block, int nranks, int rank, int max_levels, uint32_t* own_lo, uint32_t* own_hi,
+                           uint32_t* need_lo, uint32_t* need_hi, uint32_t* nshared, uint32_t* shared);
+
+/* memory mode: ONB_MEM_LEAN trades allocator calls for footprint (N = 1e9 on 8 GPUs, BASELINE configs[4]): one tree build at
+ * a time and its scratch returned to the driver, the SoA source planes released once the float4 tiles exist (onb_get_parts
+ * of sources then fails), and - in a sharded run - the target outputs and the equivalent target points become sparse planes
+ * backed by memory only where this rank's shard touches them. Call before set_sources / set_targets. */
+enum { ONB_MEM_NORMAL = 0, ONB_MEM_LEAN = 1 };
+ONB_API int onb_set_memory_mode(onb_context* c, int mode);
+/* bytes currently allocated on the context's device by this process and the device total (cudaMemGetInfo) */
+ONB_API int onb_device_memory(onb_context* c, uint64_t* used, uint64_t* total);
 
 /* outputs (device -> host copies) ------------------------------------------------------------ */
 ONB_API uint64_t onb_count(const onb_context* c, int which);
@@ -135,6 +175,11 @@ ONB_API int onb_get_parts(onb_context* c, int which, float* x, float* r, float* 
 /* results scattered back to the caller's original target order and ADDED to u (the reference's
  * external_vel_solver_f_ semantics, interface3dvortgrads.cpp:384-395); u is [OD][n] */
 ONB_API int onb_add_results_original_order(onb_context* c, float* u);
+/* the same with one pointer per output plane (out[OD]); host or device pointers. Device pointers are updated in place by one
+ * kernel; host pointers through one scatter kernel and a pinned double buffer whose copies overlap the host's += */
+ONB_API int onb_add_results_planes(onb_context* c, float* const* out);
+/* multi-GPU: the output planes of this context's shard only - elements [*lo,*hi) of every plane of u ([OD][n], tree order) */
+ONB_API int onb_get_shard_results(onb_context* c, float* u, uint64_t* lo, uint64_t* hi);
 ONB_API int onb_tree_shape(const onb_context* c, int which, int* levels, int* numnodes);
 ONB_API int onb_get_tree(onb_context* c, int which, float* x, float* nc, float* ns, float* nr, float* pr, float* s,
                  uint64_t* ioffset, uint64_t* num, uint64_t* epoffset, uint64_t* epnum);

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(HERE)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++"   # the image's CXX env points at a gcc without libgomp; use the system one
 
-CORE_SOURCES = ["context.cu", "p2p.cu", "tree.cu", "bary.cu", "traverse.cu", "pointwise.cu", "scan.cu"]
+CORE_SOURCES = ["context.cu", "p2p.cu", "tree.cu", "bary.cu", "traverse.cu", "pointwise.cu", "scan.cu", "mem.cu", "plan.cu", "comm.cu", "dist.cu"]
 CORE_LIB = os.path.join(HERE, "libonbody_b200.so")
 
 NVCC_FLAGS = [
@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
         objs.append(o)
     if force or _newer(CORE_LIB, objs):
         _run([NVCC, "-shared", "-cudart", "static", "-ccbin", HOSTCXX, "-o", CORE_LIB] + objs +
-             ["-gencode", "arch=compute_100a,code=sm_100a"], log)
+             ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"], log)
     build_hosts(force)
     return CORE_LIB
 

@@ -25,6 +25,10 @@ struct Cheb { float sk[ONB_MAX_ORDER + 1]; float wk[ONB_MAX_ORDER + 1]; };
 struct UpArgs {
     PartsView p, ep; TreeView t; Cheb ch;
     uint32_t block, ebs; int level, PD, SD, ncp, numEqps, are_sources;
+    // which nodes this launch covers: node = nodes ? nodes[blockIdx.x] : node0 + blockIdx.x (single GPU: the whole level; multi-GPU:
+    // the rank's own interval of the level, or the short list of nodes that straddle a rank boundary - plan.cu)
+    uint32_t node0; const uint32_t* nodes;
+    int strengths;      // 0: positions and radii only (target trees; the replicated positions pass of a multi-GPU source tree)
 };
 
 // 1-D weights of one point against the node's Chebyshev coordinates lsk[d*ncp+k]; row = PD*ncp floats.
@@ -51,7 +55,7 @@ __device__ __forceinline__ float bary_row(int PD, int ncp, const float* wk, cons
 constexpr int W01_STRIDE = 27;
 template <int PD, int SD, int NCP>
 __global__ void __launch_bounds__(128) k_upward(const UpArgs a) {
-    const uint32_t node = (1u << a.level) + blockIdx.x;
+    const uint32_t node = a.nodes ? a.nodes[blockIdx.x] : a.node0 + blockIdx.x;
     if (a.t.num[node] <= a.block) return;                                                 // :266 leaves have no equivalents
     const int tid = threadIdx.x, ncp = a.ncp, numEqps = a.numEqps;
     __shared__ float lsk[3 * (ONB_MAX_ORDER + 1)];
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(128) k_upward(const UpArgs a) {
             a.ep.x[d][e0 + tid] = tid < numEqps ? lsk[d * ncp + kd[d]] : a.t.nc[d][node]; // :330, :336
         a.ep.r[e0 + tid] = rr;
     }
-    if (!a.are_sources) return;                                                           // target trees: positions only (:378,:400)
+    if (!a.strengths) return;                                                             // target trees: positions only (:378,:400)
 
     float acc[3] = {0.0f, 0.0f, 0.0f};                                                    // :343-347
     for (uint32_t child = 2 * node; child < 2 * node + 2; ++child) {                      // :360
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(128) k_upward(const UpArgs a) {
 // ---- downward: zero-fill + interpolation from the parent, one CTA per target node of this level ----
 struct DownArgs {
     PartsView tl, tb; TreeView t; Cheb ch;
-    uint32_t block, ebs, shard_lo, shard_hi; int level, PD, OD, ncp, numEqps;
+    uint32_t block, ebs, shard_lo, shard_hi, node0; int level, PD, OD, ncp, numEqps;
 };
 
 // NCP > 0 (3-D, OD == 3, order+1 == NCP): the point's weights live in registers as (den*a0[k0])*a1[k1], the loops over the
@@ -147,7 +151,7 @@ struct DownArgs {
 // (separate multiply and add) stays bit-identical; FAST contracts the accumulation into FMAs.
 template <int PD, int OD, int NCP, bool FAST>
 __global__ void __launch_bounds__(128) k_downward(const DownArgs a) {
-    const uint32_t T = (1u << a.level) + blockIdx.x;
+    const uint32_t T = a.node0 + blockIdx.x;
     const uint32_t tn = a.t.num[T];
     if (tn < 1) return;                                                                   // ongrav3d.cpp:221
     const uint32_t tio = a.t.ioffset[T];
@@ -286,29 +290,73 @@ Cheb make_cheb(int order) {                                                     
 
 }  // namespace
 
-int onb_bary_upward(onb_context* c, DParts& p, DParts& ep, DTree& t) {
+// allocation of the equivalent particles of a tree: numnodes/2 blocks of ebs slots (ongrav3d.cpp:645,696). In the lean memory
+// mode the equivalent TARGET points of a sharded run are sparse planes: memory only under the blocks of the nodes that overlap
+// this rank's shard (plan.need), the full index space everywhere else.
+int onb_bary_alloc(onb_context* c, DParts& p, DParts& ep, DTree& t) {
+    const uint32_t need = (uint32_t)(t.numnodes / 2) * (uint32_t)c->ebs;
+    const bool sparse = !p.are_sources && c->mem_mode == ONB_MEM_LEAN && c->shard_n > 1;
+    if (ep.n == need && !ep.unpacked_released && ep.sparse_key == (sparse ? c->plan_key(1) : 0ull)) return ONB_OK;
+    onb_free_parts(c, ep);
+    if (!sparse) return onb_alloc_parts(c, ep, need, p.are_sources);
+    int rc = onb_plan_make(c->plan[1], p.n, c->block, c->shard_n, c->shard_rank); if (rc) { c->err = "upward: cannot plan the target partition"; return rc; }
+    const ShardPlan& P = c->plan[1];
+    std::vector<std::pair<size_t, size_t>> ranges;
+    for (int l = 0; l < P.levels; ++l)
+        if (P.need_hi[l] > P.need_lo[l]) ranges.push_back({(size_t)P.need_lo[l] * c->ebs * sizeof(float), (size_t)(P.need_hi[l] - P.need_lo[l]) * c->ebs * sizeof(float)});
+    ep = DParts();
+    ep.n = need; ep.cap = ((need + 63u) & ~31u) + 288u; ep.PD = c->PD; ep.SD = c->SD; ep.OD = c->OD; ep.are_sources = false;
+    const size_t bytes = (size_t)ep.cap * sizeof(float);
+    for (int d = 0; d < c->PD; ++d) ONB_CUDA(onb_sparse_alloc(c, (void**)&ep.x[d], bytes, ranges, ONB_ST(c)));
+    ONB_CUDA(onb_sparse_alloc(c, (void**)&ep.r, bytes, ranges, ONB_ST(c)));
+    for (int d = 0; d < c->OD; ++d) ONB_CUDA(onb_sparse_alloc(c, (void**)&ep.u[d], bytes, ranges, ONB_ST(c)));
+    ep.sparse_key = c->plan_key(1);
+    return ONB_OK;
+}
+
+template <int STR>
+static void launch_upward(onb_context* c, UpArgs a, uint32_t G) {
+    a.strengths = STR;
+    if (G == 0) return;
+    if (c->PD == 3 && c->SD == 1) { if (c->ncp == 5) k_upward<3, 1, 5><<<G, 128, 0, ONB_ST(c)>>>(a); else k_upward<3, 1, 0><<<G, 128, 0, ONB_ST(c)>>>(a); }
+    else if (c->PD == 3) { if (c->ncp == 5) k_upward<3, 3, 5><<<G, 128, 0, ONB_ST(c)>>>(a); else k_upward<3, 3, 0><<<G, 128, 0, ONB_ST(c)>>>(a); }
+    else k_upward<2, 1, 0><<<G, 128, 0, ONB_ST(c)>>>(a);
+    ONB_LAUNCH(c);
+}
+
+// mode: ONB_UP_ALL      every non-leaf node, bottom-up (single GPU)
+//       ONB_UP_OWN      the nodes completely inside this rank's particle range, bottom-up: needs no other rank's data
+//       ONB_UP_SHARED   the nodes that straddle a rank boundary, bottom-up, after the owned strengths have been exchanged
+//       ONB_UP_POS      positions and radii of every node (sources: replicated, it only needs the node boxes)
+//       ONB_UP_NEED     positions of the nodes that overlap this rank's range (targets of a sharded run)
+int onb_bary_upward_mode(onb_context* c, DParts& p, DParts& ep, DTree& t, int mode) {
     if (!t.built) { c->err = "upward: tree not built"; return ONB_ERR_ARG; }
-    const uint32_t need = (uint32_t)(t.numnodes / 2) * (uint32_t)c->ebs;                  // ongrav3d.cpp:645,696
-    if (ep.n != need) {
-        onb_free_parts(c, ep);
-        int rc = onb_alloc_parts(c, ep, need, p.are_sources);
-        if (rc) return rc;
-    }
+    { int rc = onb_bary_alloc(c, p, ep, t); if (rc) return rc; }
     UpArgs a; a.p = view_of(p); a.ep = view_of(ep); a.t = view_of(t); a.ch = make_cheb(c->order);
     a.block = c->block; a.ebs = c->ebs; a.PD = c->PD; a.SD = c->SD; a.ncp = c->ncp; a.numEqps = c->num_eqps;
-    a.are_sources = p.are_sources ? 1 : 0;
+    a.are_sources = p.are_sources ? 1 : 0; a.nodes = nullptr; a.node0 = 0; a.strengths = 0;
+    const int which = p.are_sources ? 0 : 1;
+    const ShardPlan* P = nullptr;
+    if (mode != ONB_UP_ALL && mode != ONB_UP_POS) {
+        int rc = onb_plan_make(c->plan[which], p.n, c->block, c->shard_n, c->shard_rank); if (rc) { c->err = "upward: cannot plan the partition"; return rc; }
+        P = &c->plan[which];
+        if (mode == ONB_UP_SHARED) { rc = onb_plan_upload_shared(c, which); if (rc) return rc; }
+    }
     for (int lev = t.levels - 2; lev >= 0; --lev) {      // the last level holds only leaves
         a.level = lev;
-        const uint32_t G = 1u << lev;
-        if (c->PD == 3 && c->SD == 1) { if (c->ncp == 5) k_upward<3, 1, 5><<<G, 128, 0, ONB_ST(c)>>>(a); else k_upward<3, 1, 0><<<G, 128, 0, ONB_ST(c)>>>(a); }
-        else if (c->PD == 3) { if (c->ncp == 5) k_upward<3, 3, 5><<<G, 128, 0, ONB_ST(c)>>>(a); else k_upward<3, 3, 0><<<G, 128, 0, ONB_ST(c)>>>(a); }
-        else k_upward<2, 1, 0><<<G, 128, 0, ONB_ST(c)>>>(a);
-        ONB_LAUNCH(c);
+        switch (mode) {
+            case ONB_UP_ALL:    a.node0 = 1u << lev; if (p.are_sources) launch_upward<1>(c, a, 1u << lev); else launch_upward<0>(c, a, 1u << lev); break;
+            case ONB_UP_POS:    a.node0 = 1u << lev; launch_upward<0>(c, a, 1u << lev); break;
+            case ONB_UP_OWN:    a.node0 = P->own_lo[lev]; launch_upward<1>(c, a, P->own_hi[lev] - P->own_lo[lev]); break;
+            case ONB_UP_NEED:   a.node0 = P->need_lo[lev]; launch_upward<0>(c, a, P->need_hi[lev] - P->need_lo[lev]); break;
+            case ONB_UP_SHARED: a.nodes = c->d_shared[which] + (size_t)lev * c->shard_n; launch_upward<1>(c, a, (uint32_t)P->shared[lev].size()); break;
+        }
     }
     ONB_CUDA(cudaGetLastError());
     ep.packed_valid = false;
     return ONB_OK;
 }
+int onb_bary_upward(onb_context* c, DParts& p, DParts& ep, DTree& t) { return onb_bary_upward_mode(c, p, ep, t, ONB_UP_ALL); }
 
 int onb_bary_downward_level(onb_context* c, int level) {
     DTree& t = c->trees[1];
@@ -317,7 +365,10 @@ int onb_bary_downward_level(onb_context* c, int level) {
     // shard range in particle indices (contiguous target leaves)
     onb_shard_range(c, &a.shard_lo, &a.shard_hi);
     const bool fast = c->arith != ONB_ARITH_STRICT;
-    const dim3 G(1u << level);
+    uint32_t node0, cnt; onb_level_span(c, level, &node0, &cnt);      // the whole level, or the nodes that overlap this rank's shard
+    if (cnt == 0) return ONB_OK;
+    a.node0 = node0;
+    const dim3 G(cnt);
     if (c->PD == 3 && c->ncp == 5) { if (fast) k_downward<3, 3, 5, true><<<G, 128, 0, c->stream>>>(a); else k_downward<3, 3, 5, false><<<G, 128, 0, c->stream>>>(a); }
     else if (c->PD == 3) k_downward<3, 3, 0, false><<<G, 128, 0, c->stream>>>(a);
     else k_downward<2, 2, 0, false><<<G, 128, 0, c->stream>>>(a);

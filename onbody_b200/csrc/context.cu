@@ -19,20 +19,45 @@ static std::string g_create_error;
 // ---------------------------------------------------------------------------------------------
 int onb_alloc_parts(onb_context* c, DParts& p, uint32_t n, bool are_sources) {
     p = DParts();
-    // slack: bulk copies round up to 16 B, padded all-gathers overrun by < one leaf
-    p.n = n; p.cap = ((n + 63u) & ~31u) + 288u; p.PD = c->PD; p.SD = c->SD; p.OD = c->OD; p.are_sources = are_sources;
+    // slack: bulk copies round up to 16 B; in-place all-gathers of equal leaf-aligned chunks overrun n by < one leaf per rank
+    p.n = n; p.cap = ((n + 63u) & ~31u) + 288u + (uint32_t)(ONB_MAX_RANKS + 1) * (uint32_t)std::max(c->block, 128); p.PD = c->PD; p.SD = c->SD; p.OD = c->OD; p.are_sources = are_sources;
     const size_t bytes = (size_t)p.cap * sizeof(float);
-    for (int d = 0; d < c->PD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.x[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.x[d], 0, bytes, c->stream)); }
-    ONB_CUDA(onb_pmalloc(c, (void**)&p.r, bytes)); ONB_CUDA(cudaMemsetAsync(p.r, 0, bytes, c->stream));
+    // the zero fills go on the stream of the work being enqueued (ONB_ST): onb_prepare_eval allocates the equivalent target
+    // points while its target chain runs on the second stream, and a fill ordered on the context stream could land after
+    // k_upward had written them
+    cudaStream_t st = ONB_ST(c);
+    for (int d = 0; d < c->PD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.x[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.x[d], 0, bytes, st)); }
+    ONB_CUDA(onb_pmalloc(c, (void**)&p.r, bytes)); ONB_CUDA(cudaMemsetAsync(p.r, 0, bytes, st));
     if (are_sources) {
-        for (int d = 0; d < c->SD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.s[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.s[d], 0, bytes, c->stream)); }
+        for (int d = 0; d < c->SD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.s[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.s[d], 0, bytes, st)); }
         ONB_CUDA(onb_pmalloc(c, (void**)&p.pk0, (size_t)p.cap * sizeof(float4)));
         const bool nf2 = c->physics == ONB_VORT3D || c->physics == ONB_VORTGRAD3D;
         if (nf2) ONB_CUDA(onb_pmalloc(c, (void**)&p.pk1, (size_t)p.cap * sizeof(float4)));
         if (c->physics == ONB_GRAV3D) ONB_CUDA(onb_pmalloc(c, (void**)&p.pk2, bytes));
+    } else if (c->mem_mode == ONB_MEM_LEAN && c->shard_n > 1 && &p == &c->parts[1]) {
+        // lean memory mode: the output planes keep their full index space but only this rank's shard is backed by memory
+        uint64_t lo = 0, hi = 0; onb_shard_range_for(n, c->block, c->shard_rank, c->shard_n, &lo, &hi);
+        std::vector<std::pair<size_t, size_t>> ranges(1, std::make_pair((size_t)lo * sizeof(float), (size_t)(hi - lo) * sizeof(float)));
+        for (int d = 0; d < c->OD; ++d) ONB_CUDA(onb_sparse_alloc(c, (void**)&p.u[d], bytes, ranges, st));
+        p.sparse_key = c->plan_key(1); p.u_lo = (uint32_t)lo; p.u_hi = (uint32_t)hi;
     } else {
-        for (int d = 0; d < c->OD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.u[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.u[d], 0, bytes, c->stream)); }
+        for (int d = 0; d < c->OD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.u[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.u[d], 0, bytes, st)); }
     }
+    return ONB_OK;
+}
+// lean memory mode: once the float4 tiles exist nothing on the evaluation path reads the SoA planes of a source set again
+static void release_unpacked(onb_context* c, DParts& p) {
+    if (!p.are_sources || !p.packed_valid) return;
+    for (int d = 0; d < ONB_MAX_PD; ++d) { if (p.x[d]) onb_pfree(c, p.x[d]); p.x[d] = nullptr; }
+    if (p.r) onb_pfree(c, p.r); p.r = nullptr;
+    for (int d = 0; d < ONB_MAX_SD; ++d) { if (p.s[d]) onb_pfree(c, p.s[d]); p.s[d] = nullptr; }
+    p.unpacked_released = true;
+}
+static int lean_after_prepare(onb_context* c) {
+    if (c->mem_mode != ONB_MEM_LEAN) return ONB_OK;
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    release_unpacked(c, c->parts[0]); release_unpacked(c, c->parts[2]);
+    onb_scratch_trim(c);
     return ONB_OK;
 }
 void onb_free_parts(onb_context* c, DParts& p) {
@@ -81,39 +106,12 @@ void onb_free_tree(onb_context* c, DTree& t) {
     if (t.ioffset) onb_pfree(c, t.ioffset); if (t.num) onb_pfree(c, t.num);
     t = DTree();
 }
-cudaError_t onb_dmalloc(onb_context* c, void** p, size_t bytes) {
-    bytes = (std::max<size_t>(bytes, 4) + 255) & ~(size_t)255;
-    while (c->slab_cur < c->slabs.size()) {
-        onb_context::Slab& s = c->slabs[c->slab_cur];
-        if (c->slab_off + bytes <= s.cap) { *p = s.p + c->slab_off; c->slab_off += bytes; return cudaSuccess; }
-        ++c->slab_cur; c->slab_off = 0;
-    }
-    onb_context::Slab s; s.cap = std::max<size_t>(bytes, (size_t)64 << 20); s.p = nullptr;
-    cudaError_t e = cudaMalloc((void**)&s.p, s.cap);
-    if (e != cudaSuccess) return e;
-    c->slabs.push_back(s); c->slab_cur = c->slabs.size() - 1; c->slab_off = bytes;
-    *p = s.p;
-    return cudaSuccess;
-}
 int onb_join_copies(onb_context* c) {
     if (c->tgt_copy_pending) {
         c->tgt_copy_pending = false;
         ONB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_tgt_ready, 0));
     }
     return ONB_OK;
-}
-void onb_scratch_reset(onb_context* c) {
-    c->cur_stream = nullptr;          // (an error return may have left a phase's secondary stream selected)
-    onb_join_copies(c);
-    if (c->slabs.size() > 1) {          // coalesce what the last call needed into one slab
-        cudaStreamSynchronize(c->stream);
-        size_t total = 0;
-        for (auto& s : c->slabs) { total += s.cap; cudaFree(s.p); }
-        c->slabs.clear();
-        onb_context::Slab s; s.cap = total; s.p = nullptr;
-        if (cudaMalloc((void**)&s.p, s.cap) == cudaSuccess) c->slabs.push_back(s);
-    }
-    c->slab_cur = 0; c->slab_off = 0;
 }
 int onb_check_flag(onb_context* c, const char* what) {
     ONB_CUDA(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -173,9 +171,16 @@ void onb_destroy(onb_context* c) {
     cudaStreamSynchronize(c->stream);
     if (c->d_flag) cudaFree(c->d_flag);
     if (c->d_build_stats) cudaFree(c->d_build_stats);
+    onb_comm_destroy(c);
+    for (int k = 0; k < 2; ++k) if (c->d_shared[k]) cudaFree(c->d_shared[k]);
+    if (c->ev_src_planes) cudaEventDestroy(c->ev_src_planes);
     if (c->d_epnum) cudaFree(c->d_epnum);
+    if (c->dtt_pool) cudaFree(c->dtt_pool);
+    for (auto& e : c->ev_cache) if (e) cudaEventDestroy(e);
     for (auto& sl : c->slabs) cudaFree(sl.p);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (int k = 0; k < 2; ++k) if (c->ev_stage[k]) cudaEventDestroy(c->ev_stage[k]);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->ev_tgt_ready) cudaEventDestroy(c->ev_tgt_ready);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -209,24 +214,35 @@ void onb_set_flops_per_pair(onb_context* c, int flops) { if (c && flops > 0) c->
 
 int onb_set_shard(onb_context* c, int rank, int nranks) {
     if (nranks < 1 || rank < 0 || rank >= nranks) { c->err = "bad shard"; return ONB_ERR_ARG; }
-    c->shard_rank = rank; c->shard_n = nranks; return ONB_OK;
+    if (c->comm && (rank != c->shard_rank || nranks != c->shard_n)) { c->err = "the shard of a context with a communicator is its rank"; return ONB_ERR_ARG; }
+    c->shard_rank = rank; c->shard_n = nranks;
+    c->plan[0].valid = c->plan[1].valid = false;
+    return ONB_OK;
+}
+int onb_set_memory_mode(onb_context* c, int mode) {
+    if (!c || (mode != ONB_MEM_NORMAL && mode != ONB_MEM_LEAN)) return ONB_ERR_ARG;
+    c->mem_mode = mode; return ONB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // inputs
 // ---------------------------------------------------------------------------------------------
-static int set_parts(onb_context* c, int which, uint64_t n, const float* x, const float* r, const float* s) {
+// xs[PD] / ss[SD]: one pointer per plane (the planar C-ABI layout is the special case xs[d] = x + d*n)
+static int set_parts(onb_context* c, int which, uint64_t n, const float* const* xs, const float* r, const float* const* ss) {
     if (n == 0 || n >= 0xfffff000ull) { c->err = "particle count out of range for one GPU"; return ONB_ERR_ARG; }
     ONB_CUDA(cudaSetDevice(c->device));
     DParts& p = c->parts[which];
-    if (p.n != n) { onb_free_parts(c, p); int rc = onb_alloc_parts(c, p, (uint32_t)n, which == 0); if (rc) return rc; }
+    const uint64_t want_key = (which == 1 && c->mem_mode == ONB_MEM_LEAN && c->shard_n > 1) ? c->plan_key_for(n) : 0ull;
+    if (p.n != n || p.unpacked_released || p.sparse_key != want_key) { onb_free_parts(c, p); int rc = onb_alloc_parts(c, p, (uint32_t)n, which == 0); if (rc) return rc; }
     if (p.gidx) { p.gidx_spare = p.gidx; p.gidx = nullptr; }      // no cudaFree/cudaMalloc per step: the next build takes it back
     const size_t bytes = (size_t)n * sizeof(float);
     bool async = false;
     if (c->async_inputs) {      // only buffers the copy engine reads directly can be left in flight
         cudaPointerAttributes at;
         async = true;
-        const float* ptrs[3] = { x, r, which == 0 ? s : x };
+        std::vector<const float*> ptrs; ptrs.push_back(r);
+        for (int d = 0; d < c->PD; ++d) ptrs.push_back(xs[d]);
+        if (which == 0) for (int d = 0; d < c->SD; ++d) ptrs.push_back(ss[d]);
         for (const float* q : ptrs) {
             if (cudaPointerGetAttributes(&at, q) != cudaSuccess) { cudaGetLastError(); async = false; break; }
             if (at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) { async = false; break; }
@@ -241,9 +257,9 @@ static int set_parts(onb_context* c, int which, uint64_t n, const float* x, cons
         ONB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_copy, 0));
         st = c->stream2;
     }
-    for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(p.x[d], x + (size_t)d * n, bytes, cudaMemcpyDefault, st));
+    for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(p.x[d], xs[d], bytes, cudaMemcpyDefault, st));
     ONB_CUDA(cudaMemcpyAsync(p.r, r, bytes, cudaMemcpyDefault, st));
-    if (which == 0) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(p.s[d], s + (size_t)d * n, bytes, cudaMemcpyDefault, st));
+    if (which == 0) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(p.s[d], ss[d], bytes, cudaMemcpyDefault, st));
     if (!async) ONB_CUDA(cudaStreamSynchronize(st));
     else if (which == 1) { ONB_CUDA(cudaEventRecord(c->ev_tgt_ready, c->stream2)); c->tgt_copy_pending = true; }
     p.packed_valid = false;
@@ -251,8 +267,19 @@ static int set_parts(onb_context* c, int which, uint64_t n, const float* x, cons
     return ONB_OK;
 }
 int onb_set_async_inputs(onb_context* c, int on) { if (!c) return ONB_ERR_ARG; c->async_inputs = on != 0; return ONB_OK; }
-int onb_set_sources(onb_context* c, uint64_t n, const float* x, const float* r, const float* s) { return set_parts(c, 0, n, x, r, s); }
-int onb_set_targets(onb_context* c, uint64_t n, const float* x, const float* r) { return set_parts(c, 1, n, x, r, nullptr); }
+int onb_set_sources(onb_context* c, uint64_t n, const float* x, const float* r, const float* s) {
+    const float* xs[ONB_MAX_PD]; const float* ss[ONB_MAX_SD];
+    for (int d = 0; d < ONB_MAX_PD; ++d) xs[d] = x + (size_t)d * n;
+    for (int d = 0; d < ONB_MAX_SD; ++d) ss[d] = s + (size_t)d * n;
+    return set_parts(c, 0, n, xs, r, ss);
+}
+int onb_set_targets(onb_context* c, uint64_t n, const float* x, const float* r) {
+    const float* xs[ONB_MAX_PD];
+    for (int d = 0; d < ONB_MAX_PD; ++d) xs[d] = x + (size_t)d * n;
+    return set_parts(c, 1, n, xs, r, nullptr);
+}
+int onb_set_sources_planes(onb_context* c, uint64_t n, const float* const* x, const float* r, const float* const* s) { return set_parts(c, 0, n, x, r, s); }
+int onb_set_targets_planes(onb_context* c, uint64_t n, const float* const* x, const float* r) { return set_parts(c, 1, n, x, r, nullptr); }
 
 // Parts::random_in_cube(std::mt19937) Parts.hpp:99-109 and wave_strengths :169-176, on the host like the reference
 int onb_driver_inputs(int physics, uint64_t n, int strength_mode, float* x, float* r, float* s) {
@@ -286,7 +313,15 @@ int onb_make_tree_range(onb_context* c, int which, uint64_t lo, uint64_t hi) {
     tm.stop();
     return rc;
 }
-int onb_make_tree(onb_context* c, int which) { return onb_make_tree_range(c, which, 0, ~0ull); }
+int onb_make_tree(onb_context* c, int which) {
+    if (c->comm && c->shard_n > 1) {
+        onb_scratch_reset(c);
+        if (which < 0 || which > 1 || c->parts[which].n == 0) { c->err = "make_tree: set the particles first"; return ONB_ERR_ARG; }
+        ONB_CUDA(cudaSetDevice(c->device));
+        return onb_dist_make_trees(c, which);
+    }
+    return onb_make_tree_range(c, which, 0, ~0ull);
+}
 
 // Both trees at once: the two builds are independent and their top levels are latency bound (grid-wide barriers around
 // short passes), so they are enqueued on two streams and overlap on the device.
@@ -294,7 +329,8 @@ int onb_make_trees_range(onb_context* c, uint64_t slo, uint64_t shi, uint64_t tl
     // one build after the other: on request (diagnostics), and above 5e8 particles, where two concurrent builds would hold
     // 2 x 36 B per particle of scratch at once
     static const bool seq_env = std::getenv("ONB_SEQ_BUILDS") != nullptr;
-    const bool seq_builds = seq_env || std::max(c->parts[0].n, c->parts[1].n) > 500000000u;
+    const bool dist = c->comm && c->shard_n > 1;
+    const bool seq_builds = dist ? onb_dist_sequential_builds(c) : (seq_env || c->mem_mode == ONB_MEM_LEAN || std::max(c->parts[0].n, c->parts[1].n) > 500000000u);
     // a pending asynchronous target copy sits on stream2, where the target build is enqueued behind it: the source
     // build on the context stream need not wait for it (the streams are joined at the end of this call)
     const bool tgt_in_flight = c->tgt_copy_pending && !seq_builds;
@@ -302,6 +338,7 @@ int onb_make_trees_range(onb_context* c, uint64_t slo, uint64_t shi, uint64_t tl
     onb_scratch_reset(c);
     if (c->parts[0].n == 0 || c->parts[1].n == 0) { c->err = "make_trees: set sources and targets first"; return ONB_ERR_ARG; }
     ONB_CUDA(cudaSetDevice(c->device));
+    if (dist) return onb_dist_make_trees(c, -1);        // every rank its own range of both trees (the range arguments are the plan's)
     int rc = onb_alloc_tree(c, c->trees[0], c->parts[0].n, c->block);
     if (rc == ONB_OK) rc = onb_alloc_tree(c, c->trees[1], c->parts[1].n, c->block);
     if (rc) return rc;
@@ -324,6 +361,7 @@ int onb_make_trees_range(onb_context* c, uint64_t slo, uint64_t shi, uint64_t tl
     float ms = 0.f; cudaEventElapsedTime(&ms, e0, e2);
     c->phase_ms["tree"] = ms; c->phase_ms["trees"] = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (c->mem_mode == ONB_MEM_LEAN) onb_scratch_trim(c);
     return rc;
 }
 int onb_make_trees(onb_context* c) { return onb_make_trees_range(c, 0, ~0ull, 0, ~0ull); }
@@ -340,13 +378,6 @@ int onb_set_build_range(onb_context* c, int which, uint64_t lo, uint64_t hi) {
     if (which < 0 || which > 1) return ONB_ERR_ARG;
     DParts& p = c->parts[which];
     p.build_lo = (uint32_t)std::min<uint64_t>(lo, p.n); p.build_hi = (uint32_t)std::min<uint64_t>(hi, p.n);
-    return ONB_OK;
-}
-int onb_shard_range_for(uint64_t n, int block, int rank, int nranks, uint64_t* lo, uint64_t* hi) {
-    if (nranks < 1 || rank < 0 || rank >= nranks || block < 1) return ONB_ERR_ARG;
-    const uint64_t nleaf = (n + block - 1) / block;
-    *lo = std::min<uint64_t>((nleaf * (uint64_t)rank / (uint64_t)nranks) * block, n);
-    *hi = std::min<uint64_t>((nleaf * (uint64_t)(rank + 1) / (uint64_t)nranks) * block, n);
     return ONB_OK;
 }
 int onb_shard_particle_range(const onb_context* c, uint64_t n, int rank, int nranks, uint64_t* lo, uint64_t* hi) {
@@ -370,9 +401,12 @@ int onb_upward(onb_context* c, int which) {
         return ONB_ERR_UNSUPPORTED;
     }
     PhaseTimer tm(c, "upward");
-    int rc = c->legacy ? onb_legacy_equivalents(c, c->parts[which], c->parts[which + 2], c->trees[which])
-                       : onb_bary_upward(c, c->parts[which], c->parts[which + 2], c->trees[which]);
-    if (rc == ONB_OK && which == 0) rc = onb_pack_sources(c, c->parts[2]);
+    int rc;
+    if (c->legacy) rc = onb_legacy_equivalents(c, c->parts[which], c->parts[which + 2], c->trees[which]);
+    else if (which == 0 && c->comm && c->shard_n > 1) rc = onb_dist_upward_sources(c);      // own nodes, exchange, straddling nodes, packing
+    else if (which == 1 && c->shard_n > 1) rc = onb_bary_upward_mode(c, c->parts[1], c->parts[3], c->trees[1], ONB_UP_NEED);   // only the nodes this shard evaluates
+    else rc = onb_bary_upward(c, c->parts[which], c->parts[which + 2], c->trees[which]);
+    if (rc == ONB_OK && which == 0 && !c->parts[2].packed_valid) rc = onb_pack_sources(c, c->parts[2]);
     if (rc == ONB_OK && which == 0 && !c->parts[0].packed_valid) rc = onb_pack_sources(c, c->parts[0]);
     tm.stop();
     return rc;
@@ -393,9 +427,11 @@ int onb_prepare_eval(onb_context* c, int finish, uint64_t tgt_lo, uint64_t tgt_h
     ONB_CUDA(cudaStreamWaitEvent(c->stream2, e0, 0));
     // source side on the context stream
     int rc = ONB_OK;
+    const bool dist = c->comm && c->shard_n > 1;
+    if (dist) finish = 0;       // a communicator's onb_make_trees has completed the node arrays from exchanged leaf records already
     if (finish) rc = onb_tree_finish_from_particles(c, c->parts[0], c->trees[0]);
-    if (rc == ONB_OK) rc = onb_bary_upward(c, c->parts[0], c->parts[2], c->trees[0]);
-    if (rc == ONB_OK) rc = onb_pack_sources(c, c->parts[2]);
+    if (rc == ONB_OK) rc = dist ? onb_dist_upward_sources(c) : onb_bary_upward(c, c->parts[0], c->parts[2], c->trees[0]);
+    if (rc == ONB_OK && !c->parts[2].packed_valid) rc = onb_pack_sources(c, c->parts[2]);
     if (rc == ONB_OK && !c->parts[0].packed_valid) rc = onb_pack_sources(c, c->parts[0]);
     // target side on the second stream
     if (rc == ONB_OK) {
@@ -406,7 +442,7 @@ int onb_prepare_eval(onb_context* c, int finish, uint64_t tgt_lo, uint64_t tgt_h
             p.build_lo = (uint32_t)std::min<uint64_t>(tgt_lo, p.n); p.build_hi = (uint32_t)std::min<uint64_t>(tgt_hi, p.n);
         }
         if (rc == ONB_OK) rc = onb_tree_refine(c, c->parts[1], c->trees[1], false);
-        if (rc == ONB_OK) rc = onb_bary_upward(c, c->parts[1], c->parts[3], c->trees[1]);
+        if (rc == ONB_OK) rc = onb_bary_upward_mode(c, c->parts[1], c->parts[3], c->trees[1], c->shard_n > 1 ? ONB_UP_NEED : ONB_UP_ALL);
         c->cur_stream = nullptr;
     }
     ONB_CUDA(cudaEventRecord(e1, c->stream2));
@@ -417,11 +453,13 @@ int onb_prepare_eval(onb_context* c, int finish, uint64_t tgt_lo, uint64_t tgt_h
     c->phase_ms["prepare"] = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     if (rc == ONB_OK) rc = onb_check_flag(c, "refine (introsort depth limit: libstdc++ heapsort fallback is not restated)");
+    if (rc == ONB_OK) rc = lean_after_prepare(c);
     return rc;
 }
 int onb_zero_vels(onb_context* c) {
+    ONB_CUDA(cudaSetDevice(c->device));
     DParts& t = c->parts[1];
-    for (int d = 0; d < c->OD; ++d) if (t.u[d]) ONB_CUDA(cudaMemsetAsync(t.u[d], 0, (size_t)t.cap * sizeof(float), c->stream));
+    for (int d = 0; d < c->OD; ++d) if (t.u[d]) { int rc = onb_memset_plane(c, t.u[d], (size_t)t.cap, c->stream); if (rc) return rc; }
     return ONB_OK;
 }
 int onb_naive(onb_context* c, uint64_t tskip, float* flops) {
@@ -500,13 +538,16 @@ int onb_get_parts(onb_context* c, int which, float* x, float* r, float* s, float
     if (which < 0 || which > 3) return ONB_ERR_ARG;
     ONB_CUDA(cudaSetDevice(c->device));
     DParts& p = c->parts[which];
-    const size_t n = p.n, bytes = n * sizeof(float);
+    const size_t n = p.n;
     if (n == 0) return ONB_OK;
     { int jrc = onb_join_copies(c); if (jrc) return jrc; }
-    if (x) for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(x + d * n, p.x[d], bytes, cudaMemcpyDefault, c->stream));
-    if (r) ONB_CUDA(cudaMemcpyAsync(r, p.r, bytes, cudaMemcpyDeviceToHost, c->stream));
-    if (s && p.are_sources) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(s + d * n, p.s[d], bytes, cudaMemcpyDeviceToHost, c->stream));
-    if (u && !p.are_sources) for (int d = 0; d < c->OD; ++d) ONB_CUDA(cudaMemcpyAsync(u + d * n, p.u[d], bytes, cudaMemcpyDefault, c->stream));
+    if (which == 0) { int jrc = onb_dist_join_source_planes(c, c->stream); if (jrc) return jrc; }
+    if ((x || r || (s && p.are_sources)) && p.unpacked_released) { c->err = "get_parts: the source planes were released after packing (lean memory mode)"; return ONB_ERR_ARG; }
+    // sparse planes (lean memory mode) are copied where they are backed by memory; the rest of the caller's array is left alone
+    if (x) for (int d = 0; d < c->PD; ++d) ONB_CUDA(onb_copy_plane_to_host(c, x + d * n, p.x[d], 0, n, c->stream));
+    if (r) ONB_CUDA(onb_copy_plane_to_host(c, r, p.r, 0, n, c->stream));
+    if (s && p.are_sources) for (int d = 0; d < c->SD; ++d) ONB_CUDA(onb_copy_plane_to_host(c, s + d * n, p.s[d], 0, n, c->stream));
+    if (u && !p.are_sources) for (int d = 0; d < c->OD; ++d) ONB_CUDA(onb_copy_plane_to_host(c, u + d * n, p.u[d], 0, n, c->stream));
     ONB_CUDA(cudaStreamSynchronize(c->stream));
     if (gidx && p.gidx) {
         std::vector<uint32_t> tmp(n);
@@ -515,33 +556,96 @@ int onb_get_parts(onb_context* c, int which, float* x, float* r, float* s, float
     }
     return ONB_OK;
 }
-
-// tree order -> the caller's order on the device (one scatter per output plane), so that the host only adds
-// contiguous arrays: out[gidx[i]] = u[i]
-__global__ void k_unsort_plane(const float* __restrict__ u, const uint32_t* __restrict__ g, float* __restrict__ out, uint32_t n) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[g[i]] = u[i];
+// the output planes of this context's shard only: u is [OD][n], elements [lo,hi) of every plane are written (the multi-GPU
+// drivers let every rank fill its own part of one shared host array)
+int onb_get_shard_results(onb_context* c, float* u, uint64_t* lo_out, uint64_t* hi_out) {
+    ONB_CUDA(cudaSetDevice(c->device));
+    DParts& p = c->parts[1];
+    uint32_t lo, hi; onb_shard_range(c, &lo, &hi);
+    if (lo_out) *lo_out = lo; if (hi_out) *hi_out = hi;
+    if (!u || hi <= lo) return ONB_OK;
+    for (int d = 0; d < c->OD; ++d) ONB_CUDA(cudaMemcpyAsync(u + (size_t)d * p.n + lo, p.u[d] + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDefault, c->stream));
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    return ONB_OK;
 }
 
-int onb_add_results_original_order(onb_context* c, float* u) {
+// tree order -> the caller's order for ALL output planes in one kernel: out[d][gidx[i]] (+)= u[d][i] for the targets of
+// this context's range. gidx is a permutation, so the += needs no atomics.
+struct UnsortArgs { const float* u[ONB_MAX_OD]; float* out[ONB_MAX_OD]; const uint32_t* g; uint32_t lo, hi; int OD, add; };
+__global__ void k_unsort_planes(const UnsortArgs a) {
+    const uint32_t i = a.lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.hi) return;
+    const uint32_t j = a.g[i];
+    if (a.add) { for (int d = 0; d < a.OD; ++d) a.out[d][j] += a.u[d][i]; }
+    else       { for (int d = 0; d < a.OD; ++d) a.out[d][j] = a.u[d][i]; }
+}
+
+// results of [lo,hi) (what this context evaluated: its shard, inside the range its tree build ordered) added to the caller's
+// planes. Device pointers: one kernel, in place. Host pointers: one scatter kernel into a zeroed device staging area, then
+// plane by plane a bulk copy into a pinned double buffer that overlaps the host's += of the previous plane.
+static int add_results(onb_context* c, float* const* out) {
     ONB_CUDA(cudaSetDevice(c->device));
     DParts& p = c->parts[1];
     const size_t n = p.n;
     if (!p.gidx) { c->err = "targets have no tree order yet"; return ONB_ERR_ARG; }
     { int jrc = onb_join_copies(c); if (jrc) return jrc; }
     onb_scratch_reset(c);
-    float* tmp = nullptr;
-    ONB_CUDA(onb_dmalloc(c, (void**)&tmp, n * sizeof(float)));
-    std::vector<float> h(n);
+    uint32_t lo, hi; onb_shard_range(c, &lo, &hi);
+    lo = std::max(lo, p.build_lo); hi = std::min(hi, p.build_hi);      // a range-restricted build ordered (and indexed) only its own range
+    if (hi <= lo) return ONB_OK;
+    bool all_device = true;
     for (int d = 0; d < c->OD; ++d) {
-        k_unsort_plane<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(p.u[d], p.gidx, tmp, (uint32_t)n); ONB_LAUNCH(c);
-        ONB_CUDA(cudaMemcpyAsync(h.data(), tmp, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, out[d]) != cudaSuccess) { cudaGetLastError(); all_device = false; break; }
+        if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) { all_device = false; break; }
+    }
+    UnsortArgs a; a.g = p.gidx; a.lo = lo; a.hi = hi; a.OD = c->OD;
+    for (int d = 0; d < ONB_MAX_OD; ++d) { a.u[d] = p.u[d]; a.out[d] = nullptr; }
+    const unsigned grid = (unsigned)((hi - lo + 255) / 256);
+    if (all_device) {
+        for (int d = 0; d < c->OD; ++d) a.out[d] = out[d];
+        a.add = 1;
+        k_unsort_planes<<<grid, 256, 0, c->stream>>>(a); ONB_LAUNCH(c);
+        ONB_CUDA(cudaGetLastError());
         ONB_CUDA(cudaStreamSynchronize(c->stream));
-        float* ud = u + (size_t)d * n;
+        return ONB_OK;
+    }
+    float* tmp = nullptr;
+    ONB_CUDA(onb_dmalloc(c, (void**)&tmp, (size_t)c->OD * n * sizeof(float)));
+    const bool partial = (size_t)(hi - lo) < n;
+    if (partial) ONB_CUDA(cudaMemsetAsync(tmp, 0, (size_t)c->OD * n * sizeof(float), c->stream));
+    for (int d = 0; d < c->OD; ++d) a.out[d] = tmp + (size_t)d * n;
+    a.add = 0;
+    k_unsort_planes<<<grid, 256, 0, c->stream>>>(a); ONB_LAUNCH(c);
+    ONB_CUDA(cudaGetLastError());
+    if (c->h_stage_cap < 2 * n) {
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr; c->h_stage_cap = 0;
+        ONB_CUDA(cudaMallocHost((void**)&c->h_stage, 2 * n * sizeof(float)));
+        c->h_stage_cap = 2 * n;
+    }
+    if (!c->ev_stage[0]) { ONB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[0], cudaEventDisableTiming)); ONB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[1], cudaEventDisableTiming)); }
+    auto issue = [&](int d) -> cudaError_t {
+        cudaError_t e = cudaMemcpyAsync(c->h_stage + (size_t)(d & 1) * n, tmp + (size_t)d * n, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+        return e != cudaSuccess ? e : cudaEventRecord(c->ev_stage[d & 1], c->stream);
+    };
+    ONB_CUDA(issue(0));
+    for (int d = 0; d < c->OD; ++d) {
+        ONB_CUDA(cudaEventSynchronize(c->ev_stage[d & 1]));
+        if (d + 1 < c->OD) ONB_CUDA(issue(d + 1));                     // the other half of the double buffer is free: plane d-1 was consumed
+        const float* __restrict__ h = c->h_stage + (size_t)(d & 1) * n;
+        float* __restrict__ ud = out[d];
         for (size_t i = 0; i < n; ++i) ud[i] += h[i];                                     // interface3dvortgrads.cpp:384-395
     }
     return ONB_OK;
 }
+
+int onb_add_results_original_order(onb_context* c, float* u) {
+    float* planes[ONB_MAX_OD];
+    for (int d = 0; d < c->OD; ++d) planes[d] = u + (size_t)d * c->parts[1].n;
+    return add_results(c, planes);
+}
+int onb_add_results_planes(onb_context* c, float* const* out) { return add_results(c, out); }
 
 int onb_tree_shape(const onb_context* c, int which, int* levels, int* numnodes) {
     if (which < 0 || which > 1) return ONB_ERR_ARG;
@@ -577,6 +681,14 @@ int onb_get_tree(onb_context* c, int which, float* x, float* nc, float* ns, floa
         if (epoffset) epoffset[i] = nonleaf ? (uint64_t)i * c->ebs : 0;                   // BarycentricLagrange.hpp:289
         if (epnum) epnum[i] = nonleaf ? (en.empty() ? (uint64_t)c->num_eqps : (uint64_t)en[i]) : 0;
     }
+    return ONB_OK;
+}
+
+int onb_device_memory(onb_context* c, uint64_t* used, uint64_t* total) {
+    ONB_CUDA(cudaSetDevice(c->device));
+    size_t f = 0, t = 0;
+    ONB_CUDA(cudaMemGetInfo(&f, &t));
+    if (used) *used = t - f; if (total) *total = t;
     return ONB_OK;
 }
 
@@ -644,6 +756,7 @@ int onb_load_tree(onb_context* c, int which, int levels, const float* x, const f
         std::vector<uint32_t> id(p.n); for (uint32_t i = 0; i < p.n; ++i) id[i] = i;
         ONB_CUDA(cudaMemcpy(p.gidx, id.data(), (size_t)p.n * 4, cudaMemcpyHostToDevice));
     }
+    c->parts[which].build_lo = 0; c->parts[which].build_hi = c->parts[which].n;
     t.built = true;
     return ONB_OK;
 }

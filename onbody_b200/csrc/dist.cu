@@ -1,0 +1,202 @@
+/*
+ * dist.cu - the phases of the hot path when a communicator is attached (comm.cu): one context per GPU, every context holds
+ * the same inputs, the TARGETS are sharded by contiguous leaf ranges and the SOURCES end up replicated (north_star).
+ *
+ * What crosses NVLink, per step (N particles, R ranks, L tree levels):
+ *   leaf records   13 floats per leaf of both trees, one in-place all-gather each (0.4 B per particle)   tree.cu k_leafrec_*
+ *   source planes  x[PD], r, s[SD]: each rank's tree-ordered range, one grouped in-place all-gather       (20 B per particle)
+ *   eq. strengths  s[SD] of the equivalent sources every rank anterpolated for the nodes inside its range,
+ *                  grouped in-place broadcasts, one per (level, owner)                                    (4 B per particle)
+ * Target particles are NOT exchanged: a rank sorts, refines and evaluates only its own leaves, and the node arrays of the
+ * whole target tree (the ancestors' centres enter the dual-tree MAC, ongrav3d.cpp:338) follow from the leaf records alone.
+ *
+ * Everything a rank does on its own range needs no communication, so the collectives overlap with it:
+ *   stream  : source range build -> own leaf records ............ node arrays -> upward pass of the own nodes .. positions, pack -> straddling nodes -> pack
+ *   stream2 : target range build -> own leaf records ............ node arrays -> in-leaf refinement -> equivalent target points of the needed nodes
+ *   comm    :                      gather(src rec) gather(tgt rec) gather(source planes) ...................... bcast(eq. strengths)
+ * Results are bit-identical to the single-GPU run for every rank count (tools/check_multi.py, tests/test_gpu_dist.py):
+ * per-leaf sums, per-node anterpolation and per-target accumulation orders do not depend on who computes them.
+ */
+#include "onb_internal.h"
+#include <algorithm>
+#include <cstdlib>
+
+int onb_comm_allgather(onb_context* c, const std::vector<void*>& bufs, const std::vector<size_t>& chunk_bytes);
+int onb_comm_bcast_ranges(onb_context* c, const std::vector<void*>& ptrs, const std::vector<size_t>& bytes, const std::vector<int>& owner);
+cudaStream_t onb_comm_stream(const onb_context* c);
+
+static int ensure_plan(onb_context* c, int which) {
+    const int rc = onb_plan_make(c->plan[which], c->parts[which].n, c->block, c->shard_n, c->shard_rank);
+    if (rc) c->err = "cannot plan the multi-GPU partition (rank count above ONB_MAX_RANKS, or an irregular tree shape)";
+    return rc;
+}
+
+int onb_plan_upload_shared(onb_context* c, int which) {
+    int rc = ensure_plan(c, which); if (rc) return rc;
+    const ShardPlan& P = c->plan[which];
+    const uint64_t key = c->plan_key(which);
+    if (c->d_shared[which] && c->shared_key[which] == key) return ONB_OK;
+    if (c->d_shared[which]) { cudaFree(c->d_shared[which]); c->d_shared[which] = nullptr; }
+    std::vector<uint32_t> h((size_t)P.levels * P.nranks, 0u);
+    for (int l = 0; l < P.levels; ++l) {
+        if (P.shared[l].size() > (size_t)P.nranks) { c->err = "plan: more straddling nodes than ranks on one level"; return ONB_ERR_UNSUPPORTED; }
+        for (size_t k = 0; k < P.shared[l].size(); ++k) h[(size_t)l * P.nranks + k] = P.shared[l][k];
+    }
+    ONB_CUDA(cudaMalloc((void**)&c->d_shared[which], h.size() * 4 + 4));
+    ONB_CUDA(cudaMemcpy(c->d_shared[which], h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    c->shared_key[which] = key;
+    return ONB_OK;
+}
+
+// one build after the other: on request, and in the lean memory mode (one build's scratch at a time)
+bool onb_dist_sequential_builds(const onb_context* c) {
+    static const bool seq_env = std::getenv("ONB_SEQ_BUILDS") != nullptr;
+    return seq_env || c->mem_mode == ONB_MEM_LEAN;
+}
+
+namespace {
+
+enum { EV_E0 = 400, EV_BUILT0, EV_BUILT1, EV_REC0, EV_REC1, EV_UP, EV_EQ, EV_JOIN, EV_END };
+
+struct RecBuf { float* p = nullptr; size_t chunk_bytes = 0; };
+
+// range-restricted build of one tree on ONB_ST(c) (no node summaries) + the records of the rank's own leaves
+int dist_build(onb_context* c, int which, RecBuf& rb) {
+    const ShardPlan& P = c->plan[which];
+    DParts& p = c->parts[which]; DTree& t = c->trees[which];
+    const int K = onb_leafrec_floats(c, p.are_sources);
+    const size_t leaves_per_rank = (size_t)(P.chunk / (uint64_t)c->block);
+    rb.chunk_bytes = leaves_per_rank * K * sizeof(float);
+    ONB_CUDA(onb_dmalloc(c, (void**)&rb.p, rb.chunk_bytes * (size_t)P.nranks));
+    if (P.hi > P.lo) {
+        int rc = onb_tree_build(c, p, t, (uint32_t)P.lo, (uint32_t)P.hi, false); if (rc) return rc;
+        rc = onb_tree_leaf_records(c, p, t, (uint32_t)(P.lo / c->block), (uint32_t)((P.hi + c->block - 1) / c->block), rb.p); if (rc) return rc;
+    } else {
+        // a rank without leaves (fewer leaves than ranks) still needs the shape arrays of the tree: a build of nothing
+        int rc = onb_tree_build(c, p, t, 0, std::min<uint32_t>(p.n, (uint32_t)c->block), false); if (rc) return rc;
+        p.build_lo = p.build_hi = 0;
+    }
+    return ONB_OK;
+}
+
+int source_plane_list(onb_context* c, std::vector<void*>& bufs, std::vector<size_t>& chunks) {
+    DParts& p = c->parts[0];
+    const size_t cb = (size_t)c->plan[0].chunk * sizeof(float);
+    for (int d = 0; d < c->PD; ++d) { bufs.push_back(p.x[d]); chunks.push_back(cb); }
+    bufs.push_back(p.r); chunks.push_back(cb);
+    for (int d = 0; d < c->SD; ++d) { bufs.push_back(p.s[d]); chunks.push_back(cb); }
+    if ((uint64_t)p.cap < c->plan[0].chunk * (uint64_t)c->shard_n) { c->err = "source planes are too short for the in-place all-gather"; return ONB_ERR_ARG; }
+    return ONB_OK;
+}
+
+}  // namespace
+
+// both trees (which = -1) or one: range builds, leaf-record exchange, node arrays; the all-gather of the source planes is
+// enqueued as well and, for which = -1, left in flight (its consumers wait for c->ev_src_planes)
+int onb_dist_make_trees(onb_context* c, int which) {
+    const bool both = which < 0;
+    const bool do_src = both || which == 0, do_tgt = both || which == 1;
+    int rc;
+    if (do_src && (rc = ensure_plan(c, 0))) return rc;
+    if (do_tgt && (rc = ensure_plan(c, 1))) return rc;
+    if (do_src && (rc = onb_alloc_tree(c, c->trees[0], c->parts[0].n, c->block))) return rc;
+    if (do_tgt && (rc = onb_alloc_tree(c, c->trees[1], c->parts[1].n, c->block))) return rc;
+    const bool seq = !both || onb_dist_sequential_builds(c);
+    cudaStream_t s1 = c->stream, s2 = seq ? c->stream : c->stream2, sc = onb_comm_stream(c);
+    ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_E0), s1));
+    if (s2 != s1) ONB_CUDA(cudaStreamWaitEvent(s2, onb_cached_event(c, EV_E0), 0));
+    ONB_CUDA(cudaStreamWaitEvent(sc, onb_cached_event(c, EV_E0), 0));
+    RecBuf rb0, rb1;
+    c->concurrent_builds = both && !seq;
+    if (do_src) {
+        rc = dist_build(c, 0, rb0); if (rc) { c->concurrent_builds = false; return rc; }
+        ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_BUILT0), s1));
+    }
+    auto gather_src_rec = [&]() -> int {
+        ONB_CUDA(cudaStreamWaitEvent(sc, onb_cached_event(c, EV_BUILT0), 0));
+        int r = onb_comm_allgather(c, {rb0.p}, {rb0.chunk_bytes}); if (r) return r;
+        ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_REC0), sc));
+        return ONB_OK;
+    };
+    auto gather_src_planes = [&]() -> int {
+        std::vector<void*> bufs; std::vector<size_t> chunks;
+        int r = source_plane_list(c, bufs, chunks); if (r) return r;
+        r = onb_comm_allgather(c, bufs, chunks); if (r) return r;
+        ONB_CUDA(cudaEventRecord(c->ev_src_planes, sc));
+        c->src_planes_pending = true;
+        return ONB_OK;
+    };
+    if (do_src && seq) { if ((rc = gather_src_rec())) return rc; if ((rc = gather_src_planes())) return rc; }   // under the target build
+    if (do_tgt) {
+        if (s2 != s1) { c->cur_stream = s2; c->cur_stats_off = 8; }
+        rc = dist_build(c, 1, rb1);
+        c->cur_stream = nullptr; c->cur_stats_off = 0; c->concurrent_builds = false;
+        if (rc) return rc;
+        ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_BUILT1), s2));
+    }
+    c->concurrent_builds = false;
+    if (do_src && !seq) { if ((rc = gather_src_rec())) return rc; }
+    if (do_tgt) {
+        ONB_CUDA(cudaStreamWaitEvent(sc, onb_cached_event(c, EV_BUILT1), 0));
+        std::vector<void*> bufs{rb1.p}; std::vector<size_t> chunks{rb1.chunk_bytes};
+        if (c->has_tr) { bufs.push_back(c->parts[1].r); chunks.push_back((size_t)c->plan[1].chunk * sizeof(float)); }   // target radii enter the 2-D kernel
+        rc = onb_comm_allgather(c, bufs, chunks); if (rc) return rc;
+        ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_REC1), sc));
+    }
+    if (do_src && !seq) { if ((rc = gather_src_planes())) return rc; }
+    // node arrays from the complete records
+    if (do_src) {
+        ONB_CUDA(cudaStreamWaitEvent(s1, onb_cached_event(c, EV_REC0), 0));
+        rc = onb_tree_finish_from_records(c, c->parts[0], c->trees[0], rb0.p); if (rc) return rc;
+    }
+    if (do_tgt) {
+        ONB_CUDA(cudaStreamWaitEvent(s2, onb_cached_event(c, EV_REC1), 0));
+        if (s2 != s1) c->cur_stream = s2;
+        rc = onb_tree_finish_from_records(c, c->parts[1], c->trees[1], rb1.p);
+        c->cur_stream = nullptr;
+        if (rc) return rc;
+    }
+    if (s2 != s1) { ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_JOIN), s2)); ONB_CUDA(cudaStreamWaitEvent(s1, onb_cached_event(c, EV_JOIN), 0)); }
+    if (!both && do_src) {      // the separate-call sequence: complete when the call returns
+        ONB_CUDA(cudaStreamWaitEvent(s1, c->ev_src_planes, 0)); c->src_planes_pending = false;
+    }
+    ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_END), s1));
+    ONB_CUDA(cudaEventSynchronize(onb_cached_event(c, EV_END)));
+    float ms = 0.f; cudaEventElapsedTime(&ms, onb_cached_event(c, EV_E0), onb_cached_event(c, EV_END));
+    c->phase_ms["tree"] = ms; if (both) c->phase_ms["trees"] = ms;
+    if (c->mem_mode == ONB_MEM_LEAN) onb_scratch_trim(c);       // the build scratch (~40 B per particle) goes back to the driver
+    return ONB_OK;
+}
+
+// make the stream wait for the all-gather of the source planes if it is still in flight
+int onb_dist_join_source_planes(onb_context* c, cudaStream_t st) {
+    if (c->src_planes_pending) { ONB_CUDA(cudaStreamWaitEvent(st, c->ev_src_planes, 0)); if (st == c->stream) c->src_planes_pending = false; }
+    return ONB_OK;
+}
+
+// barycentric upward pass of the source tree, on c->stream: own nodes -> exchange of their strengths (comm stream) while the
+// replicated positions pass and the packing of the real sources run -> the few nodes that straddle rank boundaries -> packing
+int onb_dist_upward_sources(onb_context* c) {
+    DParts& p = c->parts[0]; DParts& ep = c->parts[2]; DTree& t = c->trees[0];
+    int rc = ensure_plan(c, 0); if (rc) return rc;
+    const ShardPlan& P = c->plan[0];
+    cudaStream_t s1 = c->stream, sc = onb_comm_stream(c);
+    rc = onb_bary_upward_mode(c, p, ep, t, ONB_UP_OWN); if (rc) return rc;
+    ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_UP), s1));
+    ONB_CUDA(cudaStreamWaitEvent(sc, onb_cached_event(c, EV_UP), 0));
+    std::vector<void*> ptrs; std::vector<size_t> bytes; std::vector<int> owner;
+    for (int l = 0; l + 1 < P.levels; ++l)
+        for (int r = 0; r < P.nranks; ++r) {
+            const uint32_t a = P.all_own_lo[(size_t)l * P.nranks + r], b = P.all_own_hi[(size_t)l * P.nranks + r];
+            if (b <= a) continue;
+            for (int d = 0; d < c->SD; ++d) { ptrs.push_back(ep.s[d] + (size_t)a * c->ebs); bytes.push_back((size_t)(b - a) * c->ebs * sizeof(float)); owner.push_back(r); }
+        }
+    rc = onb_comm_bcast_ranges(c, ptrs, bytes, owner); if (rc) return rc;
+    ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_EQ), sc));
+    rc = onb_dist_join_source_planes(c, s1); if (rc) return rc;
+    rc = onb_bary_upward_mode(c, p, ep, t, ONB_UP_POS); if (rc) return rc;          // needs r of every node's first particle: after the plane gather
+    if (!p.packed_valid) { rc = onb_pack_sources(c, p); if (rc) return rc; }
+    ONB_CUDA(cudaStreamWaitEvent(s1, onb_cached_event(c, EV_EQ), 0));
+    rc = onb_bary_upward_mode(c, p, ep, t, ONB_UP_SHARED); if (rc) return rc;
+    return onb_pack_sources(c, ep);
+}

@@ -23,6 +23,22 @@
 #define ONB_MAX_SD 3
 #define ONB_MAX_OD 12
 #define ONB_MAX_ORDER 20
+#define ONB_MAX_RANKS 16
+
+// multi-GPU partition derived from the tree shape alone (plan.cu)
+struct ShardPlan {
+    bool valid = false;
+    uint64_t n = 0, lo = 0, hi = 0, chunk = 0;      // particles; this rank's range; particles per rank (leaf aligned, equal for all ranks)
+    int block = 0, nranks = 1, rank = 0, levels = 0;
+    std::vector<uint32_t> own_lo, own_hi;           // per level: node ids [own_lo, own_hi) completely inside this rank's range
+    std::vector<uint32_t> need_lo, need_hi;         // per level: node ids overlapping this rank's range
+    std::vector<uint32_t> all_own_lo, all_own_hi;   // [level * nranks + r]: the same for every rank
+    std::vector<std::vector<uint32_t>> shared;      // per level: non-leaf nodes straddling a rank boundary
+};
+int onb_plan_levels(uint64_t n, int block);
+uint64_t onb_shard_chunk(uint64_t n, int block, int nranks);
+int onb_plan_make(ShardPlan& P, uint64_t n, int block, int nranks, int rank);
+struct OnbComm;
 
 struct DParts {
     uint32_t n = 0;
@@ -44,6 +60,9 @@ struct DParts {
     float*  pk2 = nullptr;
     bool packed_valid = false;
     uint32_t build_lo = 0, build_hi = 0;     // particle range the last tree build was restricted to
+    uint64_t sparse_key = 0;                 // != 0: the output planes (and, for equivalent targets, all planes) are sparse, mapped for this partition
+    bool unpacked_released = false;          // lean memory mode: x/r/s were freed after packing (sources only)
+    uint32_t u_lo = 0, u_hi = 0;             // element range of the output planes that is backed by memory (sparse planes: the shard)
 };
 
 struct DTree {
@@ -112,8 +131,24 @@ struct onb_context {
     cudaStream_t stream2 = nullptr, cur_stream = nullptr;   // second stream for building both trees concurrently
     int cur_stats_off = 0;
     bool concurrent_builds = false;
-    std::vector<uint64_t> dtt_sizes;      // per level: interaction / deferred list sizes of the last dual-tree evaluation
-    bool dtt_sizes_valid = false;
+    // dual-tree lists: one persistent pool, bump-allocated per level on the device (traverse.cu); grown when a pass overflows
+    uint32_t* dtt_pool = nullptr; uint32_t dtt_pool_cap = 0; uint64_t dtt_pool_want = 0;
+    uint32_t dtt_qcap = 2048;             // per-warp FIFO of opened source nodes, x8 when a pass overflows it
+    std::vector<cudaEvent_t> ev_cache;    // timing / ordering events, created once
+    float* h_stage = nullptr; size_t h_stage_cap = 0; cudaEvent_t ev_stage[2] = {nullptr, nullptr};   // pinned double buffer of the result read-back
+    // sparse planes (mem.cu): full virtual extent, physical memory only under the ranges this rank touches
+    struct Sparse { char* base = nullptr; size_t va = 0; std::vector<size_t> off, len; std::vector<unsigned long long> handle; };
+    std::map<void*, Sparse> sparse;
+    int mem_mode = 0;                     // ONB_MEM_NORMAL / ONB_MEM_LEAN
+    // multi-GPU (comm.cu, dist.cu): communicator, its stream, the partition plans of the two trees
+    OnbComm* comm = nullptr;
+    ShardPlan plan[2];
+    uint32_t* d_shared[2] = {nullptr, nullptr};   // device copy of plan[which].shared, [levels * nranks]
+    uint64_t shared_key[2] = {0, 0};
+    // identifies the partition a sparse allocation / an uploaded plan belongs to (never 0)
+    uint64_t plan_key(int which) const { return plan_key_for(parts[which].n); }
+    uint64_t plan_key_for(uint64_t n) const { return ((n * 131u + (uint64_t)block) * 131u + (uint64_t)shard_n) * 131u + (uint64_t)shard_rank + 1u; }
+    cudaEvent_t ev_src_planes = nullptr; bool src_planes_pending = false;   // the source-plane all-gather may outlive onb_make_trees
     // opt-in asynchronous input copies (onb_set_async_inputs): the target planes arrive on stream2
     bool async_inputs = false, tgt_copy_pending = false;
     cudaEvent_t ev_copy = nullptr, ev_tgt_ready = nullptr;
@@ -135,8 +170,12 @@ int onb_join_copies(onb_context* c);   // make the context stream wait for a pen
 cudaError_t onb_dmalloc(onb_context* c, void** p, size_t bytes);
 static inline void onb_dfree(onb_context*, void*) {}
 void onb_scratch_reset(onb_context* c);
+void onb_scratch_trim(onb_context* c);
 static inline cudaError_t onb_pmalloc(onb_context*, void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 4); }
-static inline void onb_pfree(onb_context*, void* p) { if (p) cudaFree(p); }
+void onb_pfree(onb_context* c, void* p);
+cudaError_t onb_sparse_alloc(onb_context* c, void** p, size_t total_bytes, const std::vector<std::pair<size_t, size_t>>& ranges, cudaStream_t st);
+const onb_context::Sparse* onb_sparse_info(const onb_context* c, const void* p);
+cudaError_t onb_copy_plane_to_host(onb_context* c, float* dst, const float* src, size_t first, size_t count, cudaStream_t st);
 
 static inline PartsView view_of(const DParts& p) {
     PartsView v; v.n = p.n;
@@ -181,10 +220,15 @@ void onb_free_tree(onb_context* c, DTree& t);
 int onb_check_flag(onb_context* c, const char* what);
 void onb_shard_range(const onb_context* c, uint32_t* lo, uint32_t* hi);   // particle index range of this context's target shard
 // tree.cu
-int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t bhi);
+int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t bhi, bool finish = true);
+int onb_leafrec_floats(const onb_context* c, bool are_sources);
+int onb_tree_leaf_records(onb_context* c, DParts& p, DTree& t, uint32_t leaf0, uint32_t leaf1, float* rec);
+int onb_tree_finish_from_records(onb_context* c, DParts& p, DTree& t, const float* rec);
 int onb_tree_finish_from_particles(onb_context* c, DParts& p, DTree& t);
 int onb_tree_refine(onb_context* c, DParts& p, DTree& t, bool check_now = true);
 // bary.cu
+enum { ONB_UP_ALL = 0, ONB_UP_OWN = 1, ONB_UP_SHARED = 2, ONB_UP_POS = 3, ONB_UP_NEED = 4 };
+int onb_bary_upward_mode(onb_context* c, DParts& p, DParts& ep, DTree& t, int mode);
 int onb_bary_upward(onb_context* c, DParts& p, DParts& ep, DTree& t);
 int onb_bary_downward_level(onb_context* c, int level);
 int onb_legacy_equivalents(onb_context* c, DParts& p, DParts& ep, DTree& t);
@@ -200,7 +244,8 @@ struct WorkList {
     uint32_t node_base = 0;
     uint32_t* start = nullptr;     // nitems+1
     uint32_t* entries = nullptr;
-    uint64_t nentries = 0;
+    uint64_t nentries = 0;         // allocated entries (reads are clamped to it)
+    const uint32_t* ebase = nullptr;   // optional device-resident offset of the list inside `entries`
 };
 int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tgt_which_box, bool accumulate, uint32_t nsplit = 1);
 void onb_free_worklist(onb_context* c, WorkList& wl);
@@ -208,5 +253,14 @@ void onb_free_worklist(onb_context* c, WorkList& wl);
 int onb_lists_boxwise(onb_context* c, float theta, WorkList& wl);
 int onb_run_treecode2(onb_context* c, float theta, int variant);   // fused pointwise traversal + pair kernels (variant 1 = treecode1)
 int onb_run_fastsumm(onb_context* c, float theta);
+void onb_level_span(onb_context* c, int level, uint32_t* node0, uint32_t* count);
+// dist.cu / comm.cu
+int onb_plan_upload_shared(onb_context* c, int which);
+bool onb_dist_sequential_builds(const onb_context* c);
+int onb_dist_make_trees(onb_context* c, int which);
+int onb_dist_join_source_planes(onb_context* c, cudaStream_t st);
+int onb_dist_upward_sources(onb_context* c);
+cudaEvent_t onb_cached_event(onb_context* c, size_t i);
+int onb_memset_plane(onb_context* c, float* p, size_t count, cudaStream_t st);
 // scan.cu
 int onb_exclusive_scan_u32(onb_context* c, const uint32_t* in, uint32_t* out, uint32_t n, uint64_t* total);

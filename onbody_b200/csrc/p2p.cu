@@ -112,8 +112,15 @@ struct P2PArgs {
     const uint32_t* item_node; const uint32_t* start; const uint32_t* entries;
     const uint32_t* s_epnum;        // legacy equivalents: per source node count (null = num_eqps everywhere)
     float* partial;                 // nsplit > 1: [item][segment][OD][128] partial sums, reduced in segment order by k_p2p_reduce
+    const uint32_t* ebase;          // device-resident offset of this work list inside `entries` (dual tree: the level's pool base), or null
     uint32_t block, ebs, num_eqps, node_base, nentries, nsplit;
 };
+// [e0, e1) of work item w, clamped to the allocated entries (a dual-tree pass whose pool overflowed is discarded, not faulted)
+__device__ __forceinline__ void item_range(const P2PArgs& a, uint32_t w, uint32_t& e0, uint32_t& e1) {
+    const unsigned long long eb = a.ebase ? (unsigned long long)*a.ebase : 0ull;
+    e0 = (uint32_t)min(eb + a.start[w], (unsigned long long)a.nentries);
+    e1 = (uint32_t)min(eb + a.start[w + 1], (unsigned long long)a.nentries);
+}
 
 __device__ __forceinline__ TileRef decode_entry(const P2PArgs& a, uint32_t entry) {
     TileRef t;
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__
     // nsplit > 1 (under-filled launches of the upper dual-tree levels, fast arithmetic only): the item's list is cut into
     // nsplit contiguous segments, one CTA each, partial sums go to a[].partial and are added in segment order afterwards
     const uint32_t w = blockIdx.x / a.nsplit, seg = blockIdx.x - w * a.nsplit;
-    uint32_t e0 = min(a.start[w], a.nentries), e1 = min(a.start[w + 1], a.nentries);   // never read past the allocated list
+    uint32_t e0, e1; item_range(a, w, e0, e1);   // never read past the allocated list
     if (e0 >= e1) return;
     if (a.nsplit > 1) {
         const uint32_t len = e1 - e0;
@@ -242,7 +249,7 @@ __global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__
 template <int OD>
 __global__ void __launch_bounds__(128) k_p2p_reduce(const __grid_constant__ P2PArgs a) {
     const uint32_t w = blockIdx.x, slot = threadIdx.x;
-    const uint32_t e0 = min(a.start[w], a.nentries), e1 = min(a.start[w + 1], a.nentries);
+    uint32_t e0, e1; item_range(a, w, e0, e1);
     if (e0 >= e1) return;
     const uint32_t T = a.item_node ? a.item_node[w] : a.node_base + w;
     const uint32_t tn = a.t_num[T];
@@ -266,6 +273,7 @@ struct DirectArgs {
     const float4* s_pk0; const float4* s_pk1; const float* s_pk2;
     float* partial;                // [nsplit][OD][nt_eff] when nsplit > 1
     uint32_t nsrc, ntarg, tskip, nt_eff, nsplit, tiles_per_split;
+    uint32_t k0;                   // first sample handled here (a sharded context evaluates the samples inside its target range)
 };
 
 template <int PHYS, bool STRICT>
@@ -273,9 +281,9 @@ __global__ void __launch_bounds__(128) k_p2p_direct(const __grid_constant__ Dire
     constexpr int OD = Phys<PHYS>::OD;
     __shared__ TileSmem<PHYS> sm;
     const int tid = threadIdx.x;
-    const uint32_t k = blockIdx.x * 128u + tid;
+    const uint32_t k = blockIdx.x * 128u + tid;          // sample index relative to k0
     const bool valid = k < a.nt_eff;
-    const uint32_t ti = valid ? k * a.tskip : 0u;
+    const uint32_t ti = (a.k0 + (valid ? k : 0u)) * a.tskip;
     Tgt tg;
     tg.x = a.tx[0][ti]; tg.y = a.tx[1][ti]; tg.z = Phys<PHYS>::PD > 2 ? a.tx[2][ti] : 0.f; tg.r2 = 0.f;
     if (Phys<PHYS>::TR) { const float r = a.tr[ti]; tg.r2 = __fmul_rn(r, r); }
@@ -317,7 +325,7 @@ __global__ void __launch_bounds__(128) k_p2p_direct(const __grid_constant__ Dire
 __global__ void k_reduce_partials(DirectArgs a, int OD) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.nt_eff) return;
-    const uint32_t ti = k * a.tskip;
+    const uint32_t ti = (a.k0 + k) * a.tskip;
     for (int d = 0; d < OD; ++d) {
         float v = a.tu[d][ti];
         for (uint32_t y = 0; y < a.nsplit; ++y) v += a.partial[((size_t)y * OD + d) * a.nt_eff + k];
@@ -357,12 +365,10 @@ void launch_lists(onb_context* c, const P2PArgs& a, uint32_t nitems) {
     // time ONE warp needs for the longest list, so spread each target block over more warps there (fewer targets per
     // thread). Per-target sums do not depend on the blocking, results stay bit-identical.
     if (!(g_p2p_tpt & 15) && c->arith != ONB_ARITH_STRICT) {
-        static uint32_t t1 = 0, t2 = 0;      // launch sizes up to which TPT = 1 / TPT = 2 are used (tunable: ONB_TPT1_MAX, ONB_TPT2_MAX)
-        if (!t1) {
-            t1 = (uint32_t)c->sm_count * 8u; t2 = 4u * t1;
-            if (const char* e = std::getenv("ONB_TPT1_MAX")) t1 = (uint32_t)std::max(1, atoi(e));
-            if (const char* e = std::getenv("ONB_TPT2_MAX")) t2 = (uint32_t)std::max(1, atoi(e));
-        }
+        // launch sizes up to which TPT = 1 / TPT = 2 are used (tunable: ONB_TPT1_MAX, ONB_TPT2_MAX; otherwise from this device's SM count)
+        static const int e1 = std::getenv("ONB_TPT1_MAX") ? std::max(1, atoi(std::getenv("ONB_TPT1_MAX"))) : 0;
+        static const int e2 = std::getenv("ONB_TPT2_MAX") ? std::max(1, atoi(std::getenv("ONB_TPT2_MAX"))) : 0;
+        const uint32_t t1 = e1 ? (uint32_t)e1 : (uint32_t)c->sm_count * 8u, t2 = e2 ? (uint32_t)e2 : 4u * (uint32_t)c->sm_count * 8u;
         const uint32_t ncta = nitems * a.nsplit;
         if (ncta <= t1) tpt = 1; else if (ncta <= t2 && tpt > 2) tpt = 2;
     }
@@ -385,6 +391,8 @@ void launch_direct(onb_context* c, const DirectArgs& a) {
 int onb_pack_sources(onb_context* c, DParts& p) {
     if (!p.are_sources) { c->err = "pack: not a source set"; return ONB_ERR_ARG; }
     if (p.n == 0) return ONB_OK;
+    if (p.unpacked_released) { c->err = "pack: the source planes were released (lean memory mode): set the sources again"; return ONB_ERR_ARG; }
+    if (&p == &c->parts[0]) { int rc = onb_dist_join_source_planes(c, ONB_ST(c)); if (rc) return rc; }     // a multi-GPU plane gather may still be in flight
     const uint32_t cap = p.cap;
     const int T = 256; const uint32_t G = (cap + T - 1) / T;
     PartsView v = view_of(p);
@@ -420,7 +428,7 @@ int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tg
     a.item_node = wl.tgt_node; a.start = wl.start; a.entries = wl.entries;
     a.block = c->block; a.ebs = c->ebs; a.num_eqps = c->num_eqps; a.node_base = wl.node_base; a.nentries = (uint32_t)wl.nentries;
     a.s_epnum = c->legacy ? c->d_epnum : nullptr;
-    a.nsplit = nsplit; a.partial = nullptr;
+    a.nsplit = nsplit; a.partial = nullptr; a.ebase = wl.ebase;
     if (nsplit > 1) ONB_CUDA(onb_dmalloc(c, (void**)&a.partial, (size_t)wl.nitems * nsplit * c->OD * 128u * sizeof(float)));
     switch (c->physics) {
         case ONB_GRAV3D:     launch_lists<ONB_GRAV3D>(c, a, wl.nitems); break;
@@ -445,7 +453,13 @@ int onb_p2p_direct(onb_context* c, uint64_t tskip) {
     for (int d = 0; d < ONB_MAX_OD; ++d) a.tu[d] = targs.u[d];
     a.s_pk0 = srcs.pk0; a.s_pk1 = srcs.pk1; a.s_pk2 = srcs.pk2;
     a.nsrc = srcs.n; a.ntarg = targs.n; a.tskip = (uint32_t)tskip;
-    a.nt_eff = (uint32_t)((targs.n + tskip - 1) / tskip);     // i = 0, tskip, 2 tskip, ... < n
+    // i = 0, tskip, 2 tskip, ... < n; a sharded context takes the samples that fall into its target range
+    uint32_t lo = 0, hi = targs.n;
+    if (c->shard_n > 1) onb_shard_range(c, &lo, &hi);
+    a.k0 = (uint32_t)((lo + tskip - 1) / tskip);
+    const uint32_t k1 = (uint32_t)((hi + tskip - 1) / tskip);
+    a.nt_eff = k1 > a.k0 ? k1 - a.k0 : 0u;
+    if (a.nt_eff == 0) { c->last_pairs = 0; return ONB_OK; }
     const uint32_t ntiles = (srcs.n + 127u) / 128u;
     const uint32_t tgt_blocks = (a.nt_eff + 127u) / 128u;
     uint32_t nsplit = 1;

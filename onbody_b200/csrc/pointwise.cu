@@ -171,10 +171,8 @@ int onb_run_treecode2(onb_context* c, float theta, int variant) {
     a.s_pk0 = srcs.pk0; a.s_pk1 = srcs.pk1; a.s_pk2 = srcs.pk2;
     a.e_pk0 = eqs.pk0; a.e_pk1 = eqs.pk1; a.e_pk2 = eqs.pk2;
     a.stats = d_stats;
-    // without a target tree the shard is a plain index range (treecode1/2 do not need one)
-    const uint64_t n = t.n;
-    a.t_lo = (uint32_t)(n * (uint64_t)c->shard_rank / (uint64_t)c->shard_n);
-    a.t_hi = (uint32_t)(n * (uint64_t)(c->shard_rank + 1) / (uint64_t)c->shard_n);
+    // the shard is the same leaf-aligned index range as for the list-driven methods (treecode1/2 need no target tree for it)
+    onb_shard_range(c, &a.t_lo, &a.t_hi);
     a.block = c->block; a.ebs = c->ebs; a.num_eqps = c->num_eqps; a.theta = theta;
     a.s_epnum = c->legacy ? c->d_epnum : nullptr;
     const uint32_t nt = a.t_hi - a.t_lo;

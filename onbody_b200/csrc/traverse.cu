@@ -100,18 +100,21 @@ __global__ void k_leaf_table(TreeView t, uint32_t block, uint32_t* leaf_nodes) {
 // ---------------------------------------------------------------------------------------------
 struct DttArgs {
     TreeView st, tt;
-    int level; uint32_t nnodes;             // target nodes of this level: T = 2^level + local
+    int level; uint32_t nnodes;             // target nodes of this level handled here: T = node0 + local (the whole level, or the
+    uint32_t node0, pnode0;                 // nodes overlapping this rank's shard); pnode0 = node0 of the level above
+    // All lists of one evaluation live in ONE device pool, bump-allocated level by level ON THE DEVICE (k_dtt_bases):
+    // bases[2*l] / bases[2*l+1] = first pool entry of level l's interaction / deferred lists. The host never needs a list
+    // size, so an evaluation is enqueued without a single synchronisation - first call or hundredth, old input or new.
+    uint32_t* pool; uint32_t pool_cap;      // every access is clamped to pool_cap (an overflowing pass is redone with a larger pool)
+    const uint32_t* bases;
     // inherited lists = the parent's deferred list
-    const uint32_t* pc_start;               // per node of level-1 (+1); null at the root level
-    const uint32_t* pc_entries; uint32_t pccap;
+    const uint32_t* pc_start;               // per node of level-1 (+1), relative to bases[2*(level-1)+1]; null at the root level
     // outputs
     uint32_t* icount; uint32_t* ccount;     // count pass, per node of this level
-    const uint32_t* istart; const uint32_t* cstart;   // fill pass
-    uint32_t* ientries; uint32_t* centries;
-    uint32_t icap, ccap;                    // allocated entries (a stale size cache must not cause out-of-bounds writes)
+    const uint32_t* istart; const uint32_t* cstart;   // fill pass, relative to this level's bases
     uint32_t* queue; uint32_t qcap;         // per-warp FIFO scratch: 2 x qcap entries per warp slot
     unsigned long long* stats;              // [2] sltl [3] sbtl [4] sltb [5] sbtb [6] tlc [7] lpc [8] bpc [9] pairs
-    int* flag;
+    unsigned long long* ctl;                // [0] pool top [1] FIFO overflow flag [2] pool overflow flag
     uint32_t block, num_eqps, shard_lo, shard_hi; int PD; float theta;
 };
 
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(256) k_dtt(const DttArgs a) {
     unsigned long long st_sltl = 0, st_sbtl = 0, st_sltb = 0, st_sbtb = 0, st_pairs = 0, st_tlc = 0, st_lpc = 0, st_bpc = 0;
 
     for (uint32_t local = wslot; local < a.nnodes; local += nwarps) {
-        const uint32_t T = (1u << a.level) + local;
+        const uint32_t T = a.node0 + local;
         const uint32_t tn = a.tt.num[T];
         const uint32_t tio = a.tt.ioffset[T];
         const bool needed = tn >= 1 && tio < a.shard_hi && tio + tn > a.shard_lo;         // ongrav3d.cpp:221 (+ sharding)
@@ -141,13 +144,15 @@ __global__ void __launch_bounds__(256) k_dtt(const DttArgs a) {
         uint32_t root_list = 1;
         if (a.level == 0) { cur = nullptr; len = 1; }
         else {
-            const uint32_t pl = (T >> 1) - (1u << (a.level - 1));
-            const uint32_t s0 = min(a.pc_start[pl], a.pccap), s1 = min(a.pc_start[pl + 1], a.pccap);     // clamp to the allocated list
-            cur = a.pc_entries + s0; len = s1 - s0;
+            const uint32_t pl = (T >> 1) - a.pnode0;
+            const uint32_t pb = a.bases[2 * (a.level - 1) + 1];
+            const uint32_t s0 = (uint32_t)min((unsigned long long)pb + a.pc_start[pl], (unsigned long long)a.pool_cap);     // clamp to the pool
+            const uint32_t s1 = (uint32_t)min((unsigned long long)pb + a.pc_start[pl + 1], (unsigned long long)a.pool_cap);
+            cur = a.pool + s0; len = s1 - s0;
         }
         uint32_t nI = 0, nC = 0;
-        uint32_t* oI = FILL ? a.ientries + a.istart[local] : nullptr;
-        uint32_t* oC = FILL ? a.centries + a.cstart[local] : nullptr;
+        const unsigned long long oI = FILL ? (unsigned long long)a.bases[2 * a.level] + a.istart[local] : 0ull;       // first pool entry of my interaction list
+        const unsigned long long oC = FILL ? (unsigned long long)a.bases[2 * a.level + 1] + a.cstart[local] : 0ull;   // ... and of the list my children inherit
         uint32_t* nxt = q0;
         bool overflow = false;
         while (len > 0 && !overflow) {
@@ -182,19 +187,19 @@ __global__ void __launch_bounds__(256) k_dtt(const DttArgs a) {
                 if (outcome == 4) { const uint32_t pos = nextlen + 2u * __popc(bX & lt_mask); nxt[pos] = 2 * S; nxt[pos + 1] = 2 * S + 1; }   // :374,:395
                 if (FILL) {
                     if (outcome == 1 || outcome == 2) {
-                        const uint32_t pos = a.istart[local] + nI + __popc(bE & lt_mask);
-                        if (pos < a.icap) a.ientries[pos] = outcome == 2 ? (S | 0x80000000u) : S;
+                        const unsigned long long pos = oI + nI + __popc(bE & lt_mask);
+                        if (pos < a.pool_cap) a.pool[pos] = outcome == 2 ? (S | 0x80000000u) : S;
                         st_pairs += (unsigned long long)(outcome == 2 ? a.num_eqps : sn) * tcnt;
                         if (outcome == 1) { if (tleaf) ++st_sltl; else ++st_sltb; } else { if (tleaf) ++st_sbtl; else ++st_sbtb; }
                     }
-                    if (outcome == 3) { const uint32_t pos = a.cstart[local] + nC + __popc(bC & lt_mask); if (pos < a.ccap) a.centries[pos] = S; }
+                    if (outcome == 3) { const unsigned long long pos = oC + nC + __popc(bC & lt_mask); if (pos < a.pool_cap) a.pool[pos] = S; }
                 }
                 nI += __popc(bE); nC += __popc(bC); nextlen += 2u * __popc(bX);
             }
             __syncwarp();
             cur = nxt; len = nextlen; nxt = (nxt == q0) ? q1 : q0;
         }
-        if (overflow && lane == 0) atomicExch(a.flag, ONB_ERR_CAPACITY);
+        if (overflow && lane == 0) a.ctl[1] = 1ull;
         if (!FILL && lane == 0) { a.icount[local] = nI; a.ccount[local] = tleaf ? 0u : nC; }
     }
     if (FILL) {
@@ -209,18 +214,38 @@ __global__ void __launch_bounds__(256) k_dtt(const DttArgs a) {
     }
 }
 
+// device-side bump allocation of one level's two lists: totals are the last elements of the two exclusive scans
+__global__ void k_dtt_bases(const uint32_t* istart, const uint32_t* cstart, uint32_t nn, int level, uint32_t* bases, uint32_t* totals,
+                            unsigned long long* ctl, uint32_t pool_cap) {
+    const unsigned long long it = istart[nn], ct = cstart[nn];
+    const unsigned long long top = ctl[0];
+    const unsigned long long ib = top, cb = top + it, nt = cb + ct;
+    bases[2 * level] = (uint32_t)(ib < pool_cap ? ib : pool_cap);
+    bases[2 * level + 1] = (uint32_t)(cb < pool_cap ? cb : pool_cap);
+    totals[2 * level] = (uint32_t)it; totals[2 * level + 1] = (uint32_t)ct;
+    ctl[0] = nt;
+    if (nt > pool_cap) ctl[2] = 1ull;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
 // host drivers
 // ---------------------------------------------------------------------------------------------
 void onb_shard_range(const onb_context* c, uint32_t* lo, uint32_t* hi) {
-    const DParts& t = c->parts[1];
-    const uint64_t nleaf = (t.n + c->block - 1) / c->block;
-    const uint64_t l0 = nleaf * (uint64_t)c->shard_rank / (uint64_t)c->shard_n;
-    const uint64_t l1 = nleaf * (uint64_t)(c->shard_rank + 1) / (uint64_t)c->shard_n;
-    *lo = (uint32_t)std::min<uint64_t>(l0 * c->block, t.n);
-    *hi = (uint32_t)std::min<uint64_t>(l1 * c->block, t.n);
+    uint64_t a = 0, b = 0;
+    onb_shard_range_for(c->parts[1].n, c->block, c->shard_rank, c->shard_n, &a, &b);      // equal leaf-aligned chunks (plan.cu)
+    *lo = (uint32_t)a; *hi = (uint32_t)b;
+}
+
+// the target nodes of one level a sharded context works on: those that overlap its particle range (plan.cu); unsharded: all
+void onb_level_span(onb_context* c, int level, uint32_t* node0, uint32_t* count) {
+    *node0 = 1u << level; *count = 1u << level;
+    if (c->shard_n <= 1) return;
+    if (onb_plan_make(c->plan[1], c->parts[1].n, c->block, c->shard_n, c->shard_rank) != ONB_OK) return;
+    const ShardPlan& P = c->plan[1];
+    if (level >= P.levels) { *count = 0; return; }
+    *node0 = P.need_lo[level]; *count = P.need_hi[level] - P.need_lo[level];
 }
 
 static int fetch_stats(onb_context* c, unsigned long long* d_stats) {
@@ -271,88 +296,92 @@ int onb_lists_boxwise(onb_context* c, float theta, WorkList& wl) {
     return rc;
 }
 
-// One dual-tree evaluation. List storage for level l can only be sized once level l's count pass has run, which would cost
-// three host round trips per level (~70 per evaluation, each one exposed to host scheduling noise). The list sizes of the
-// previous evaluation are therefore cached per context: when they are available the whole evaluation is enqueued without a
-// single host synchronisation and the sizes are verified at the end (same particles, same theta -> same lists); on a miss
-// (first call, new input) the evaluation is redone on the synchronous path, which also refreshes the cache.
-static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cache_ok) {
+// One dual-tree evaluation, enqueued without a single host synchronisation. All interaction and deferred lists live in one
+// persistent device pool that is bump-allocated per level on the device (k_dtt_bases), so the host needs no list size: the
+// first evaluation of a context costs what every later one costs, and new particle positions cost nothing extra. The
+// traversal of level l+1 depends only on the deferred lists of level l, not on the pair kernels, so the lists are built on
+// the second stream and run underneath the pair kernels of the levels above. One read-back at the very end fetches the
+// statistics and the two overflow flags (pool too small / a per-warp FIFO too small); an overflowing pass - whose every
+// pool access was clamped - is redone with larger buffers (geometric growth: at most a few times in a context's life).
+namespace {
+struct StreamScope { onb_context* c; explicit StreamScope(onb_context* x) : c(x) {} ~StreamScope() { c->cur_stream = nullptr; } };
+}  // namespace
+
+static int fastsumm_pass(onb_context* c, float theta, bool* redo) {
     DTree& st = c->trees[0]; DTree& tt = c->trees[1];
+    StreamScope scope(c);
+    *redo = false;
     uint32_t lo, hi; onb_shard_range(c, &lo, &hi);
-    unsigned long long* d_stats = nullptr;
-    ONB_CUDA(onb_dmalloc(c, (void**)&d_stats, 10 * sizeof(unsigned long long)));
-    ONB_CUDA(cudaMemsetAsync(d_stats, 0, 10 * sizeof(unsigned long long), c->stream));
+    const int L = tt.levels;
+    // pool: first guess 512 entries per target leaf of the shard (uniform clouds at theta 1.4 need ~330), grown on overflow
+    if (!c->dtt_pool) {
+        const uint64_t nleaf = (hi > lo ? (uint64_t)(hi - lo) : 0) / (uint64_t)c->block + 1;
+        uint64_t want = std::max<uint64_t>(c->dtt_pool_want, std::max<uint64_t>((uint64_t)1 << 20, nleaf * 512));
+        want = std::min<uint64_t>(want, 0xfffffff0ull);
+        ONB_CUDA(onb_pmalloc(c, (void**)&c->dtt_pool, (size_t)want * 4));
+        c->dtt_pool_cap = (uint32_t)want;
+    }
+    unsigned long long* d_stats = nullptr;   // [0..9] counters, [10..13] ctl: pool top, FIFO overflow, pool overflow
+    ONB_CUDA(onb_dmalloc(c, (void**)&d_stats, 14 * sizeof(unsigned long long)));
+    ONB_CUDA(cudaMemsetAsync(d_stats, 0, 14 * sizeof(unsigned long long), c->stream));
+    unsigned long long* d_ctl = d_stats + 10;
     const int TB = 256, WPB = TB / 32;
-    const uint32_t max_blocks = (uint32_t)c->sm_count * 8u;
-    const uint32_t qcap = 8192;
+    // per-warp FIFO of opened source nodes: 2 x qcap entries per resident warp, the whole scratch kept under 256 MB
+    const uint32_t qcap = c->dtt_qcap;
+    uint32_t max_blocks = (uint32_t)c->sm_count * 8u;
+    while (max_blocks > 16u && (size_t)max_blocks * WPB * 2 * qcap * 4 > ((size_t)256 << 20)) max_blocks >>= 1;
+    max_blocks = std::min<uint32_t>(max_blocks, ((1u << (L - 1)) + WPB - 1) / WPB);
     uint32_t* queue = nullptr;
     ONB_CUDA(onb_dmalloc(c, (void**)&queue, (size_t)max_blocks * WPB * 2 * qcap * 4));
-    const int L = tt.levels;
-    uint32_t* d_totals = nullptr;            // [2*L]: itotal, ctotal per level (for the end-of-pass verification)
-    ONB_CUDA(onb_dmalloc(c, (void**)&d_totals, (size_t)2 * L * 4));
-    std::vector<uint64_t> sizes(2 * L, 0);
-    if (use_cache) sizes = c->dtt_sizes;
+    uint32_t *d_bases = nullptr, *d_totals = nullptr;      // [2*L] each
+    ONB_CUDA(onb_dmalloc(c, (void**)&d_bases, (size_t)4 * L * 4));
+    ONB_CUDA(cudaMemsetAsync(d_bases, 0, (size_t)4 * L * 4, c->stream));
+    d_totals = d_bases + 2 * L;
     static const bool want_prof = std::getenv("ONB_DTT_PROF") != nullptr;      // diagnostics: pairs and pair-kernel time per level
     unsigned long long* d_lvl = nullptr;
     if (want_prof) ONB_CUDA(onb_dmalloc(c, (void**)&d_lvl, (size_t)L * 8));
 
-    uint32_t *pc_start = nullptr, *pc_entries = nullptr;     // previous level's deferred lists
-    std::vector<cudaEvent_t> ev((size_t)4 * L), ev_d0((size_t)L);
-    for (auto& e : ev) cudaEventCreate(&e);
-    for (auto& e : ev_d0) cudaEventCreate(&e);
     static const bool no_ahead = std::getenv("ONB_DTT_ONE_STREAM") != nullptr;
-    const bool ahead = use_cache && !no_ahead;
+    const bool ahead = !no_ahead;
+    auto ev = [&](int lev, int k) { return onb_cached_event(c, (size_t)5 * lev + k); };    // 0..3 phase stamps, 4 = pair stream joined
     if (ahead) {      // the list stream starts behind everything enqueued so far (statistics reset, earlier phases)
-        cudaEventRecord(ev_d0[0], c->stream);
-        ONB_CUDA(cudaStreamWaitEvent(c->stream2, ev_d0[0], 0));
+        ONB_CUDA(cudaEventRecord(ev(0, 4), c->stream));
+        ONB_CUDA(cudaStreamWaitEvent(c->stream2, ev(0, 4), 0));
     }
-    int rc = ONB_OK;
+    uint32_t* pc_start = nullptr;            // previous level's deferred-list offsets
+    uint32_t pnode0 = 0;
+    int rc = ONB_OK, levels_done = 0;
     for (int lev = 0; lev < L && rc == ONB_OK; ++lev) {
-        const uint32_t nn = 1u << lev;
-        // With cached list sizes nothing below needs the host: the traversal of level lev+1 depends only on the deferred
-        // lists of level lev, not on the pair kernels, so it is enqueued on the second stream and runs underneath them.
+        uint32_t node0, nn; onb_level_span(c, lev, &node0, &nn);      // the whole level, or the nodes that overlap this rank's shard
+        if (nn == 0) break;                                            // (nothing below either: children of nothing)
+        levels_done = lev + 1;
         if (ahead) c->cur_stream = c->stream2;
-        cudaEventRecord(ev[4 * lev + 0], ONB_ST(c));
-        uint32_t *istart = nullptr, *cstart = nullptr, *ientries = nullptr, *centries = nullptr;
+        ONB_CUDA(cudaEventRecord(ev(lev, 0), ONB_ST(c)));
+        uint32_t *istart = nullptr, *cstart = nullptr;
         ONB_CUDA(onb_dmalloc(c, (void**)&istart, (size_t)(nn + 1) * 4)); ONB_CUDA(onb_dmalloc(c, (void**)&cstart, (size_t)(nn + 1) * 4));
-        DttArgs a; a.st = view_of(st); a.tt = view_of(tt); a.level = lev; a.nnodes = nn;
-        a.pc_start = pc_start; a.pc_entries = pc_entries; a.pccap = lev > 0 ? (uint32_t)sizes[2 * (lev - 1) + 1] : 0u;
-        a.icount = istart; a.ccount = cstart; a.istart = istart; a.cstart = cstart; a.ientries = nullptr; a.centries = nullptr;
-        a.queue = queue; a.qcap = qcap; a.stats = d_stats; a.flag = c->d_flag;
+        DttArgs a; a.st = view_of(st); a.tt = view_of(tt); a.level = lev; a.nnodes = nn; a.node0 = node0; a.pnode0 = pnode0;
+        a.pool = c->dtt_pool; a.pool_cap = c->dtt_pool_cap; a.bases = d_bases; a.pc_start = pc_start;
+        a.icount = istart; a.ccount = cstart; a.istart = istart; a.cstart = cstart;
+        a.queue = queue; a.qcap = qcap; a.stats = d_stats; a.ctl = d_ctl;
         a.block = c->block; a.num_eqps = c->num_eqps; a.shard_lo = lo; a.shard_hi = hi; a.PD = c->PD; a.theta = theta;
         const uint32_t blocks = std::min<uint32_t>(max_blocks, (nn + WPB - 1) / WPB);
         k_dtt<false><<<blocks, TB, 0, ONB_ST(c)>>>(a); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
         ONB_CUDA(cudaMemsetAsync(istart + nn, 0, 4, ONB_ST(c))); ONB_CUDA(cudaMemsetAsync(cstart + nn, 0, 4, ONB_ST(c)));
-        uint64_t itotal = 0, ctotal = 0;
-        if (use_cache) {
-            if ((rc = onb_exclusive_scan_u32(c, istart, istart, nn + 1, nullptr))) break;
-            if ((rc = onb_exclusive_scan_u32(c, cstart, cstart, nn + 1, nullptr))) break;
-            itotal = sizes[2 * lev]; ctotal = sizes[2 * lev + 1];
-        } else {
-            if ((rc = onb_exclusive_scan_u32(c, istart, istart, nn + 1, &itotal))) break;
-            if ((rc = onb_exclusive_scan_u32(c, cstart, cstart, nn + 1, &ctotal))) break;
-            if ((rc = onb_check_flag(c, "dual-tree traversal: per-node source FIFO overflow"))) break;
-            if (itotal >= 0xffffffffull || ctotal >= 0xffffffffull) { c->err = "fastsumm: list exceeds 2^32 entries on one GPU"; rc = ONB_ERR_CAPACITY; break; }
-            sizes[2 * lev] = itotal; sizes[2 * lev + 1] = ctotal;
-        }
-        // after the exclusive scan the appended last element holds the total
-        ONB_CUDA(cudaMemcpyAsync(d_totals + 2 * lev, istart + nn, 4, cudaMemcpyDeviceToDevice, ONB_ST(c)));
-        ONB_CUDA(cudaMemcpyAsync(d_totals + 2 * lev + 1, cstart + nn, 4, cudaMemcpyDeviceToDevice, ONB_ST(c)));
-        ONB_CUDA(onb_dmalloc(c, (void**)&ientries, std::max<size_t>(4, (size_t)itotal * 4)));
-        ONB_CUDA(onb_dmalloc(c, (void**)&centries, std::max<size_t>(4, (size_t)ctotal * 4)));
-        a.ientries = ientries; a.centries = centries;
-        a.icap = (uint32_t)itotal; a.ccap = (uint32_t)ctotal;
+        if ((rc = onb_exclusive_scan_u32(c, istart, istart, nn + 1, nullptr))) break;
+        if ((rc = onb_exclusive_scan_u32(c, cstart, cstart, nn + 1, nullptr))) break;
+        k_dtt_bases<<<1, 1, 0, ONB_ST(c)>>>(istart, cstart, nn, lev, d_bases, d_totals, d_ctl, c->dtt_pool_cap); ONB_LAUNCH(c);
         k_dtt<true><<<blocks, TB, 0, ONB_ST(c)>>>(a); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
         if (d_lvl) ONB_CUDA(cudaMemcpyAsync(d_lvl + lev, d_stats + 9, 8, cudaMemcpyDeviceToDevice, ONB_ST(c)));
-        cudaEventRecord(ev[4 * lev + 1], ONB_ST(c));
-        if (ahead) { c->cur_stream = nullptr; ONB_CUDA(cudaStreamWaitEvent(c->stream, ev[4 * lev + 1], 0)); cudaEventRecord(ev_d0[lev], c->stream); }
+        ONB_CUDA(cudaEventRecord(ev(lev, 1), ONB_ST(c)));
+        if (ahead) { c->cur_stream = nullptr; ONB_CUDA(cudaStreamWaitEvent(c->stream, ev(lev, 1), 0)); ONB_CUDA(cudaEventRecord(ev(lev, 4), c->stream)); }
         // node entry: zero + interpolate from the parent (ongrav3d.cpp:232-304)
         if ((rc = onb_bary_downward_level(c, lev))) break;
-        cudaEventRecord(ev[4 * lev + 2], c->stream);
+        ONB_CUDA(cudaEventRecord(ev(lev, 2), c->stream));
         // then this level's interactions, in list order, on top of the interpolated values (:315-402)
-        WorkList wl; wl.nitems = nn; wl.tgt_node = nullptr; wl.node_base = nn; wl.start = istart; wl.entries = ientries; wl.nentries = itotal;
+        WorkList wl; wl.nitems = nn; wl.tgt_node = nullptr; wl.node_base = node0; wl.start = istart; wl.entries = c->dtt_pool; wl.nentries = c->dtt_pool_cap;
+        wl.ebase = d_bases + 2 * lev;
         // Upper levels have too few target nodes to fill the machine with one warp per node. Cutting every list into nsplit
         // segments (ONB_P2P_SPLIT_TARGET=<CTAs per launch to aim for>) makes the pair kernel 4 % faster at N = 1e7 (79.5 ->
         // 76.1 ms), but it is OFF by default: adding the far-field partial sums in another order than the reference moves
@@ -363,51 +392,56 @@ static int fastsumm_pass(onb_context* c, float theta, bool use_cache, bool* cach
         { static int target = -1;
           if (target < 0) { target = 0; if (const char* e = std::getenv("ONB_P2P_SPLIT_TARGET")) target = std::max(0, atoi(e)); }
           while (nsplit < 16u && (unsigned long long)nn * nsplit < (unsigned long long)target) nsplit <<= 1; }
-        if (itotal > 0) if ((rc = onb_p2p_lists(c, wl, 1, 3, true, nsplit))) break;
-        cudaEventRecord(ev[4 * lev + 3], c->stream);
-        pc_start = cstart; pc_entries = centries;
+        if ((rc = onb_p2p_lists(c, wl, 1, 3, true, nsplit))) break;
+        ONB_CUDA(cudaEventRecord(ev(lev, 3), c->stream));
+        pc_start = cstart; pnode0 = node0;
     }
     c->cur_stream = nullptr;
-    double ms_lists = 0.0, ms_p2p = 0.0, ms_down = 0.0;
-    *cache_ok = true;
-    if (rc == ONB_OK) {
-        std::vector<uint32_t> h_tot(2 * L);
-        ONB_CUDA(cudaMemcpyAsync(h_tot.data(), d_totals, (size_t)2 * L * 4, cudaMemcpyDeviceToHost, c->stream));
-        ONB_CUDA(cudaStreamSynchronize(c->stream));
-        std::vector<unsigned long long> h_lvl(L, 0);
-        if (d_lvl) ONB_CUDA(cudaMemcpy(h_lvl.data(), d_lvl, (size_t)L * 8, cudaMemcpyDeviceToHost));
-        for (int lev = 0; lev < L; ++lev) {
-            if (d_lvl) {
-                float tp = 0; cudaEventElapsedTime(&tp, ev[4 * lev + 2], ev[4 * lev + 3]);
-                const unsigned long long pr = h_lvl[lev] - (lev ? h_lvl[lev - 1] : 0ull);
-                fprintf(stderr, "dtt level %2d: entries %10llu pairs %14llu p2p %8.3f ms -> %7.1f Gpairs/s\n", lev, (unsigned long long)sizes[2 * lev], pr, tp, tp > 0 ? pr / tp * 1e-6 : 0.0);
-            }
-            float t01 = 0, t12 = 0, t23 = 0;
-            cudaEventElapsedTime(&t01, ev[4 * lev], ev[4 * lev + 1]); cudaEventElapsedTime(&t12, ahead ? ev_d0[lev] : ev[4 * lev + 1], ev[4 * lev + 2]); cudaEventElapsedTime(&t23, ev[4 * lev + 2], ev[4 * lev + 3]);
-            ms_lists += t01; ms_down += t12; ms_p2p += t23;
-            if (h_tot[2 * lev] != (uint32_t)sizes[2 * lev] || h_tot[2 * lev + 1] != (uint32_t)sizes[2 * lev + 1]) *cache_ok = false;
-        }
-        if (use_cache && *cache_ok) rc = onb_check_flag(c, "dual-tree traversal: per-node source FIFO overflow");
-        if (!use_cache) { c->dtt_sizes = sizes; c->dtt_sizes_valid = true; }
+    if (rc != ONB_OK) return rc;
+    // the one read-back of the evaluation: counters, overflow flags, per-level totals
+    unsigned long long h[14];
+    std::vector<uint32_t> h_tot(2 * L);
+    ONB_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    ONB_CUDA(cudaMemcpyAsync(h_tot.data(), d_totals, (size_t)2 * L * 4, cudaMemcpyDeviceToHost, c->stream));
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
+    if (h[11]) {                       // a target node opened more source nodes in one round than its FIFO holds
+        if (c->dtt_qcap >= (1u << 22)) { c->err = "dual-tree traversal: per-node source FIFO overflow"; return ONB_ERR_CAPACITY; }
+        c->dtt_qcap *= 8; *redo = true; return ONB_OK;
     }
-    for (auto& e : ev) cudaEventDestroy(e);
-    for (auto& e : ev_d0) cudaEventDestroy(e);
-    if (rc == ONB_OK && *cache_ok) rc = fetch_stats(c, d_stats);
+    if (h[12]) {                       // the pool was too small: at least h[10] entries are needed (a lower bound, lists were clamped)
+        const uint64_t want = std::max<uint64_t>((uint64_t)c->dtt_pool_cap * 2, h[10] + h[10] / 4);
+        if (c->dtt_pool_cap >= 0xfffffff0u) { c->err = "fastsumm: lists exceed 2^32 entries on one GPU"; return ONB_ERR_CAPACITY; }
+        ONB_CUDA(cudaStreamSynchronize(c->stream2));
+        onb_pfree(c, c->dtt_pool); c->dtt_pool = nullptr; c->dtt_pool_cap = 0;
+        c->dtt_pool_want = std::min<uint64_t>(want, 0xfffffff0ull);
+        *redo = true; return ONB_OK;
+    }
+    for (int i = 0; i < 9; ++i) c->stats[i] = h[i];
+    c->last_pairs = h[9];
+    std::vector<unsigned long long> h_lvl(L, 0);
+    if (d_lvl) ONB_CUDA(cudaMemcpy(h_lvl.data(), d_lvl, (size_t)L * 8, cudaMemcpyDeviceToHost));
+    double ms_lists = 0.0, ms_p2p = 0.0, ms_down = 0.0;
+    for (int lev = 0; lev < levels_done; ++lev) {
+        float t01 = 0, t12 = 0, t23 = 0;
+        cudaEventElapsedTime(&t01, ev(lev, 0), ev(lev, 1)); cudaEventElapsedTime(&t12, ahead ? ev(lev, 4) : ev(lev, 1), ev(lev, 2)); cudaEventElapsedTime(&t23, ev(lev, 2), ev(lev, 3));
+        ms_lists += t01; ms_down += t12; ms_p2p += t23;
+        if (d_lvl) {
+            const unsigned long long pr = h_lvl[lev] - (lev ? h_lvl[lev - 1] : 0ull);
+            fprintf(stderr, "dtt level %2d: entries %10u deferred %10u pairs %14llu lists %7.3f ms down %7.3f ms p2p %8.3f ms -> %7.1f Gpairs/s\n", lev, h_tot[2 * lev], h_tot[2 * lev + 1], pr, t01, t12, t23, t23 > 0 ? pr / t23 * 1e-6 : 0.0);
+        }
+    }
     c->phase_ms["lists"] = ms_lists; c->phase_ms["downward"] = ms_down; c->phase_ms["p2p"] = ms_p2p;
-    return rc;
+    c->phase_ms["dtt_pool_used"] = (double)h[10]; c->phase_ms["dtt_pool_cap"] = (double)c->dtt_pool_cap;
+    return ONB_OK;
 }
 
 int onb_run_fastsumm(onb_context* c, float theta) {
-    const bool try_cache = c->dtt_sizes_valid && (int)c->dtt_sizes.size() == 2 * c->trees[1].levels;
-    bool ok = true;
-    if (try_cache) {
-        int rc = fastsumm_pass(c, theta, true, &ok);
+    for (int attempt = 0; attempt < 12; ++attempt) {
+        bool redo = false;
+        const int rc = fastsumm_pass(c, theta, &redo);
         if (rc != ONB_OK) return rc;
-        if (ok) return ONB_OK;
-        // the cached list sizes did not match this input: discard the pass (kernels clamp their writes to the allocated
-        // capacity) and redo it on the synchronous path
-        ONB_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
-        onb_scratch_reset(c);
+        if (!redo) { c->phase_ms["dtt_attempts"] = attempt + 1; return ONB_OK; }
+        onb_scratch_reset(c);          // the discarded pass is complete (its read-back synchronised): reuse its scratch
     }
-    return fastsumm_pass(c, theta, false, &ok);
+    c->err = "fastsumm: list buffers kept overflowing"; return ONB_ERR_CAPACITY;
 }

@@ -526,6 +526,71 @@ __global__ void k_bbox_final(const FinishArgs a, const float* lohi) {
     a.t.nr[node] = __fmul_rn(0.5f, __fsqrt_rn(bsss));
 }
 
+// ---- leaf records (multi-GPU): everything finishTree and the bounding boxes need from a leaf, as one fixed-size record, so
+// that ranks exchange 13 floats per LEAF instead of 4-5 floats per PARTICLE and no rank ever has to read another rank's
+// particles to complete its node arrays. Record of leaf j (particles [j*block, ...)), K = 3*PD + SD + 1 floats:
+//   [0,PD) bbox min   [PD,2PD) bbox max   [2PD,3PD) centre (t.x)   [3PD,3PD+SD) strength sums (t.s)   [3PD+SD] mean radius (t.pr)
+// The sums are the same sequential double sums as k_finish_leaves (finishTree :753-806), so the values are bit-identical.
+__global__ void k_leafrec_make(const FinishArgs a, uint32_t leaf0, uint32_t leaf1, float* __restrict__ rec, int K) {
+    const uint32_t leaf = leaf0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (leaf >= leaf1) return;
+    const uint32_t pf = leaf * a.block, pl = min(pf + a.block, a.p.n), n = pl - pf;
+    const int PD = a.PD, SD = a.are_sources ? a.SD : 0;
+    float* out = rec + (size_t)leaf * K;
+    for (int d = 0; d < PD; ++d) {
+        float lo = INFINITY, hi = -INFINITY;
+        for (uint32_t i = pf + lane; i < pl; i += 32) { const float v = a.p.x[d][i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        lo = warp_min(lo); hi = warp_max(hi);
+        if (lane == 0) { out[d] = lo; out[PD + d] = hi; }
+    }
+    double acc = 0.0;
+    if (lane <= PD) {
+        for (uint32_t i = pf; i < pl; ++i) {
+            float w;
+            if (!a.are_sources) w = 1.0f;
+            else if (a.SD == 1) w = fabsf(a.p.s[0][i]);
+            else {
+                w = 0.0f;
+                for (int d = 0; d < a.SD; ++d) { const double sd = (double)a.p.s[d][i]; w = __double2float_rn(__dadd_rn((double)w, __dmul_rn(sd, sd))); }   // :775
+                w = __fsqrt_rn(w);
+            }
+            if (lane < PD) acc = __dadd_rn(acc, (double)__fmul_rn(a.p.x[lane][i], w));     // :790
+            else           acc = __dadd_rn(acc, (double)w);                                // :786
+        }
+    } else if (lane <= PD + SD) {
+        const float* __restrict__ sd = a.p.s[lane - PD - 1];
+        for (uint32_t i = pf; i < pl; ++i) acc = __dadd_rn(acc, (double)sd[i]);            // :796
+    } else if (lane == PD + SD + 1) {
+        for (uint32_t i = pf; i < pl; ++i) acc = __dadd_rn(acc, (double)a.p.r[i]);         // :800
+    }
+    const double wsum = __shfl_sync(0xffffffffu, acc, PD);
+    if (lane < PD) {
+        const float ooass = __double2float_rn(__ddiv_rn(1.0, __dadd_rn(1.e-20, wsum)));
+        out[2 * PD + lane] = __double2float_rn(__dmul_rn((double)ooass, acc));
+    } else if (lane > PD && lane <= PD + SD) {
+        out[3 * PD + (lane - PD - 1)] = __double2float_rn(acc);
+    } else if (lane == PD + SD + 1) {
+        out[3 * PD + a.SD * a.are_sources] = __fdiv_rn(__double2float_rn(acc), __uint2float_rn(n));   // :801
+    }
+}
+// records (complete after the all-gather) -> node arrays of the leaves + the box scratch of k_bbox_parents
+__global__ void k_leafrec_apply(const FinishArgs a, const float* __restrict__ rec, int K, float* lohi) {
+    const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= (uint32_t)a.t.numnodes || node == 0) return;
+    const uint32_t n = a.t.num[node];
+    if (n == 0 || n > a.block) return;
+    const float* in = rec + (size_t)(a.t.ioffset[node] / a.block) * K;
+    const size_t nn = a.t.numnodes;
+    const int PD = a.PD, SD = a.are_sources ? a.SD : 0;
+    for (int d = 0; d < PD; ++d) {
+        lohi[(size_t)(2 * d) * nn + node] = in[d]; lohi[(size_t)(2 * d + 1) * nn + node] = in[PD + d];
+        a.t.x[d][node] = in[2 * PD + d];
+    }
+    for (int d = 0; d < SD; ++d) a.t.s[d][node] = in[3 * PD + d];
+    a.t.pr[node] = in[3 * PD + SD];
+}
+
 #include "tree_big.cuh"
 #include "tree_sub.cuh"
 
@@ -563,7 +628,7 @@ static int run_finish(onb_context* c, DParts& p, DTree& t) {      // finishTree 
     return ONB_OK;
 }
 
-int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t bhi) {
+int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t bhi, bool finish) {
     const uint32_t n = p.n;
     if (bhi > n) bhi = n;
     if (blo >= bhi) { c->err = "make_tree: empty build range"; return ONB_ERR_ARG; }
@@ -629,11 +694,11 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
             sa.g = cg; sa.og = own_g; sa.t = view_of(t); sa.stats = ONB_STATS(c);
             sa.block = c->block; sa.blo = blo; sa.bhi = bhi; sa.level = lev; sa.nsub = t.levels - lev; sa.PD = PD; sa.pivot_mode = onb_pivot_mode;
             const size_t sub_smem = (size_t)sub_max * (3 * sizeof(float) + 2 * sizeof(uint16_t));
-            static bool attr_set = false;
-            if (!attr_set) {
+            static bool attr_set[64] = {false};      // function attributes are per device (a process may hold contexts on several)
+            if (!attr_set[c->device & 63]) {
                 ONB_CUDA(cudaFuncSetAttribute(k_subtree<1024, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
                 ONB_CUDA(cudaFuncSetAttribute(k_subtree<512, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
-                attr_set = true;
+                attr_set[c->device & 63] = true;
             }
             if (sub_max == 8192) k_subtree<1024, 8192><<<1u << lev, 1024, sub_smem, ONB_ST(c)>>>(sa);
             else                 k_subtree<512, 4096><<<1u << lev, 512, sub_smem, ONB_ST(c)>>>(sa);
@@ -653,7 +718,8 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
             ba.max_nodes = lev_nodes; ba.max_chunks = max_chunks;
             const uint32_t chunks_ub = std::min<uint32_t>(max_chunks, n / BIG_CH + lev_nodes + 1);
             {
-                static int coop_max = 0, coop_want = 4, coop_want_conc = 2;
+                static int coop_max_dev[64] = {0}, coop_want = 4, coop_want_conc = 2;
+                int& coop_max = coop_max_dev[c->device & 63];      // occupancy is a per-device property
                 if (!coop_max) {
                     ONB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_max, k_big_level, BIG_T, 0));
                     if (const char* e = std::getenv("ONB_BIG_BLOCKS_PER_SM")) coop_want = std::max(1, atoi(e));
@@ -720,9 +786,38 @@ int onb_tree_build(onb_context* c, DParts& p, DTree& t, uint32_t blo, uint32_t b
         }
     }
 
-    int rc = run_finish(c, p, t);
-    if (rc) return rc;
+    // (multi-GPU: the node summaries come from exchanged leaf records instead, onb_tree_leaf_records / onb_tree_finish_from_records)
+    if (finish) { int rc = run_finish(c, p, t); if (rc) return rc; }
     t.built = true;
+    return ONB_OK;
+}
+
+// multi-GPU: the records of the leaves [leaf0, leaf1) of a tree-ordered particle range, K floats each, into rec[leaf*K ...]
+int onb_leafrec_floats(const onb_context* c, bool are_sources) { return 3 * c->PD + (are_sources ? c->SD : 0) + 1; }
+int onb_tree_leaf_records(onb_context* c, DParts& p, DTree& t, uint32_t leaf0, uint32_t leaf1, float* rec) {
+    if (leaf1 <= leaf0) return ONB_OK;
+    FinishArgs fa; fa.p = view_of(p); fa.t = view_of(t); fa.block = c->block; fa.PD = c->PD; fa.SD = c->SD; fa.are_sources = p.are_sources ? 1 : 0;
+    const int K = onb_leafrec_floats(c, p.are_sources);
+    k_leafrec_make<<<(unsigned)(((size_t)(leaf1 - leaf0) * 32 + 255) / 256), 256, 0, ONB_ST(c)>>>(fa, leaf0, leaf1, rec, K); ONB_LAUNCH(c);
+    ONB_CUDA(cudaGetLastError());
+    return ONB_OK;
+}
+// ... and every node array from the complete set of records: leaves copied, parents bottom-up (boxes as unions - exact
+// min/max, bit-identical to the top-down build -, centres / strengths / radii as finishTree :721-746)
+int onb_tree_finish_from_records(onb_context* c, DParts& p, DTree& t, const float* rec) {
+    if (!t.built) { c->err = "finish_tree: build the tree first"; return ONB_ERR_ARG; }
+    float* lohi = nullptr;
+    ONB_CUDA(onb_dmalloc(c, (void**)&lohi, (size_t)6 * t.numnodes * sizeof(float)));
+    FinishArgs fa; fa.p = view_of(p); fa.t = view_of(t); fa.block = c->block; fa.PD = c->PD; fa.SD = c->SD; fa.are_sources = p.are_sources ? 1 : 0;
+    const int K = onb_leafrec_floats(c, p.are_sources);
+    k_leafrec_apply<<<(t.numnodes + 255) / 256, 256, 0, ONB_ST(c)>>>(fa, rec, K, lohi); ONB_LAUNCH(c);
+    for (int lev = t.levels - 2; lev >= 0; --lev) {
+        const uint32_t nn = 1u << lev;
+        k_bbox_parents<<<(nn + 127) / 128, 128, 0, ONB_ST(c)>>>(fa, lohi, lev); ONB_LAUNCH(c);
+        k_finish_parents<<<(nn + 127) / 128, 128, 0, ONB_ST(c)>>>(fa, lev); ONB_LAUNCH(c);
+    }
+    k_bbox_final<<<(t.numnodes + 127) / 128, 128, 0, ONB_ST(c)>>>(fa, lohi); ONB_LAUNCH(c);
+    ONB_CUDA(cudaGetLastError());
     return ONB_OK;
 }
 
@@ -755,6 +850,7 @@ int onb_tree_refine(onb_context* c, DParts& p, DTree& t, bool check_now) {
     // leaves of the build range only (whole tree unless onb_make_tree_range restricted it; ranges are leaf aligned)
     const uint32_t leaf0 = p.build_lo / c->block, leaf1 = (std::min(p.build_hi, p.n) + c->block - 1) / c->block;
     ra.leaf0 = leaf0;
+    if (leaf1 <= leaf0) return ONB_OK;                  // a rank without leaves
     k_refine<<<leaf1 - leaf0, 128, 0, ONB_ST(c)>>>(ra); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
     p.packed_valid = false;
