@@ -91,6 +91,10 @@ ONB_API int onb_set_targets_planes(onb_context* c, uint64_t n, const float* cons
  * buffers untouched until the next phase call that consumes them has returned (every phase call blocks). Pageable
  * buffers are still copied synchronously. Default off: the copies complete before set_* returns. */
 ONB_API int onb_set_async_inputs(onb_context* c, int on);
+/* opt-in, with a communicator attached (every context is handed the SAME arrays): each context copies only its 1/nranks
+ * slice of every plane from the caller's buffers and the slices are replicated by one grouped all-gather over NVLink, so
+ * that every input byte crosses PCIe once per node instead of once per GPU. The device arrays end up identical. */
+ONB_API int onb_set_sliced_inputs(onb_context* c, int on);
 /* the drivers' own synthetic initialisation (std::mt19937(12345), Parts.hpp:99-109,169-176), done on the
  * host into caller buffers: x [PD][n], r [n], s [SD][n] (s may be NULL for targets). strength_mode 1 = wave_strengths */
 ONB_API int onb_driver_inputs(int physics, uint64_t n, int strength_mode, float* x, float* r, float* s);
@@ -178,8 +182,9 @@ ONB_API int onb_add_results_original_order(onb_context* c, float* u);
 /* the same with one pointer per output plane (out[OD]); host or device pointers. Device pointers are updated in place by one
  * kernel; host pointers through one scatter kernel and a pinned double buffer whose copies overlap the host's += */
 ONB_API int onb_add_results_planes(onb_context* c, float* const* out);
-/* multi-GPU: the output planes of this context's shard only - elements [*lo,*hi) of every plane of u ([OD][n], tree order) */
-ONB_API int onb_get_shard_results(onb_context* c, float* u, uint64_t* lo, uint64_t* hi);
+/* multi-GPU: the output planes of this context's shard only - u[d*plane_stride + i] for i in [*lo,*hi), tree order
+ * (plane_stride 0 = n: the full [OD][n] layout, every rank filling its own part of one shared array) */
+ONB_API int onb_get_shard_results(onb_context* c, float* u, uint64_t plane_stride, uint64_t* lo, uint64_t* hi);
 ONB_API int onb_tree_shape(const onb_context* c, int which, int* levels, int* numnodes);
 ONB_API int onb_get_tree(onb_context* c, int which, float* x, float* nc, float* ns, float* nr, float* pr, float* s,
                  uint64_t* ioffset, uint64_t* num, uint64_t* epoffset, uint64_t* epnum);

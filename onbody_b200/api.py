@@ -70,6 +70,7 @@ def load_library():
     L.onb_fastsumm.argtypes = [C.c_void_p, C.c_float]
     L.onb_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.onb_set_async_inputs.argtypes = [C.c_void_p, C.c_int]
+    L.onb_set_sliced_inputs.argtypes = [C.c_void_p, C.c_int]
     L.onb_count.restype = C.c_uint64
     L.onb_count.argtypes = [C.c_void_p, C.c_int]
     L.onb_get_parts.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -90,6 +91,21 @@ def load_library():
     L.onb_measure_fp32_peak.argtypes = [C.c_void_p]
     L.onb_load_tree.argtypes = [C.c_void_p, C.c_int, C.c_int] + [_f32p] * 6 + [_u64p] * 2
     L.onb_get_build_stats.argtypes = [C.c_void_p, C.c_uint64 * 5]
+    vpp = C.POINTER(C.c_void_p)
+    L.onb_set_sources_planes.argtypes = [C.c_void_p, C.c_uint64, vpp, C.c_void_p, vpp]
+    L.onb_set_targets_planes.argtypes = [C.c_void_p, C.c_uint64, vpp, C.c_void_p]
+    L.onb_add_results_planes.argtypes = [C.c_void_p, vpp]
+    L.onb_get_shard_results.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, _u64p, _u64p]
+    L.onb_comm_unique_id.argtypes = [C.c_void_p, C.c_uint64]
+    L.onb_comm_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
+    L.onb_comm_init_all.argtypes = [vpp, C.c_int]
+    L.onb_comm_init_loopback.argtypes = [vpp, C.c_int]
+    L.onb_comm_destroy.argtypes = [C.c_void_p]
+    L.onb_comm_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+    L.onb_set_memory_mode.argtypes = [C.c_void_p, C.c_int]
+    L.onb_device_memory.argtypes = [C.c_void_p, _u64p, _u64p]
+    L.onb_shard_range_for.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, _u64p, _u64p]
+    L.onb_set_pivot_mode.argtypes = [C.c_int]
     if os.environ.get("ONB_P2P_TPT"):          # tuning knob: targets per thread of the pair kernel (1, 2, 4; +16 = scalar arithmetic)
         L.onb_set_p2p_tpt(int(os.environ["ONB_P2P_TPT"]))
     _lib = L
@@ -117,6 +133,46 @@ def driver_inputs(physics, n, sources=True):
     return x, r, s
 
 
+MEM_NORMAL, MEM_LEAN = 0, 1
+UNIQUE_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """128 bytes rank 0 ships to the other ranks (ncclGetUniqueId inside the library)"""
+    L = load_library()
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    rc = L.onb_comm_unique_id(buf, UNIQUE_ID_BYTES)
+    if rc != 0:
+        raise OnbodyError("onb_comm_unique_id failed (%d): is libnccl.so.2 loadable?" % rc)
+    return buf.raw
+
+
+def _join(sessions, fn, what):
+    L = load_library()
+    arr = (C.c_void_p * len(sessions))(*[s.h for s in sessions])
+    rc = getattr(L, fn)(arr, len(sessions))
+    if rc != 0:
+        raise OnbodyError("%s failed (%d): %s" % (what, rc, L.onb_error(sessions[0].h).decode()))
+    for i, s in enumerate(sessions):
+        s.rank, s.world = i, len(sessions)
+
+
+def comm_init_all(sessions):
+    """one process, one session per GPU: ncclCommInitAll; then drive each session from its own host thread"""
+    _join(sessions, "onb_comm_init_all", "onb_comm_init_all")
+
+
+def comm_init_loopback(sessions):
+    """test transport: sessions of this process (any devices, also one) joined by device copies instead of NCCL"""
+    _join(sessions, "onb_comm_init_loopback", "onb_comm_init_loopback")
+
+
+def shard_range_for(n, block, rank, nranks):
+    lo, hi = C.c_uint64(), C.c_uint64()
+    load_library().onb_shard_range_for(n, block, rank, nranks, C.byref(lo), C.byref(hi))
+    return int(lo.value), int(hi.value)
+
+
 class GpuSession:
     """One source set + one target set on one B200, phase by phase."""
 
@@ -126,6 +182,7 @@ class GpuSession:
         self.PD, self.SD, self.OD = _DIMS[physics]
         self.has_fastsumm = physics != "vortgrad3d"
         self.nsrc, self.ntarg = nsrc, ntarg
+        self.block, self.rank, self.world = block, 0, 1
         self.h = self.lib.onb_create(PHYSICS.index(physics), device)
         if not self.h:
             raise OnbodyError("onb_create failed: %s" % self.lib.onb_last_create_error().decode())
@@ -182,8 +239,63 @@ class GpuSession:
     def set_async_inputs(self, on):
         self._chk(self.lib.onb_set_async_inputs(self.h, 1 if on else 0))
 
+    def set_sliced_inputs(self, on):
+        self._chk(self.lib.onb_set_sliced_inputs(self.h, 1 if on else 0))
+
     def set_shard(self, rank, nranks):
         self._chk(self.lib.onb_set_shard(self.h, rank, nranks))
+        self.rank, self.world = rank, nranks
+
+    # ---- multi-GPU: the communicator lives in the library (csrc/comm.cu); with one attached the same phase calls run distributed
+    def comm_init_rank(self, rank, nranks, unique_id):
+        self._chk(self.lib.onb_comm_init_rank(self.h, rank, nranks, unique_id, len(unique_id)))
+        self.rank, self.world = rank, nranks
+
+    def comm_destroy(self):
+        self._chk(self.lib.onb_comm_destroy(self.h))
+        self.rank, self.world = 0, 1
+
+    def comm_info(self):
+        v = [C.c_int() for _ in range(4)]
+        self.lib.onb_comm_info(self.h, *[C.byref(x) for x in v])
+        return {"rank": v[0].value, "nranks": v[1].value, "transport": ("none", "nccl", "loopback")[v[2].value], "nccl_version": v[3].value}
+
+    def set_memory_mode(self, mode):
+        self._chk(self.lib.onb_set_memory_mode(self.h, mode))
+
+    def device_memory(self):
+        u, t = C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.onb_device_memory(self.h, C.byref(u), C.byref(t)))
+        return int(u.value), int(t.value)
+
+    def shard_results_into(self, u_ptr, stride=0):
+        """device -> host copy of this rank's shard of the target outputs: u[d*stride + i] for i in [lo, hi) (stride 0 = n, the
+        full [OD][n] layout; a caller holding only its shard passes the shard length and a pointer shifted by -lo); returns (lo, hi)"""
+        lo, hi = C.c_uint64(), C.c_uint64()
+        self._chk(self.lib.onb_get_shard_results(self.h, u_ptr, stride, C.byref(lo), C.byref(hi)))
+        return int(lo.value), int(hi.value)
+
+    def set_planes_ptr(self, n, x_ptrs, r_ptr, s_ptrs):
+        """sources and targets from raw per-plane pointers (host or device)"""
+        self.nsrc = self.ntarg = n
+        X = (C.c_void_p * len(x_ptrs))(*x_ptrs); S = (C.c_void_p * len(s_ptrs))(*s_ptrs)
+        self._chk(self.lib.onb_set_sources_planes(self.h, n, X, r_ptr, S))
+        self._chk(self.lib.onb_set_targets_planes(self.h, n, X, r_ptr))
+
+    def set_sources_planes(self, xs, r, ss):
+        """one array per plane (what the Fortran-style entry points receive)"""
+        n = r.shape[0]; self.nsrc = n
+        X = (C.c_void_p * len(xs))(*[a.ctypes.data for a in xs]); S = (C.c_void_p * len(ss))(*[a.ctypes.data for a in ss])
+        self._chk(self.lib.onb_set_sources_planes(self.h, n, X, r.ctypes.data, S))
+
+    def set_targets_planes(self, xs, r):
+        n = r.shape[0]; self.ntarg = n
+        X = (C.c_void_p * len(xs))(*[a.ctypes.data for a in xs])
+        self._chk(self.lib.onb_set_targets_planes(self.h, n, X, r.ctypes.data))
+
+    def add_results_planes(self, planes):
+        P = (C.c_void_p * len(planes))(*[a.ctypes.data if hasattr(a, "ctypes") else int(a) for a in planes])
+        self._chk(self.lib.onb_add_results_planes(self.h, P))
 
     # ---- phases
     def make_tree(self, which): self._chk(self.lib.onb_make_tree(self.h, which))

@@ -7,6 +7,9 @@
 #include "onb_internal.h"
 #include <cstdlib>
 
+int onb_comm_allgather(onb_context* c, const std::vector<void*>& bufs, const std::vector<size_t>& chunk_bytes);
+cudaStream_t onb_comm_stream(const onb_context* c);
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -257,9 +260,31 @@ static int set_parts(onb_context* c, int which, uint64_t n, const float* const* 
         ONB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_copy, 0));
         st = c->stream2;
     }
-    for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(p.x[d], xs[d], bytes, cudaMemcpyDefault, st));
-    ONB_CUDA(cudaMemcpyAsync(p.r, r, bytes, cudaMemcpyDefault, st));
-    if (which == 0) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(p.s[d], ss[d], bytes, cudaMemcpyDefault, st));
+    if (c->comm && c->shard_n > 1 && c->sliced_inputs) {
+        // every context is handed the same arrays: each pulls 1/nranks of every plane over its own PCIe link and the slices
+        // are replicated over NVLink (one grouped in-place all-gather), so every input byte crosses PCIe once in total
+        const size_t chunk = ((n + (size_t)c->shard_n - 1) / (size_t)c->shard_n + 31) & ~(size_t)31;
+        const size_t lo = std::min<size_t>(n, chunk * (size_t)c->shard_rank), hi = std::min<size_t>(n, lo + chunk);
+        if ((size_t)p.cap < chunk * (size_t)c->shard_n) { c->err = "set: planes too short for the sliced input gather"; return ONB_ERR_ARG; }
+        std::vector<void*> bufs; std::vector<size_t> chunks;
+        auto slice = [&](float* dst, const float* src) -> int {
+            if (hi > lo) ONB_CUDA(cudaMemcpyAsync(dst + lo, src + lo, (hi - lo) * sizeof(float), cudaMemcpyDefault, st));
+            bufs.push_back(dst); chunks.push_back(chunk * sizeof(float));
+            return ONB_OK;
+        };
+        for (int d = 0; d < c->PD; ++d) { int rc = slice(p.x[d], xs[d]); if (rc) return rc; }
+        { int rc = slice(p.r, r); if (rc) return rc; }
+        if (which == 0) for (int d = 0; d < c->SD; ++d) { int rc = slice(p.s[d], ss[d]); if (rc) return rc; }
+        cudaStream_t sc = onb_comm_stream(c);
+        cudaEvent_t e_in = onb_cached_event(c, 390 + which), e_out = onb_cached_event(c, 392 + which);
+        ONB_CUDA(cudaEventRecord(e_in, st)); ONB_CUDA(cudaStreamWaitEvent(sc, e_in, 0));
+        { int rc = onb_comm_allgather(c, bufs, chunks); if (rc) return rc; }
+        ONB_CUDA(cudaEventRecord(e_out, sc)); ONB_CUDA(cudaStreamWaitEvent(st, e_out, 0));
+    } else {
+        for (int d = 0; d < c->PD; ++d) ONB_CUDA(cudaMemcpyAsync(p.x[d], xs[d], bytes, cudaMemcpyDefault, st));
+        ONB_CUDA(cudaMemcpyAsync(p.r, r, bytes, cudaMemcpyDefault, st));
+        if (which == 0) for (int d = 0; d < c->SD; ++d) ONB_CUDA(cudaMemcpyAsync(p.s[d], ss[d], bytes, cudaMemcpyDefault, st));
+    }
     if (!async) ONB_CUDA(cudaStreamSynchronize(st));
     else if (which == 1) { ONB_CUDA(cudaEventRecord(c->ev_tgt_ready, c->stream2)); c->tgt_copy_pending = true; }
     p.packed_valid = false;
@@ -267,6 +292,7 @@ static int set_parts(onb_context* c, int which, uint64_t n, const float* const* 
     return ONB_OK;
 }
 int onb_set_async_inputs(onb_context* c, int on) { if (!c) return ONB_ERR_ARG; c->async_inputs = on != 0; return ONB_OK; }
+int onb_set_sliced_inputs(onb_context* c, int on) { if (!c) return ONB_ERR_ARG; c->sliced_inputs = on != 0; return ONB_OK; }
 int onb_set_sources(onb_context* c, uint64_t n, const float* x, const float* r, const float* s) {
     const float* xs[ONB_MAX_PD]; const float* ss[ONB_MAX_SD];
     for (int d = 0; d < ONB_MAX_PD; ++d) xs[d] = x + (size_t)d * n;
@@ -558,13 +584,14 @@ int onb_get_parts(onb_context* c, int which, float* x, float* r, float* s, float
 }
 // the output planes of this context's shard only: u is [OD][n], elements [lo,hi) of every plane are written (the multi-GPU
 // drivers let every rank fill its own part of one shared host array)
-int onb_get_shard_results(onb_context* c, float* u, uint64_t* lo_out, uint64_t* hi_out) {
+int onb_get_shard_results(onb_context* c, float* u, uint64_t plane_stride, uint64_t* lo_out, uint64_t* hi_out) {
     ONB_CUDA(cudaSetDevice(c->device));
     DParts& p = c->parts[1];
     uint32_t lo, hi; onb_shard_range(c, &lo, &hi);
     if (lo_out) *lo_out = lo; if (hi_out) *hi_out = hi;
     if (!u || hi <= lo) return ONB_OK;
-    for (int d = 0; d < c->OD; ++d) ONB_CUDA(cudaMemcpyAsync(u + (size_t)d * p.n + lo, p.u[d] + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDefault, c->stream));
+    const size_t stride = plane_stride ? (size_t)plane_stride : (size_t)p.n;
+    for (int d = 0; d < c->OD; ++d) ONB_CUDA(cudaMemcpyAsync(u + (size_t)d * stride + lo, p.u[d] + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDefault, c->stream));
     ONB_CUDA(cudaStreamSynchronize(c->stream));
     return ONB_OK;
 }

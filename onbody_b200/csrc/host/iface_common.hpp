@@ -27,37 +27,34 @@ inline onb_context* context(int physics, float /*unused*/ = 0.f) {
     return ctx[physics];
 }
 
-// PD coordinate arrays + SD strength arrays (separate caller arrays) -> the planar layout of the C ABI
-inline void planar(std::vector<float>& out, int n, const float* const* a, int na) {
-    out.resize((size_t)n * na);
-    for (int d = 0; d < na; ++d) std::memcpy(out.data() + (size_t)d * n, a[d], (size_t)n * sizeof(float));
-}
-
 // solver = makeTree(srcs) -> barycentric upward -> makeTree(targs) -> boxwise treecode -> += in original order
 // direct = nbody_naive -> += (targets were never reordered)
+// The caller's separate coordinate / strength / output arrays go to the library as they are (one pointer per plane): no
+// re-packing on the host, and the += of the solver path is one scatter kernel + pipelined pinned read-back (or fully in place
+// when the caller's arrays are device memory).
 inline float run(int physics, bool direct, float theta, int ns, const float* const* sx, int PD, const float* const* ss, int SD, const float* sr,
                  int nt, const float* const* tx, const float* tr, float* const* out, int OD) {
+    (void)PD; (void)SD;
     onb_context* c = context(physics);
     if (!c) return fail(nullptr, "create");
     if (physics == ONB_VORT2DTR) onb_set_flops_per_pair(c, 13);      // interface2dvorttr.cpp:53
-    std::vector<float> x, s, t, r0, u;
-    planar(x, ns, sx, PD); planar(s, ns, ss, SD); planar(t, nt, tx, PD);
+    std::vector<float> r0;
     const float* trp = tr;
     if (!trp) { r0.assign(nt, 0.0f); trp = r0.data(); }        // the reference leaves targs.r zero-initialised here
-    if (onb_set_sources(c, (uint64_t)ns, x.data(), sr, s.data()) != ONB_OK) return fail(c, "set_sources");
-    if (onb_set_targets(c, (uint64_t)nt, t.data(), trp) != ONB_OK) return fail(c, "set_targets");
+    if (onb_set_sources_planes(c, (uint64_t)ns, sx, sr, ss) != ONB_OK) return fail(c, "set_sources");
+    if (onb_set_targets_planes(c, (uint64_t)nt, tx, trp) != ONB_OK) return fail(c, "set_targets");
     float flops = 0.0f;
-    u.assign((size_t)OD * nt, 0.0f);
     if (direct) {
+        std::vector<float> u((size_t)OD * nt, 0.0f);
         if (onb_zero_vels(c) != ONB_OK || onb_naive(c, 1, &flops) != ONB_OK) return fail(c, "naive");
         if (onb_get_parts(c, 1, nullptr, nullptr, nullptr, u.data(), nullptr) != ONB_OK) return fail(c, "get");
+        for (int d = 0; d < OD; ++d) { float* o = out[d]; const float* ud = u.data() + (size_t)d * nt; for (int i = 0; i < nt; ++i) o[i] += ud[i]; }
     } else {
         if (onb_make_trees(c) != ONB_OK) return fail(c, "make_trees");         // both builds overlap on the device
         if (onb_upward(c, 0) != ONB_OK) return fail(c, "upward");
         if (onb_zero_vels(c) != ONB_OK || onb_treecode3(c, theta, &flops) != ONB_OK) return fail(c, "treecode3");
-        if (onb_add_results_original_order(c, u.data()) != ONB_OK) return fail(c, "results");
+        if (onb_add_results_planes(c, out) != ONB_OK) return fail(c, "results");   // interface3dvortgrads.cpp:384-395
     }
-    for (int d = 0; d < OD; ++d) { float* o = out[d]; const float* ud = u.data() + (size_t)d * nt; for (int i = 0; i < nt; ++i) o[i] += ud[i]; }
     return flops;
 }
 

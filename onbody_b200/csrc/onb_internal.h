@@ -150,7 +150,7 @@ struct onb_context {
     uint64_t plan_key_for(uint64_t n) const { return ((n * 131u + (uint64_t)block) * 131u + (uint64_t)shard_n) * 131u + (uint64_t)shard_rank + 1u; }
     cudaEvent_t ev_src_planes = nullptr; bool src_planes_pending = false;   // the source-plane all-gather may outlive onb_make_trees
     // opt-in asynchronous input copies (onb_set_async_inputs): the target planes arrive on stream2
-    bool async_inputs = false, tgt_copy_pending = false;
+    bool async_inputs = false, tgt_copy_pending = false, sliced_inputs = false;
     cudaEvent_t ev_copy = nullptr, ev_tgt_ready = nullptr;
 };
 int onb_join_copies(onb_context* c);   // make the context stream wait for a pending asynchronous target copy

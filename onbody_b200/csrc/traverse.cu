@@ -317,6 +317,10 @@ static int fastsumm_pass(onb_context* c, float theta, bool* redo) {
     if (!c->dtt_pool) {
         const uint64_t nleaf = (hi > lo ? (uint64_t)(hi - lo) : 0) / (uint64_t)c->block + 1;
         uint64_t want = std::max<uint64_t>(c->dtt_pool_want, std::max<uint64_t>((uint64_t)1 << 20, nleaf * 512));
+        if (!c->dtt_pool_want) {                                   // tests: start small so that the overflow path runs
+            if (const char* e = std::getenv("ONB_DTT_POOL_INIT")) want = std::max<uint64_t>(16, strtoull(e, nullptr, 10));
+            if (const char* e = std::getenv("ONB_DTT_QCAP_INIT")) c->dtt_qcap = (uint32_t)std::max<uint64_t>(4, strtoull(e, nullptr, 10));
+        }
         want = std::min<uint64_t>(want, 0xfffffff0ull);
         ONB_CUDA(onb_pmalloc(c, (void**)&c->dtt_pool, (size_t)want * 4));
         c->dtt_pool_cap = (uint32_t)want;
@@ -409,7 +413,7 @@ static int fastsumm_pass(onb_context* c, float theta, bool* redo) {
         c->dtt_qcap *= 8; *redo = true; return ONB_OK;
     }
     if (h[12]) {                       // the pool was too small: at least h[10] entries are needed (a lower bound, lists were clamped)
-        const uint64_t want = std::max<uint64_t>((uint64_t)c->dtt_pool_cap * 2, h[10] + h[10] / 4);
+        const uint64_t want = std::max<uint64_t>((uint64_t)c->dtt_pool_cap * 4, h[10] + h[10] / 4);
         if (c->dtt_pool_cap >= 0xfffffff0u) { c->err = "fastsumm: lists exceed 2^32 entries on one GPU"; return ONB_ERR_CAPACITY; }
         ONB_CUDA(cudaStreamSynchronize(c->stream2));
         onb_pfree(c, c->dtt_pool); c->dtt_pool = nullptr; c->dtt_pool_cap = 0;
@@ -436,7 +440,7 @@ static int fastsumm_pass(onb_context* c, float theta, bool* redo) {
 }
 
 int onb_run_fastsumm(onb_context* c, float theta) {
-    for (int attempt = 0; attempt < 12; ++attempt) {
+    for (int attempt = 0; attempt < 24; ++attempt) {
         bool redo = false;
         const int rc = fastsumm_pass(c, theta, &redo);
         if (rc != ONB_OK) return rc;

@@ -165,18 +165,16 @@ def test_target_shards_reproduce_the_unsharded_result(arith):
         g.zero_vels(); g.treecode3(theta); u3 = g.parts(1, ("u",))["u"]
         g.zero_vels(); g.treecode2(theta); u2 = g.parts(1, ("u",))["u"]
         return uf, u3, u2
+    from onbody_b200.api import shard_range_for
     full = run(0, 1)
-    nleaf = (n + 127) // 128
     acc = [np.zeros_like(full[0]) for _ in range(3)]
     for rk in range(3):
-        lo = min(n, (nleaf * rk // 3) * 128); hi = min(n, (nleaf * (rk + 1) // 3) * 128)
+        lo, hi = shard_range_for(n, 128, rk, 3)                 # equal leaf-aligned chunks (csrc/plan.cu)
         part = run(rk, 3)
-        for k in range(2):
+        for k in range(3):
             acc[k][:, lo:hi] = part[k][:, lo:hi]
             outside = np.ones(n, bool); outside[lo:hi] = False
-            assert not part[k][:, outside].any() or k == 0      # boxwise touches only its own leaves
-        l2, h2 = n * rk // 3, n * (rk + 1) // 3
-        acc[2][:, l2:h2] = part[2][:, l2:h2]
+            assert not part[k][:, outside].any() or k == 0      # boxwise and pointwise touch only their own leaves
     for k in range(3):
         assert bits_equal(acc[k], full[k]), k
 
@@ -309,23 +307,31 @@ def test_concurrent_tree_builds_equal_sequential():
             assert bits_equal(ta[k], tb[k]), (which, k)
 
 
-def test_fastsumm_size_cache_hit_and_miss():
-    """second evaluation runs without host synchronisation from cached list sizes; a different theta must fall back cleanly"""
+def test_fastsumm_needs_no_history_and_survives_overflow(monkeypatch):
+    """the dual-tree lists live in a device-side bump pool: every evaluation - first or repeated, same or new theta - is one
+    pass without host round trips; a pool (or per-warp FIFO) that turns out too small is grown and the pass redone, with
+    identical results"""
     n = 60000
     g = _gpu("grav3d", n)
     g.init_driver(); g.make_trees(); g.upward(0); g.refine(1); g.upward(1)
     res = {}
-    for i, th in enumerate((1.4, 1.4, 1.4, 1.1, 1.1, 1.4)):       # miss(first), hit, hit, miss, hit, miss
+    for i, th in enumerate((1.4, 1.4, 1.1, 1.1, 1.4, 0.8)):
         g.zero_vels(); g.fastsumm(th)
+        assert g.phase_ms("dtt_attempts") == 1.0, (i, th)          # the default pool fits: no redo, not even on the very first call
         u = g.parts(1, ("u",))["u"]; st = g.stats(); pr = g.last_pairs()
         if th in res:
             assert bits_equal(u, res[th][0]) and st == res[th][1] and pr == res[th][2], (i, th)
         else:
             res[th] = (u, st, pr)
+    monkeypatch.setenv("ONB_DTT_POOL_INIT", "2000")                # a pool of 2000 entries and a FIFO of 8: both must overflow and grow
+    monkeypatch.setenv("ONB_DTT_QCAP_INIT", "8")
     h = _gpu("grav3d", n)
     h.init_driver(); h.make_tree(0); h.upward(0); h.make_tree(1); h.refine(1); h.upward(1)
     h.zero_vels(); h.fastsumm(1.1)
+    assert h.phase_ms("dtt_attempts") > 2.0
     assert bits_equal(h.parts(1, ("u",))["u"], res[1.1][0]) and h.stats() == res[1.1][1]
+    h.zero_vels(); h.fastsumm(1.1)
+    assert h.phase_ms("dtt_attempts") == 1.0 and bits_equal(h.parts(1, ("u",))["u"], res[1.1][0])
 
 
 def _run_legacy(s, theta):

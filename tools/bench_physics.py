@@ -8,8 +8,7 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
-from onbody_b200.api import GpuSession, driver_inputs
-from onbody_b200 import multigpu
+from onbody_b200.api import GpuSession, driver_inputs, comm_unique_id
 
 FLOPS = {"grav3d": 19, "vort3d": 28, "vortgrad3d": 64, "vort2d": 13, "vort2dtr": 15}
 physics = sys.argv[1]; method = sys.argv[2]; N = int(float(sys.argv[3])); theta = float(sys.argv[4]); steps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
@@ -20,24 +19,20 @@ if world > 1:
 x, r, s = driver_inputs(physics, N, True)
 dx = torch.from_numpy(x).cuda(); dr = torch.from_numpy(r).cuda(); ds = torch.from_numpy(s).cuda()
 g = GpuSession(physics, N, N, device=local)
-g.set_shard(rank, world)
-scratch = None
+if world > 1:      # the library's own NCCL communicator; torch only ships the id
+    box = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    g.comm_init_rank(rank, world, box[0])
 
 
 def step():
-    global scratch
     g.set_sources_ptr(N, dx.data_ptr(), dr.data_ptr(), ds.data_ptr()); g.set_targets_ptr(N, dx.data_ptr(), dr.data_ptr())
     g.timer_start()
-    if world > 1:
-        if method == "dualtree":
-            scratch = multigpu.build_both_distributed(g, N, N, rank, world, scratch)
-        else:
-            scratch = multigpu.build_sources_distributed(g, N, rank, world, scratch)
-            lo, hi = g.shard_particle_range(N, rank, world); g.make_tree_range(1, lo, hi)   # boxwise needs nc/nr of its own leaves only
+    g.make_trees()                      # with a communicator attached: range builds + exchanges inside the library
+    if method == "dualtree":
+        g.prepare_eval()
     else:
-        g.make_trees(); g.upward(0)
-        if method == "dualtree":
-            g.refine(1); g.upward(1)
+        g.upward(0)
     g.zero_vels()
     if method == "dualtree":
         g.fastsumm(theta)
