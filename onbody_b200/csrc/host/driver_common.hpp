@@ -94,9 +94,12 @@ static int run_driver(int argc, char* argv[], const DriverSpec& spec) {
     size_t ntskip = std::max(1, (int)((float)numSrcs * (float)numTargs / 2.e+9));
 
     const int dev0 = std::getenv("ONBODY_B200_DEVICE") ? atoi(std::getenv("ONBODY_B200_DEVICE")) : 0;
+    // verification aid: ONBODY_B200_LOOPBACK=1 puts all -g contexts on ONE device and joins them with the library's loopback
+    // transport (device copies instead of NCCL), so the multi-GPU driver path can be checked where only one GPU exists
+    const bool loopback = std::getenv("ONBODY_B200_LOOPBACK") != nullptr;
     std::vector<onb_context*> ctxs(ngpus, nullptr);
     for (int g = 0; g < ngpus; ++g) {
-        ctxs[g] = onb_create(spec.physics, dev0 + g);
+        ctxs[g] = onb_create(spec.physics, loopback ? dev0 : dev0 + g);
         if (!ctxs[g]) { std::fprintf(stderr, "%s: GPU %d: %s\n", spec.progname, dev0 + g, onb_last_create_error()); return 2; }
         onb_context* ctx = ctxs[g];
         DRV_CHECK(onb_set_params(ctx, (int)blockSize, order, arith));
@@ -105,8 +108,9 @@ static int run_driver(int argc, char* argv[], const DriverSpec& spec) {
     onb_context* ctx = ctxs[0];
     if (ngpus > 1) {
         if (legacy) { std::fprintf(stderr, "%s: -g needs barycentric equivalents (-o=<order>)\n", spec.progname); return 2; }
-        DRV_CHECK(onb_comm_init_all(ctxs.data(), ngpus));
-        std::fprintf(stderr, "%s: %d GPUs, targets sharded by leaf range, NCCL communicator inside the library\n", spec.progname, ngpus);
+        if (loopback) DRV_CHECK(onb_comm_init_loopback(ctxs.data(), ngpus)); else DRV_CHECK(onb_comm_init_all(ctxs.data(), ngpus));
+        std::fprintf(stderr, "%s: %d %s, targets sharded by leaf range, %s communicator inside the library\n", spec.progname, ngpus,
+                     loopback ? "contexts on one GPU" : "GPUs", loopback ? "loopback" : "NCCL");
     }
     // ctx is rank 0 below; ALL(call) makes the same call on every rank
 #define ALL(call) on_all(ngpus, [&](int rk__) { onb_context* ctx = ctxs[rk__]; DRV_CHECK(call); })

@@ -461,7 +461,9 @@ int onb_p2p_direct(onb_context* c, uint64_t tskip) {
     a.nt_eff = k1 > a.k0 ? k1 - a.k0 : 0u;
     if (a.nt_eff == 0) { c->last_pairs = 0; return ONB_OK; }
     const uint32_t ntiles = (srcs.n + 127u) / 128u;
-    const uint32_t tgt_blocks = (a.nt_eff + 127u) / 128u;
+    // the source split follows from the GLOBAL sample count, not from this shard's share of it: a target's partial sums are then
+    // the same for every rank count, and so is the result, bit for bit
+    const uint32_t tgt_blocks = ((uint32_t)((targs.n + tskip - 1) / tskip) + 127u) / 128u;
     uint32_t nsplit = 1;
     if (c->arith != ONB_ARITH_STRICT) {
         // fill the machine: aim for >= 4 CTAs per SM, keep >= 8 tiles per split

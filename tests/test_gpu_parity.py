@@ -2,9 +2,9 @@
 
 Bars: tree order, node arrays, equivalent strengths, interaction counts and - in ARITH_STRICT - every output value are
 BIT-EXACT against the oracle (the compiled reference when oracle/_ref travelled with the snapshot, else the CPU
-restatement) and against tests/golden/golden.json. The product arithmetic (ARITH_FAST: rsqrt + FMA) must stay within
-2e-6 relative rms of the reference treecode result (north_star: 1e-6 relative deviation; 2e-6 is what float32
-accumulation in a different order can itself reach) and reproduce the reference's own error against the direct sum.
+restatement) and against tests/golden/golden.json. The product arithmetic (ARITH_FAST: rsqrt + FMA, reference
+accumulation order) must stay within 1e-6 relative rms of the reference treecode result (north_star) - checked at
+N = 3e4 for every physics and at N = 1e6 for the headline one - and reproduce the reference's own error against the direct sum.
 """
 import numpy as np
 import pytest
@@ -61,7 +61,9 @@ def test_fast_arithmetic_within_tolerance(physics):
     for k in ("srcs.x", "targs.gidx", "stree.nr", "stree.x", "eqsrcs.s", "treecode2.flops", "treecode3.flops", "treecode1.flops"):
         v = a[k]
         assert bits_equal(v, b[k]) if isinstance(v, np.ndarray) else v == b[k], k
-    tol = 2e-6 if physics != "vortgrad3d" else 5e-6      # 9 gradient outputs cancel more strongly than velocities
+    # north_star: 1e-6 relative deviation from the reference treecode; the 9 gradient outputs of vortgrad3d cancel more
+    # strongly than velocities (their own float32 noise is larger): measured 3.6e-6 for its treecode1
+    tol = 1e-6 if physics != "vortgrad3d" else 5e-6
     for k in ("treecode1.u", "treecode2.u", "treecode3.u", "fastsumm.u"):
         if k in a:
             assert rel_rms(b[k], a[k]) < tol, (k, rel_rms(b[k], a[k]))
@@ -470,3 +472,61 @@ def test_prepare_eval_equals_separate_calls():
             tx, ty = x.tree(which), y.tree(which)
             for k in ("num", "ioffset", "nc", "ns", "nr", "x", "pr"):
                 assert bits_equal(tx[k], ty[k]), (which, k)
+
+
+def test_pivot_mode_1_matches_the_fast_math_reference_build():
+    """Tier B against the reference built with ITS OWN flags (-O3 -ffast-math, FMA target): g++ contracts the pivot blend of
+    barneshut.hpp:538-540 into FMAs there, which changes the intra-leaf source order of a few particles from N ~ 1e6 up.
+    onb_set_pivot_mode(1) evaluates the pivot with exactly those contractions: the source order must then equal the fast
+    build's (oracle/_ref/fast, -march=x86-64-v3) and the hashes SURVEY.md section 4 obtained independently from a
+    -march=native build at N = 1e6 and N = 1e7."""
+    from onbody_b200.api import load_library, ARITH_FAST
+    from oracle.refapi import RefSession, ref_available, fnv1a64
+    L = load_library()
+    h = lambda a: "%016x" % fnv1a64(np.ascontiguousarray(a))
+    try:
+        L.onb_set_pivot_mode(1)
+        n = 1000000
+        g = _gpu("grav3d", n, arith=ARITH_FAST); g.init_driver(); g.make_tree(0); g.make_tree(1); g.refine(1)
+        sx = g.parts(0, ("x", "s")); tg = g.parts(1, ("gidx",))["gidx"]
+        assert h(sx["x"][0]) == "9f9b637700c080e1"                       # SURVEY section 4, fast build, N = 1e6
+        assert h(tg) == "502bae5161063bf7"                                # the refined target order is the same in both builds
+        if ref_available("grav3d", "fast"):
+            o = RefSession("grav3d", n, n, build="fast"); o.init_driver(); o.make_tree(0)
+            po = o.parts(0)
+            assert bits_equal(po["x"], sx["x"]) and bits_equal(po["s"], sx["s"])
+            o.close()
+        g.close()
+        L.onb_set_pivot_mode(0)
+        g = _gpu("grav3d", n, arith=ARITH_FAST); g.init_driver(); g.make_tree(0)
+        assert h(g.parts(0, ("x",))["x"][0]) == "5b0b68d776e49dc5"       # ... and mode 0 is the strict (-O2, no contraction) build
+        g.close()
+        L.onb_set_pivot_mode(1)
+        n = 10000000
+        g = _gpu("grav3d", n, arith=ARITH_FAST); g.init_driver(); g.make_tree(0)
+        assert h(g.parts(0, ("x",))["x"][0]) == "d55259c3112840c7"       # SURVEY section 4, fast build, N = 1e7
+        g.close()
+    finally:
+        L.onb_set_pivot_mode(0)
+
+
+def test_fast_arithmetic_deviation_at_1e6():
+    """north_star: 1e-6 relative deviation from the reference treecode. The product arithmetic (rsqrt.approx + FMA, reference
+    accumulation order) against the compiled strict reference at N = 1e6: boxwise treecode (parallel-safe in the reference)
+    and the serial dual tree (the reference's OpenMP dual tree has a data race, README.md:200)."""
+    from onbody_b200.api import ARITH_FAST
+    from oracle.refapi import RefSession, ref_available
+    if not ref_available("grav3d"):
+        pytest.skip("compiled reference (oracle/_ref) not present")
+    n = 1000000
+    o = RefSession("grav3d", n, n); o.init_driver()
+    o.make_tree(0); o.upward(0); o.make_tree(1); o.refine(1); o.upward(1)
+    g = _gpu("grav3d", n, arith=ARITH_FAST); g.init_driver(); g.make_trees(); g.prepare_eval()
+    o.zero_vels(); o.treecode3(1.11111); u3 = o.parts(1)["u"]
+    g.zero_vels(); g.treecode3(1.11111)
+    d3 = rel_rms(g.parts(1, ("u",))["u"], u3)
+    o.zero_vels(); o.fastsumm(1.4); uf = o.parts(1)["u"]
+    g.zero_vels(); g.fastsumm(1.4)
+    df = rel_rms(g.parts(1, ("u",))["u"], uf)
+    print("fast arithmetic vs strict reference at N=1e6: boxwise %.3e dual tree %.3e" % (d3, df))
+    assert d3 < 1e-6 and df < 1e-6, (d3, df)
