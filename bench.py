@@ -272,6 +272,9 @@ def run_ours(args):
         # work) and evaluates the rank's target shard
         g.make_trees(); phases["both_trees"] = phases.get("both_trees", 0.0) + g.phase_ms("tree")
         g.prepare_eval(); phases["upward_refine_tgt_equiv"] = phases.get("upward_refine_tgt_equiv", 0.0) + g.phase_ms("prepare")
+        if world > 1:
+            for k in ("ag_src_planes", "bcast_eq_strengths"):
+                phases[k] = phases.get(k, 0.0) + max(0.0, g.phase_ms(k))
         g.fastsumm(THETA)
         for k in ("eval", "lists", "p2p", "downward"):
             phases[k] = phases.get(k, 0.0) + g.phase_ms(k)
@@ -330,6 +333,7 @@ def run_ours(args):
     barrier()
     launches = g.launch_count() - l0
     ph_res = dict(phases)
+    phases_last = {k: v / args.steps for k, v in ph_res.items()}
     pairs_local = g.last_pairs()
     pool_used, pool_cap = g.phase_ms("dtt_pool_used"), g.phase_ms("dtt_pool_cap")
     # ---- timed: K end-to-end steps
@@ -382,9 +386,15 @@ def run_ours(args):
         pairs_total, launches_total = int(sm[2].item()), int(sm[3].item())
     else:
         pairs_total, launches_total = int(pairs_local), int(launches)
+    exch = None
+    if world > 1:
+        exch = {k: {"ms": phases_last.get(k), "bytes_per_rank": g.phase_ms(k + "_bytes"),
+                    "GBps_algorithmic": (g.phase_ms(k + "_bytes") / (phases_last[k] * 1e-3) * 1e-9) if phases_last.get(k) else None}
+                for k in ("ag_src_planes", "bcast_eq_strengths")}
+    # tear down in the same order on every rank: the library's communicator first, then torch's
     if rank != 0:
+        g.close()
         if world > 1:
-            g.close()
             dist.destroy_process_group()
         return 0
 
@@ -430,6 +440,7 @@ def run_ours(args):
         "cold_ms_per_step": cold_ms, "cold_dtt_attempts": cold_attempts,
         "dtt_list_pool": {"entries_used": pool_used, "entries_allocated": pool_cap},
         "device_memory_peak_bytes_per_gpu": mem_peak,
+        "exchange": exch,
         "accuracy": err,
         "e2e": {"value": e2e, "unit": "Ginteractions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": sec_e2e * 1e3,
                 "note": "multi GPU: every input plane crosses PCIe once in total (onb_set_sliced_inputs: 1/world per rank, replicated by the library over NVLink); each rank returns its own target shard" if world > 1 else "sources and targets copied separately from pinned host memory; all outputs copied back"},
@@ -476,7 +487,8 @@ def run_ours(args):
                                    "sample": "N=%d particles of the same generator, whole step (trees+upward+dual-tree eval) once; the dual tree is O(N)" % n_cpu}
         except Exception as e:  # the baseline must never take the GPU number down with it
             rec["cpu_baseline"] = {"value": None, "unit": "Ginteractions/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
-    print(json.dumps(rec))
+    print(json.dumps(rec), flush=True)
+    g.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -479,6 +479,7 @@ int onb_prepare_eval(onb_context* c, int finish, uint64_t tgt_lo, uint64_t tgt_h
     c->phase_ms["prepare"] = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     if (rc == ONB_OK) rc = onb_check_flag(c, "refine (introsort depth limit: libstdc++ heapsort fallback is not restated)");
+    if (dist) onb_dist_record_exchange_times(c);
     if (rc == ONB_OK) rc = lean_after_prepare(c);
     return rc;
 }

@@ -56,7 +56,7 @@ bool onb_dist_sequential_builds(const onb_context* c) {
 
 namespace {
 
-enum { EV_E0 = 400, EV_BUILT0, EV_BUILT1, EV_REC0, EV_REC1, EV_UP, EV_EQ, EV_JOIN, EV_END };
+enum { EV_E0 = 400, EV_BUILT0, EV_BUILT1, EV_REC0, EV_REC1, EV_UP, EV_EQ, EV_JOIN, EV_END, EV_AG0, EV_AG1, EV_EQ0 };
 
 struct RecBuf { float* p = nullptr; size_t chunk_bytes = 0; };
 
@@ -121,7 +121,10 @@ int onb_dist_make_trees(onb_context* c, int which) {
     auto gather_src_planes = [&]() -> int {
         std::vector<void*> bufs; std::vector<size_t> chunks;
         int r = source_plane_list(c, bufs, chunks); if (r) return r;
+        ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_AG0), sc));
         r = onb_comm_allgather(c, bufs, chunks); if (r) return r;
+        ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_AG1), sc));
+        c->ag_timed = true;
         ONB_CUDA(cudaEventRecord(c->ev_src_planes, sc));
         c->src_planes_pending = true;
         return ONB_OK;
@@ -191,12 +194,30 @@ int onb_dist_upward_sources(onb_context* c) {
             if (b <= a) continue;
             for (int d = 0; d < c->SD; ++d) { ptrs.push_back(ep.s[d] + (size_t)a * c->ebs); bytes.push_back((size_t)(b - a) * c->ebs * sizeof(float)); owner.push_back(r); }
         }
+    ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_EQ0), sc));
     rc = onb_comm_bcast_ranges(c, ptrs, bytes, owner); if (rc) return rc;
     ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_EQ), sc));
+    c->eq_timed = true;
     rc = onb_dist_join_source_planes(c, s1); if (rc) return rc;
     rc = onb_bary_upward_mode(c, p, ep, t, ONB_UP_POS); if (rc) return rc;          // needs r of every node's first particle: after the plane gather
     if (!p.packed_valid) { rc = onb_pack_sources(c, p); if (rc) return rc; }
     ONB_CUDA(cudaStreamWaitEvent(s1, onb_cached_event(c, EV_EQ), 0));
     rc = onb_bary_upward_mode(c, p, ep, t, ONB_UP_SHARED); if (rc) return rc;
     return onb_pack_sources(c, ep);
+}
+
+// device times of the two big exchanges of the last step (valid once the streams have been synchronised): the in-place
+// all-gather of the source planes and the broadcasts of the equivalent strengths, with the bytes each rank ends up holding
+void onb_dist_record_exchange_times(onb_context* c) {
+    float ms = 0.f;
+    if (c->ag_timed && cudaEventElapsedTime(&ms, onb_cached_event(c, EV_AG0), onb_cached_event(c, EV_AG1)) == cudaSuccess) {
+        c->phase_ms["ag_src_planes"] = ms;
+        c->phase_ms["ag_src_planes_bytes"] = (double)c->plan[0].chunk * c->shard_n * sizeof(float) * (c->PD + 1 + c->SD);
+    }
+    if (c->eq_timed && cudaEventElapsedTime(&ms, onb_cached_event(c, EV_EQ0), onb_cached_event(c, EV_EQ)) == cudaSuccess) {
+        c->phase_ms["bcast_eq_strengths"] = ms;
+        c->phase_ms["bcast_eq_strengths_bytes"] = (double)c->parts[2].n * sizeof(float) * c->SD;
+    }
+    cudaGetLastError();
+    c->ag_timed = c->eq_timed = false;
 }

@@ -148,6 +148,7 @@ struct onb_context {
     // identifies the partition a sparse allocation / an uploaded plan belongs to (never 0)
     uint64_t plan_key(int which) const { return plan_key_for(parts[which].n); }
     uint64_t plan_key_for(uint64_t n) const { return ((n * 131u + (uint64_t)block) * 131u + (uint64_t)shard_n) * 131u + (uint64_t)shard_rank + 1u; }
+    bool ag_timed = false, eq_timed = false;
     cudaEvent_t ev_src_planes = nullptr; bool src_planes_pending = false;   // the source-plane all-gather may outlive onb_make_trees
     // opt-in asynchronous input copies (onb_set_async_inputs): the target planes arrive on stream2
     bool async_inputs = false, tgt_copy_pending = false, sliced_inputs = false;
@@ -260,6 +261,7 @@ bool onb_dist_sequential_builds(const onb_context* c);
 int onb_dist_make_trees(onb_context* c, int which);
 int onb_dist_join_source_planes(onb_context* c, cudaStream_t st);
 int onb_dist_upward_sources(onb_context* c);
+void onb_dist_record_exchange_times(onb_context* c);
 cudaEvent_t onb_cached_event(onb_context* c, size_t i);
 int onb_memset_plane(onb_context* c, float* p, size_t count, cudaStream_t st);
 // scan.cu
