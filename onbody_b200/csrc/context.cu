@@ -175,7 +175,7 @@ void onb_destroy(onb_context* c) {
     if (c->d_flag) cudaFree(c->d_flag);
     if (c->d_build_stats) cudaFree(c->d_build_stats);
     onb_comm_destroy(c);
-    for (int k = 0; k < 2; ++k) if (c->d_shared[k]) cudaFree(c->d_shared[k]);
+    for (int k = 0; k < 2; ++k) { if (c->d_shared[k]) cudaFree(c->d_shared[k]); if (c->rec_buf[k]) cudaFree(c->rec_buf[k]); }
     if (c->ev_src_planes) cudaEventDestroy(c->ev_src_planes);
     if (c->d_epnum) cudaFree(c->d_epnum);
     if (c->dtt_pool) cudaFree(c->dtt_pool);
@@ -375,6 +375,7 @@ int onb_make_trees_range(onb_context* c, uint64_t slo, uint64_t shi, uint64_t tl
     c->concurrent_builds = !seq_builds;
     rc = onb_tree_build(c, c->parts[0], c->trees[0], (uint32_t)slo, (uint32_t)std::min<uint64_t>(shi, c->parts[0].n));
     if (rc == ONB_OK) {
+        if (seq_builds) { c->slab_cur = 0; c->slab_off = 0; }     // same stream: the second build reuses the first one's scratch
         c->cur_stream = seq_builds ? nullptr : c->stream2; c->cur_stats_off = 8;
         rc = onb_tree_build(c, c->parts[1], c->trees[1], (uint32_t)tlo, (uint32_t)std::min<uint64_t>(thi, c->parts[1].n));
         c->cur_stream = nullptr; c->cur_stats_off = 0;

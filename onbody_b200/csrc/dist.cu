@@ -67,7 +67,16 @@ int dist_build(onb_context* c, int which, RecBuf& rb) {
     const int K = onb_leafrec_floats(c, p.are_sources);
     const size_t leaves_per_rank = (size_t)(P.chunk / (uint64_t)c->block);
     rb.chunk_bytes = leaves_per_rank * K * sizeof(float);
-    ONB_CUDA(onb_dmalloc(c, (void**)&rb.p, rb.chunk_bytes * (size_t)P.nranks));
+    // persistent (not arena scratch): with sequential builds the arena is rewound between the two builds while the records of
+    // the first tree are still waiting to be turned into node arrays
+    const size_t need = rb.chunk_bytes * (size_t)P.nranks;
+    if (c->rec_cap[which] < need) {
+        if (c->rec_buf[which]) cudaFree(c->rec_buf[which]);
+        c->rec_buf[which] = nullptr; c->rec_cap[which] = 0;
+        ONB_CUDA(cudaMalloc((void**)&c->rec_buf[which], need));
+        c->rec_cap[which] = need;
+    }
+    rb.p = c->rec_buf[which];
     if (P.hi > P.lo) {
         int rc = onb_tree_build(c, p, t, (uint32_t)P.lo, (uint32_t)P.hi, false); if (rc) return rc;
         rc = onb_tree_leaf_records(c, p, t, (uint32_t)(P.lo / c->block), (uint32_t)((P.hi + c->block - 1) / c->block), rb.p); if (rc) return rc;
@@ -129,7 +138,10 @@ int onb_dist_make_trees(onb_context* c, int which) {
         c->src_planes_pending = true;
         return ONB_OK;
     };
-    if (do_src && seq) { if ((rc = gather_src_rec())) return rc; if ((rc = gather_src_planes())) return rc; }   // under the target build
+    if (do_src && seq) {
+        if ((rc = gather_src_rec())) return rc; if ((rc = gather_src_planes())) return rc;                          // under the target build
+        c->slab_cur = 0; c->slab_off = 0;     // same stream: the target build may reuse the source build's scratch (~40 B per particle)
+    }
     if (do_tgt) {
         if (s2 != s1) { c->cur_stream = s2; c->cur_stats_off = 8; }
         rc = dist_build(c, 1, rb1);

@@ -149,6 +149,7 @@ struct onb_context {
     uint64_t plan_key(int which) const { return plan_key_for(parts[which].n); }
     uint64_t plan_key_for(uint64_t n) const { return ((n * 131u + (uint64_t)block) * 131u + (uint64_t)shard_n) * 131u + (uint64_t)shard_rank + 1u; }
     bool ag_timed = false, eq_timed = false;
+    float* rec_buf[2] = {nullptr, nullptr}; size_t rec_cap[2] = {0, 0};   // leaf records of the two trees (dist.cu)
     cudaEvent_t ev_src_planes = nullptr; bool src_planes_pending = false;   // the source-plane all-gather may outlive onb_make_trees
     // opt-in asynchronous input copies (onb_set_async_inputs): the target planes arrive on stream2
     bool async_inputs = false, tgt_copy_pending = false, sliced_inputs = false;
