@@ -164,6 +164,16 @@ ONB_API uint64_t onb_shard_chunk_for(uint64_t n, int block, int nranks);
 ONB_API int onb_plan_query(uint64_t n, int block, int nranks, int rank, int max_levels, uint32_t* own_lo, uint32_t* own_hi,
                            uint32_t* need_lo, uint32_t* need_hi, uint32_t* nshared, uint32_t* shared);
 
+/* precision of the accumulations - the reference's compile-time ACCUM macro (ongrav3d.cpp:7-8; README.md:107-112: "performing
+ * accumulations in fp64 allows the RMS error to drop to about 4e-7"). 0 (default) = float like the shipped drivers; 1 = double:
+ * the pair arithmetic stays fp32 (STORE = float), every "+=" into a target value and the downward interpolation run in fp64 and
+ * the outputs are kept in fp64 (onb_get_results_f64; onb_get_parts / onb_add_results_* return them rounded to float). All
+ * methods (direct, treecode1/2/3, dual tree), all physics; bit-exact against the reference built with ACCUM = double in
+ * ONB_ARITH_STRICT. Call before set_targets. */
+ONB_API int onb_set_accum(onb_context* c, int accum_double);
+/* which = 1 targets, 3 equivalent target points; u is [OD][n] doubles */
+ONB_API int onb_get_results_f64(onb_context* c, int which, double* u);
+
 /* memory mode: ONB_MEM_LEAN trades allocator calls for footprint (N = 1e9 on 8 GPUs, BASELINE configs[4]): one tree build at
  * a time and its scratch returned to the driver, the SoA source planes released once the float4 tiles exist (onb_get_parts
  * of sources then fails), and - in a sharded run - the target outputs and the equivalent target points become sparse planes

@@ -221,6 +221,54 @@ __global__ void __launch_bounds__(128) k_downward(const DownArgs a) {
     if (tid < cnt) for (int d = 0; d < OD; ++d) tp.u[d][p0 + tid] = acc[d];
 }
 
+// ACCUM = double (onb_set_accum): tp.u[d][ip] += wgt * sp.u[d][iep] with float weights and fp64 values (BarycentricLagrange.hpp:156
+// with A = double: the product and the sum are fp64). One CTA per target node, generic in PD / OD / order.
+template <int PD, int OD>
+__global__ void __launch_bounds__(128) k_downward_a64(const DownArgs a) {
+    const uint32_t T = a.node0 + blockIdx.x;
+    const uint32_t tn = a.t.num[T];
+    if (tn < 1) return;
+    const uint32_t tio = a.t.ioffset[T];
+    if (!(tio < a.shard_hi && tio + tn > a.shard_lo)) return;
+    const int tid = threadIdx.x, ncp = a.ncp, numEqps = a.numEqps;
+    const bool leaf = tn <= a.block;
+    const PartsView& tp = leaf ? a.tl : a.tb;
+    const uint32_t p0 = leaf ? tio : T * a.ebs;
+    const int cnt = leaf ? (int)tn : numEqps;
+    __shared__ float lsk[3 * (ONB_MAX_ORDER + 1)];
+    __shared__ float s_am[128 * AM_STRIDE];
+    __shared__ double s_pu[OD][128];
+    double acc[OD];
+    #pragma unroll
+    for (int d = 0; d < OD; ++d) acc[d] = 0.0;
+    if (T > 1) {
+        const uint32_t pe0 = (T >> 1) * a.ebs;
+        if (tid < PD * ncp) {
+            const int d = tid / ncp, k = tid % ncp;
+            int stride = 1; for (int q = 0; q < d; ++q) stride *= ncp;
+            lsk[tid] = a.tb.x[d][pe0 + stride * k];
+        }
+        if (tid < numEqps) for (int d = 0; d < OD; ++d) s_pu[d][tid] = a.tb.ud[d][pe0 + tid];
+        __syncthreads();
+        if (tid < cnt) {
+            float px[3];
+            for (int d = 0; d < PD; ++d) px[d] = tp.x[d][p0 + tid];
+            float* row = &s_am[tid * AM_STRIDE];
+            const float denom = bary_row(PD, ncp, a.ch.wk, px, lsk, row);
+            int k0 = 0, k1 = 0, k2 = 0;
+            for (int i = 0; i < numEqps; ++i) {
+                float wgt = __fmul_rn(denom, row[k0]);
+                if (PD > 1) wgt = __fmul_rn(wgt, row[ncp + k1]);
+                if (PD > 2) wgt = __fmul_rn(wgt, row[2 * ncp + k2]);
+                #pragma unroll
+                for (int d = 0; d < OD; ++d) acc[d] = __dadd_rn(acc[d], __dmul_rn((double)wgt, s_pu[d][i]));
+                if (++k0 == ncp) { k0 = 0; if (++k1 == ncp) { k1 = 0; ++k2; } }
+            }
+        }
+    }
+    if (tid < cnt) for (int d = 0; d < OD; ++d) tp.ud[d][p0 + tid] = acc[d];
+}
+
 // ---------------------------------------------------------------------------------------------
 // calcEquivalents barneshut.hpp:946-1061 - the drivers' default when -o is omitted: every non-leaf node gets
 // ceil(cnt/2) equivalents per child, each the strength-weighted merge of two consecutive points of the child (its real
@@ -296,7 +344,9 @@ Cheb make_cheb(int order) {                                                     
 int onb_bary_alloc(onb_context* c, DParts& p, DParts& ep, DTree& t) {
     const uint32_t need = (uint32_t)(t.numnodes / 2) * (uint32_t)c->ebs;
     const bool sparse = !p.are_sources && c->mem_mode == ONB_MEM_LEAN && c->shard_n > 1;
-    if (ep.n == need && !ep.unpacked_released && ep.sparse_key == (sparse ? c->plan_key(1) : 0ull)) return ONB_OK;
+    const bool want64 = !p.are_sources && c->accum64;
+    if (ep.n == need && !ep.unpacked_released && ep.sparse_key == (sparse ? c->plan_key(1) : 0ull) && (ep.ud[0] != nullptr) == want64) return ONB_OK;
+    if (sparse && want64) { c->err = "ACCUM = double is not available together with the lean memory mode of a sharded run"; return ONB_ERR_UNSUPPORTED; }
     onb_free_parts(c, ep);
     if (!sparse) return onb_alloc_parts(c, ep, need, p.are_sources);
     int rc = onb_plan_make(c->plan[1], p.n, c->block, c->shard_n, c->shard_rank); if (rc) { c->err = "upward: cannot plan the target partition"; return rc; }
@@ -369,6 +419,13 @@ int onb_bary_downward_level(onb_context* c, int level) {
     if (cnt == 0) return ONB_OK;
     a.node0 = node0;
     const dim3 G(cnt);
+    if (c->accum64) {
+        if (!c->parts[1].ud[0] || !c->parts[3].ud[0]) { c->err = "ACCUM = double: set the targets and run the target upward pass after onb_set_accum"; return ONB_ERR_ARG; }
+        if (c->PD == 3) k_downward_a64<3, 3><<<G, 128, 0, c->stream>>>(a); else k_downward_a64<2, 2><<<G, 128, 0, c->stream>>>(a);
+        ONB_LAUNCH(c);
+        ONB_CUDA(cudaGetLastError());
+        return ONB_OK;
+    }
     if (c->PD == 3 && c->ncp == 5) { if (fast) k_downward<3, 3, 5, true><<<G, 128, 0, c->stream>>>(a); else k_downward<3, 3, 5, false><<<G, 128, 0, c->stream>>>(a); }
     else if (c->PD == 3) k_downward<3, 3, 0, false><<<G, 128, 0, c->stream>>>(a);
     else k_downward<2, 2, 0, false><<<G, 128, 0, c->stream>>>(a);

@@ -46,6 +46,10 @@ int onb_alloc_parts(onb_context* c, DParts& p, uint32_t n, bool are_sources) {
     } else {
         for (int d = 0; d < c->OD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.u[d], bytes)); ONB_CUDA(cudaMemsetAsync(p.u[d], 0, bytes, st)); }
     }
+    if (!are_sources && c->accum64) {
+        if (p.sparse_key) { c->err = "ACCUM = double is not available together with the lean memory mode of a sharded run"; return ONB_ERR_UNSUPPORTED; }
+        for (int d = 0; d < c->OD; ++d) { ONB_CUDA(onb_pmalloc(c, (void**)&p.ud[d], 2 * bytes)); ONB_CUDA(cudaMemsetAsync(p.ud[d], 0, 2 * bytes, st)); }
+    }
     return ONB_OK;
 }
 // lean memory mode: once the float4 tiles exist nothing on the evaluation path reads the SoA planes of a source set again
@@ -67,7 +71,7 @@ void onb_free_parts(onb_context* c, DParts& p) {
     for (int d = 0; d < ONB_MAX_PD; ++d) if (p.x[d]) onb_pfree(c, p.x[d]);
     if (p.r) onb_pfree(c, p.r);
     for (int d = 0; d < ONB_MAX_SD; ++d) if (p.s[d]) onb_pfree(c, p.s[d]);
-    for (int d = 0; d < ONB_MAX_OD; ++d) if (p.u[d]) onb_pfree(c, p.u[d]);
+    for (int d = 0; d < ONB_MAX_OD; ++d) { if (p.u[d]) onb_pfree(c, p.u[d]); if (p.ud[d]) onb_pfree(c, p.ud[d]); }
     if (p.gidx) onb_pfree(c, p.gidx);
     if (p.gidx_spare) onb_pfree(c, p.gidx_spare);
     if (p.pk0) onb_pfree(c, p.pk0); if (p.pk1) onb_pfree(c, p.pk1); if (p.pk2) onb_pfree(c, p.pk2);
@@ -222,6 +226,14 @@ int onb_set_shard(onb_context* c, int rank, int nranks) {
     c->plan[0].valid = c->plan[1].valid = false;
     return ONB_OK;
 }
+// ACCUM of the reference drivers (ongrav3d.cpp:7-8, README.md:107-112): 0 = float (default), 1 = double - the pair arithmetic
+// stays fp32 (STORE = float), every "+=" into a target value and the downward interpolation run in fp64
+int onb_set_accum(onb_context* c, int accum_double) {
+    if (!c) return ONB_ERR_ARG;
+    if (accum_double && c->legacy) { c->err = "ACCUM = double needs barycentric equivalents (-o=<order>)"; return ONB_ERR_UNSUPPORTED; }
+    c->accum64 = accum_double != 0;
+    return ONB_OK;
+}
 int onb_set_memory_mode(onb_context* c, int mode) {
     if (!c || (mode != ONB_MEM_NORMAL && mode != ONB_MEM_LEAN)) return ONB_ERR_ARG;
     c->mem_mode = mode; return ONB_OK;
@@ -236,7 +248,7 @@ static int set_parts(onb_context* c, int which, uint64_t n, const float* const* 
     ONB_CUDA(cudaSetDevice(c->device));
     DParts& p = c->parts[which];
     const uint64_t want_key = (which == 1 && c->mem_mode == ONB_MEM_LEAN && c->shard_n > 1) ? c->plan_key_for(n) : 0ull;
-    if (p.n != n || p.unpacked_released || p.sparse_key != want_key) { onb_free_parts(c, p); int rc = onb_alloc_parts(c, p, (uint32_t)n, which == 0); if (rc) return rc; }
+    if (p.n != n || p.unpacked_released || p.sparse_key != want_key || (which == 1 && (p.ud[0] != nullptr) != c->accum64)) { onb_free_parts(c, p); int rc = onb_alloc_parts(c, p, (uint32_t)n, which == 0); if (rc) return rc; }
     if (p.gidx) { p.gidx_spare = p.gidx; p.gidx = nullptr; }      // no cudaFree/cudaMalloc per step: the next build takes it back
     const size_t bytes = (size_t)n * sizeof(float);
     bool async = false;
@@ -488,6 +500,7 @@ int onb_zero_vels(onb_context* c) {
     ONB_CUDA(cudaSetDevice(c->device));
     DParts& t = c->parts[1];
     for (int d = 0; d < c->OD; ++d) if (t.u[d]) { int rc = onb_memset_plane(c, t.u[d], (size_t)t.cap, c->stream); if (rc) return rc; }
+    for (int d = 0; d < c->OD; ++d) if (t.ud[d]) ONB_CUDA(cudaMemsetAsync(t.ud[d], 0, (size_t)t.cap * sizeof(double), c->stream));
     return ONB_OK;
 }
 int onb_naive(onb_context* c, uint64_t tskip, float* flops) {
@@ -575,6 +588,7 @@ int onb_get_parts(onb_context* c, int which, float* x, float* r, float* s, float
     if (x) for (int d = 0; d < c->PD; ++d) ONB_CUDA(onb_copy_plane_to_host(c, x + d * n, p.x[d], 0, n, c->stream));
     if (r) ONB_CUDA(onb_copy_plane_to_host(c, r, p.r, 0, n, c->stream));
     if (s && p.are_sources) for (int d = 0; d < c->SD; ++d) ONB_CUDA(onb_copy_plane_to_host(c, s + d * n, p.s[d], 0, n, c->stream));
+    if (u && !p.are_sources && p.ud[0]) { int rrc = onb_round_outputs(c, p); if (rrc) return rrc; }      // ACCUM = double: u = (float) ud
     if (u && !p.are_sources) for (int d = 0; d < c->OD; ++d) ONB_CUDA(onb_copy_plane_to_host(c, u + d * n, p.u[d], 0, n, c->stream));
     ONB_CUDA(cudaStreamSynchronize(c->stream));
     if (gidx && p.gidx) {
@@ -582,6 +596,16 @@ int onb_get_parts(onb_context* c, int which, float* x, float* r, float* s, float
         ONB_CUDA(cudaMemcpy(tmp.data(), p.gidx, n * 4, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < n; ++i) gidx[i] = tmp[i];
     }
+    return ONB_OK;
+}
+// ACCUM = double: the outputs of targets (which = 1) or equivalent target points (which = 3) in full precision, u is [OD][n]
+int onb_get_results_f64(onb_context* c, int which, double* u) {
+    if (which != 1 && which != 3) return ONB_ERR_ARG;
+    ONB_CUDA(cudaSetDevice(c->device));
+    DParts& p = c->parts[which];
+    if (!p.ud[0]) { c->err = "get_results_f64: ACCUM = double is not selected (onb_set_accum)"; return ONB_ERR_ARG; }
+    for (int d = 0; d < c->OD; ++d) ONB_CUDA(cudaMemcpyAsync(u + (size_t)d * p.n, p.ud[d], (size_t)p.n * sizeof(double), cudaMemcpyDefault, c->stream));
+    ONB_CUDA(cudaStreamSynchronize(c->stream));
     return ONB_OK;
 }
 // the output planes of this context's shard only: u is [OD][n], elements [lo,hi) of every plane are written (the multi-GPU
@@ -592,6 +616,7 @@ int onb_get_shard_results(onb_context* c, float* u, uint64_t plane_stride, uint6
     uint32_t lo, hi; onb_shard_range(c, &lo, &hi);
     if (lo_out) *lo_out = lo; if (hi_out) *hi_out = hi;
     if (!u || hi <= lo) return ONB_OK;
+    if (p.ud[0]) { int rrc = onb_round_outputs(c, p); if (rrc) return rrc; }
     const size_t stride = plane_stride ? (size_t)plane_stride : (size_t)p.n;
     for (int d = 0; d < c->OD; ++d) ONB_CUDA(cudaMemcpyAsync(u + (size_t)d * stride + lo, p.u[d] + lo, (size_t)(hi - lo) * sizeof(float), cudaMemcpyDefault, c->stream));
     ONB_CUDA(cudaStreamSynchronize(c->stream));
@@ -622,6 +647,7 @@ static int add_results(onb_context* c, float* const* out) {
     uint32_t lo, hi; onb_shard_range(c, &lo, &hi);
     lo = std::max(lo, p.build_lo); hi = std::min(hi, p.build_hi);      // a range-restricted build ordered (and indexed) only its own range
     if (hi <= lo) return ONB_OK;
+    if (p.ud[0]) { int rrc = onb_round_outputs(c, p); if (rrc) return rrc; }
     bool all_device = true;
     for (int d = 0; d < c->OD; ++d) {
         cudaPointerAttributes at;
@@ -739,6 +765,7 @@ int onb_timer_start(onb_context* c) {
 }
 double onb_timer_stop_ms(onb_context* c) {
     if (!c->ev_t0) return -1.0;
+    cudaSetDevice(c->device);
     if (cudaEventRecord(c->ev_t1, c->stream) != cudaSuccess || cudaEventSynchronize(c->ev_t1) != cudaSuccess) return -1.0;
     float ms = 0.f; cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1);
     return ms;
@@ -747,6 +774,7 @@ uint64_t onb_launch_count(const onb_context* c) { return c->launches; }
 
 void* onb_device_ptr(onb_context* c, int which, int field) {
     if (which < 0 || which > 3) return nullptr;
+    cudaSetDevice(c->device);
     onb_join_copies(c);
     DParts& p = c->parts[which];
     if (field >= 0 && field < 3) return p.x[field];

@@ -54,6 +54,7 @@ cudaError_t onb_dmalloc(onb_context* c, void** p, size_t bytes) {
         ++c->slab_cur; c->slab_off = 0;
     }
     onb_context::Slab s; s.cap = std::max<size_t>(bytes, (size_t)64 << 20); s.p = nullptr;
+    cudaSetDevice(c->device);
     cudaError_t e = cudaMalloc((void**)&s.p, s.cap);
     if (e != cudaSuccess) return e;
     c->slabs.push_back(s); c->slab_cur = c->slabs.size() - 1; c->slab_off = bytes;
@@ -62,6 +63,8 @@ cudaError_t onb_dmalloc(onb_context* c, void** p, size_t bytes) {
 }
 
 void onb_scratch_reset(onb_context* c) {
+    cudaSetDevice(c->device);         // every public phase call starts here, possibly on a fresh host thread (the -g drivers): the
+                                      // current device is per-thread state and all allocations below must land on OUR device
     c->cur_stream = nullptr;          // (an error return may have left a phase's secondary stream selected)
     onb_join_copies(c);
     if (c->slabs.size() > 1) {          // coalesce what the last call needed into one slab
@@ -77,6 +80,7 @@ void onb_scratch_reset(onb_context* c) {
 
 // lean memory mode: hand the arena back to the driver (the big users are the tree builds: ~40 B per particle)
 void onb_scratch_trim(onb_context* c) {
+    cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     for (auto& s : c->slabs) cudaFree(s.p);

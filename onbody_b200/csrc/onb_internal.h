@@ -49,6 +49,7 @@ struct DParts {
     float* r = nullptr;
     float* s[ONB_MAX_SD] = {nullptr, nullptr, nullptr};
     float* u[ONB_MAX_OD] = {nullptr};
+    double* ud[ONB_MAX_OD] = {nullptr};   // ACCUM = double (onb_set_accum): the outputs are accumulated and kept in fp64, u is their rounded copy
     uint32_t* gidx = nullptr;
     uint32_t* gidx_spare = nullptr;   // the index plane of the previous build, kept for reuse (gidx == nullptr means "no tree order yet")
     // packed planes for the pair kernels (see p2p.cu):
@@ -85,6 +86,7 @@ struct PartsView {
     float* r;
     float* s[ONB_MAX_SD];
     float* u[ONB_MAX_OD];
+    double* ud[ONB_MAX_OD];
     uint32_t* gidx;
 };
 struct TreeView {
@@ -104,6 +106,7 @@ struct onb_context {
     int PD = 3, SD = 1, OD = 3, flops_per_pair = 19;
     bool has_tr = false, has_fastsumm = true;
     int block = 128, order = 4, arith = ONB_ARITH_FAST;
+    bool accum64 = false;   // the reference's ACCUM = double (ongrav3d.cpp:8): fp32 pair arithmetic, fp64 accumulation and outputs
     int ncp = 5, num_eqps = 125, ebs = 128;
     // legacy equivalents (-o omitted, order = -1, barneshut.hpp:946-1061): per-node counts of pair-merged equivalents
     bool legacy = false;
@@ -184,7 +187,7 @@ static inline PartsView view_of(const DParts& p) {
     for (int d = 0; d < ONB_MAX_PD; ++d) v.x[d] = p.x[d];
     v.r = p.r;
     for (int d = 0; d < ONB_MAX_SD; ++d) v.s[d] = p.s[d];
-    for (int d = 0; d < ONB_MAX_OD; ++d) v.u[d] = p.u[d];
+    for (int d = 0; d < ONB_MAX_OD; ++d) { v.u[d] = p.u[d]; v.ud[d] = p.ud[d]; }
     v.gidx = p.gidx;
     return v;
 }
@@ -237,6 +240,7 @@ int onb_legacy_equivalents(onb_context* c, DParts& p, DParts& ep, DTree& t);
 // p2p.cu
 int onb_pack_sources(onb_context* c, DParts& p);
 int onb_p2p_direct(onb_context* c, uint64_t tskip);
+int onb_round_outputs(onb_context* c, DParts& p);      // ACCUM = double: u = (float) ud
 // interaction lists are CSR over "target work items": item w covers targets [tgt_off[w], +tgt_cnt[w]) of
 // parts[tgt_which], and interacts with entries [start[w], start[w+1]); entry = source node id, bit 31 set = use the
 // node's equivalent particles, clear = its real particles.

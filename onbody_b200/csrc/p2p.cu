@@ -105,6 +105,7 @@ __device__ __forceinline__ void tile_compute(const TileSmem<PHYS>& sm, int buf, 
 struct P2PArgs {
     const float* tx[3]; const float* tr; float* tu[ONB_MAX_OD];     // leaf targets (real particles)
     const float* bx[3]; const float* br; float* bu[ONB_MAX_OD];     // box targets (equivalent points)
+    double* tud[ONB_MAX_OD]; double* bud[ONB_MAX_OD];               // ACCUM = double: the fp64 output planes of the two target sets
     const uint32_t* t_ioffset; const uint32_t* t_num;
     const float4* s_pk0; const float4* s_pk1; const float* s_pk2;   // real sources
     const float4* e_pk0; const float4* e_pk1; const float* e_pk2;   // equivalent sources
@@ -245,6 +246,109 @@ __global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__
     }
 }
 
+// ACCUM = double (the reference's STORE = float, ACCUM = double build, ongrav3d.cpp:7-8): the pair arithmetic is the fp32 one of
+// pair<> - each contribution is a rounded float, exactly the "(A)(r3 * dx)" of the reference kernels - and every "+=" is an fp64
+// addition into fp64 outputs. One target per thread, list order; the fp64 adds and the float->double conversions run at a
+// fraction of the FP32 rate on this GPU, which is the price the reference's README describes for the last digits.
+template <int PHYS, bool STRICT>
+__global__ void __launch_bounds__(128) k_p2p_lists_a64(const __grid_constant__ P2PArgs a) {
+    constexpr int OD = Phys<PHYS>::OD;
+    __shared__ TileSmem<PHYS> sm;
+    const int tid = threadIdx.x;
+    const uint32_t w = blockIdx.x;
+    uint32_t e0, e1; item_range(a, w, e0, e1);
+    if (e0 >= e1) return;
+    const uint32_t T = a.item_node ? a.item_node[w] : a.node_base + w;
+    const uint32_t tn = a.t_num[T];
+    const bool leaf = tn <= a.block;
+    const uint32_t toff = leaf ? a.t_ioffset[T] : T * a.ebs;
+    const uint32_t tcnt = leaf ? tn : a.num_eqps;
+    const bool valid = (uint32_t)tid < tcnt;
+    const uint32_t ti = toff + (valid ? (uint32_t)tid : 0u);
+    Tgt tg;
+    tg.x = leaf ? a.tx[0][ti] : a.bx[0][ti];
+    tg.y = leaf ? a.tx[1][ti] : a.bx[1][ti];
+    tg.z = Phys<PHYS>::PD > 2 ? (leaf ? a.tx[2][ti] : a.bx[2][ti]) : 0.f;
+    tg.r2 = 0.f;
+    if (Phys<PHYS>::TR) { const float r = leaf ? a.tr[ti] : a.br[ti]; tg.r2 = __fmul_rn(r, r); }
+    double acc[OD];
+    #pragma unroll
+    for (int d = 0; d < OD; ++d) acc[d] = valid ? (leaf ? a.tud[d][ti] : a.bud[d][ti]) : 0.0;
+    if (tid == 0) { ptx::mbar_init(&sm.bar[0], 1); ptx::mbar_init(&sm.bar[1], 1); ptx::fence_mbar_init(); }
+    __syncthreads();
+    TileRef cur = decode_entry(a, a.entries[e0]);
+    if (tid == 0) tile_issue<PHYS>(sm, 0, cur);
+    for (uint32_t e = e0; e < e1; ++e) {
+        const int buf = (e - e0) & 1;
+        const uint32_t par = ((e - e0) >> 1) & 1;
+        TileRef nxt = cur;
+        if (e + 1 < e1) { nxt = decode_entry(a, a.entries[e + 1]); if (tid == 0) tile_issue<PHYS>(sm, buf ^ 1, nxt); }
+        ptx::mbar_wait(&sm.bar[buf], par);
+        const float4* __restrict__ A = sm.a[buf];
+        const float4* __restrict__ B = sm.b[buf];
+        const float*  __restrict__ C = sm.c[buf] + (Phys<PHYS>::F1 ? (cur.off & 3u) : 0u);
+        const int cnt = (int)cur.cnt;
+        #pragma unroll 4
+        for (int j = 0; j < cnt; ++j)
+            pair_a64<PHYS, STRICT>(A[j], Phys<PHYS>::NF4 > 1 ? B[j] : make_float4(0.f, 0.f, 0.f, 0.f), Phys<PHYS>::F1 ? C[j] : 0.f, tg, acc);
+        __syncthreads();
+        cur = nxt;
+    }
+    if (valid) {
+        #pragma unroll
+        for (int d = 0; d < OD; ++d) { if (leaf) a.tud[d][ti] = acc[d]; else a.bud[d][ti] = acc[d]; }
+    }
+}
+
+// ACCUM = double direct sum: every sample target against all sources in source order, one thread per target
+struct DirectArgs64 { const float* tx[3]; const float* tr; double* tud[ONB_MAX_OD]; const float4* s_pk0; const float4* s_pk1; const float* s_pk2; uint32_t nsrc, tskip, nt_eff, k0; };
+template <int PHYS, bool STRICT>
+__global__ void __launch_bounds__(128) k_p2p_direct_a64(const __grid_constant__ DirectArgs64 a) {
+    constexpr int OD = Phys<PHYS>::OD;
+    __shared__ TileSmem<PHYS> sm;
+    const int tid = threadIdx.x;
+    const uint32_t k = blockIdx.x * 128u + tid;
+    const bool valid = k < a.nt_eff;
+    const uint32_t ti = (a.k0 + (valid ? k : 0u)) * a.tskip;
+    Tgt tg;
+    tg.x = a.tx[0][ti]; tg.y = a.tx[1][ti]; tg.z = Phys<PHYS>::PD > 2 ? a.tx[2][ti] : 0.f; tg.r2 = 0.f;
+    if (Phys<PHYS>::TR) { const float r = a.tr[ti]; tg.r2 = __fmul_rn(r, r); }
+    double acc[OD];
+    #pragma unroll
+    for (int d = 0; d < OD; ++d) acc[d] = valid ? a.tud[d][ti] : 0.0;
+    const uint32_t ntiles = (a.nsrc + 127u) / 128u;
+    if (tid == 0) { ptx::mbar_init(&sm.bar[0], 1); ptx::mbar_init(&sm.bar[1], 1); ptx::fence_mbar_init(); }
+    __syncthreads();
+    auto tile_of = [&](uint32_t t) { TileRef r; r.p0 = a.s_pk0; r.p1 = a.s_pk1; r.p2 = a.s_pk2; r.off = t * 128u; r.cnt = min(128u, a.nsrc - t * 128u); return r; };
+    TileRef cur = tile_of(0);
+    if (tid == 0) tile_issue<PHYS>(sm, 0, cur);
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        const uint32_t par = (t >> 1) & 1;
+        TileRef nxt = cur;
+        if (t + 1 < ntiles) { nxt = tile_of(t + 1); if (tid == 0) tile_issue<PHYS>(sm, buf ^ 1, nxt); }
+        ptx::mbar_wait(&sm.bar[buf], par);
+        const float4* __restrict__ A = sm.a[buf];
+        const float4* __restrict__ B = sm.b[buf];
+        const float*  __restrict__ C = sm.c[buf];
+        const int cnt = (int)cur.cnt;
+        #pragma unroll 4
+        for (int j = 0; j < cnt; ++j)
+            pair_a64<PHYS, STRICT>(A[j], Phys<PHYS>::NF4 > 1 ? B[j] : make_float4(0.f, 0.f, 0.f, 0.f), Phys<PHYS>::F1 ? C[j] : 0.f, tg, acc);
+        __syncthreads();
+        cur = nxt;
+    }
+    if (valid) {
+        #pragma unroll
+        for (int d = 0; d < OD; ++d) a.tud[d][ti] = acc[d];
+    }
+}
+
+__global__ void k_round_outputs(const double* __restrict__ ud, float* __restrict__ u, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) u[i] = __double2float_rn(ud[i]);
+}
+
 // nsplit > 1: acc(target) = ((stored + partial_0) + partial_1) + ... in segment order (deterministic for a given nsplit)
 template <int OD>
 __global__ void __launch_bounds__(128) k_p2p_reduce(const __grid_constant__ P2PArgs a) {
@@ -377,6 +481,17 @@ void launch_lists(onb_context* c, const P2PArgs& a, uint32_t nitems) {
     else launch_lists_t<PHYS, 4>(c, a, nitems, packed);
 }
 template <int PHYS>
+void launch_lists_a64(onb_context* c, const P2PArgs& a, uint32_t nitems) {
+    if (c->arith == ONB_ARITH_STRICT) k_p2p_lists_a64<PHYS, true><<<nitems, 128, 0, c->stream>>>(a);
+    else                              k_p2p_lists_a64<PHYS, false><<<nitems, 128, 0, c->stream>>>(a);
+}
+template <int PHYS>
+void launch_direct_a64(onb_context* c, const DirectArgs64& a) {
+    const uint32_t grid = (a.nt_eff + 127) / 128;
+    if (c->arith == ONB_ARITH_STRICT) k_p2p_direct_a64<PHYS, true><<<grid, 128, 0, c->stream>>>(a);
+    else                              k_p2p_direct_a64<PHYS, false><<<grid, 128, 0, c->stream>>>(a);
+}
+template <int PHYS>
 void launch_direct(onb_context* c, const DirectArgs& a) {
     dim3 grid((a.nt_eff + 127) / 128, a.nsplit);
     if (c->arith == ONB_ARITH_STRICT) k_p2p_direct<PHYS, true><<<grid, 128, 0, c->stream>>>(a);
@@ -429,6 +544,21 @@ int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tg
     a.block = c->block; a.ebs = c->ebs; a.num_eqps = c->num_eqps; a.node_base = wl.node_base; a.nentries = (uint32_t)wl.nentries;
     a.s_epnum = c->legacy ? c->d_epnum : nullptr;
     a.nsplit = nsplit; a.partial = nullptr; a.ebase = wl.ebase;
+    for (int d = 0; d < ONB_MAX_OD; ++d) { a.tud[d] = tl.ud[d]; a.bud[d] = tb.ud[d]; }
+    if (c->accum64) {
+        if (!tl.ud[0] || (tgt_which_box != tgt_which_leaf && tb.n && !tb.ud[0])) { c->err = "ACCUM = double: set the targets (and build the equivalent target points) after onb_set_accum"; return ONB_ERR_ARG; }
+        a.nsplit = 1;
+        switch (c->physics) {
+            case ONB_GRAV3D:     launch_lists_a64<ONB_GRAV3D>(c, a, wl.nitems); break;
+            case ONB_VORT3D:     launch_lists_a64<ONB_VORT3D>(c, a, wl.nitems); break;
+            case ONB_VORTGRAD3D: launch_lists_a64<ONB_VORTGRAD3D>(c, a, wl.nitems); break;
+            case ONB_VORT2D:     launch_lists_a64<ONB_VORT2D>(c, a, wl.nitems); break;
+            default:             launch_lists_a64<ONB_VORT2DTR>(c, a, wl.nitems); break;
+        }
+        ONB_LAUNCH(c);
+        ONB_CUDA(cudaGetLastError());
+        return ONB_OK;
+    }
     if (nsplit > 1) ONB_CUDA(onb_dmalloc(c, (void**)&a.partial, (size_t)wl.nitems * nsplit * c->OD * 128u * sizeof(float)));
     switch (c->physics) {
         case ONB_GRAV3D:     launch_lists<ONB_GRAV3D>(c, a, wl.nitems); break;
@@ -460,6 +590,25 @@ int onb_p2p_direct(onb_context* c, uint64_t tskip) {
     const uint32_t k1 = (uint32_t)((hi + tskip - 1) / tskip);
     a.nt_eff = k1 > a.k0 ? k1 - a.k0 : 0u;
     if (a.nt_eff == 0) { c->last_pairs = 0; return ONB_OK; }
+    if (c->accum64) {
+        if (!targs.ud[0]) { c->err = "ACCUM = double: set the targets after onb_set_accum"; return ONB_ERR_ARG; }
+        DirectArgs64 b;
+        for (int d = 0; d < 3; ++d) b.tx[d] = targs.x[d];
+        b.tr = targs.r;
+        for (int d = 0; d < ONB_MAX_OD; ++d) b.tud[d] = targs.ud[d];
+        b.s_pk0 = srcs.pk0; b.s_pk1 = srcs.pk1; b.s_pk2 = srcs.pk2; b.nsrc = srcs.n; b.tskip = (uint32_t)tskip; b.nt_eff = a.nt_eff; b.k0 = a.k0;
+        switch (c->physics) {
+            case ONB_GRAV3D:     launch_direct_a64<ONB_GRAV3D>(c, b); break;
+            case ONB_VORT3D:     launch_direct_a64<ONB_VORT3D>(c, b); break;
+            case ONB_VORTGRAD3D: launch_direct_a64<ONB_VORTGRAD3D>(c, b); break;
+            case ONB_VORT2D:     launch_direct_a64<ONB_VORT2D>(c, b); break;
+            default:             launch_direct_a64<ONB_VORT2DTR>(c, b); break;
+        }
+        ONB_LAUNCH(c);
+        ONB_CUDA(cudaGetLastError());
+        c->last_pairs = (uint64_t)a.nt_eff * (uint64_t)srcs.n;
+        return ONB_OK;
+    }
     const uint32_t ntiles = (srcs.n + 127u) / 128u;
     // the source split follows from the GLOBAL sample count, not from this shard's share of it: a target's partial sums are then
     // the same for every rank count, and so is the result, bit for bit
@@ -495,6 +644,13 @@ int onb_p2p_direct(onb_context* c, uint64_t tskip) {
     return ONB_OK;
 }
 
+int onb_round_outputs(onb_context* c, DParts& p) {
+    if (!p.ud[0] || p.n == 0) return ONB_OK;
+    for (int d = 0; d < c->OD; ++d) { k_round_outputs<<<(p.n + 255) / 256, 256, 0, c->stream>>>(p.ud[d], p.u[d], p.n); ONB_LAUNCH(c); }
+    ONB_CUDA(cudaGetLastError());
+    return ONB_OK;
+}
+
 void onb_free_worklist(onb_context* c, WorkList& wl) {
     if (wl.tgt_node) onb_dfree(c, wl.tgt_node);
     if (wl.start) onb_dfree(c, wl.start);
@@ -506,7 +662,7 @@ extern "C" void onb_set_p2p_tpt(int tpt) { const int t = tpt & 15; g_p2p_tpt = (
 
 extern "C" double onb_measure_fp32_peak(onb_context* c) {
     if (!c) return -1.0;
-    onb_scratch_reset(c);
+    onb_scratch_reset(c);      // (selects the context's device)
     const int blocks = c->sm_count * 8, threads = 256, iters = 2000;
     float* d = nullptr;
     if (onb_dmalloc(c, (void**)&d, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return -1.0;

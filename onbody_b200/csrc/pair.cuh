@@ -125,6 +125,24 @@ __device__ __forceinline__ void pair(const float4 p0, const float4 p1, const flo
     }
 }
 
+// ACCUM = double: float contributions, fp64 accumulation (see p2p.cu k_p2p_lists_a64)
+template <int PHYS, bool STRICT>
+__device__ __forceinline__ void pair_a64(const float4 p0, const float4 p1, const float p2, const Tgt& t, double* __restrict__ acc) {
+    constexpr int OD = Phys<PHYS>::OD;
+    float cc[OD];
+    #pragma unroll
+    for (int d = 0; d < OD; ++d) cc[d] = 0.0f;
+    pair<PHYS, STRICT>(p0, p1, p2, t, cc);             // 0 + x and fma(a, b, 0) are exact: cc holds the rounded float contributions
+    #pragma unroll
+    for (int d = 0; d < OD; ++d) acc[d] = __dadd_rn(acc[d], (double)cc[d]);
+}
+
+// one name for both accumulator types (pointwise.cu instantiates its traversal for float and for double outputs)
+template <int PHYS, bool STRICT>
+__device__ __forceinline__ void pair_acc(const float4 p0, const float4 p1, const float p2, const Tgt& t, float* __restrict__ acc) { pair<PHYS, STRICT>(p0, p1, p2, t, acc); }
+template <int PHYS, bool STRICT>
+__device__ __forceinline__ void pair_acc(const float4 p0, const float4 p1, const float p2, const Tgt& t, double* __restrict__ acc) { pair_a64<PHYS, STRICT>(p0, p1, p2, t, acc); }
+
 
 }  // namespace
 

@@ -21,7 +21,7 @@ __device__ __forceinline__ float dist_sq_step(float dist, float v) {
 }
 
 struct PwArgs {
-    const float* tx[3]; const float* tr; float* tu[ONB_MAX_OD];
+    const float* tx[3]; const float* tr; float* tu[ONB_MAX_OD]; double* tud[ONB_MAX_OD];
     TreeView st;
     const float4* s_pk0; const float4* s_pk1; const float* s_pk2;
     const float4* e_pk0; const float4* e_pk1; const float* e_pk2;
@@ -32,9 +32,13 @@ struct PwArgs {
 
 constexpr int PW_WARPS = 4;
 
-template <int PHYS, bool STRICT, int VARIANT>
+template <bool A64> struct AccType { typedef float type; };
+template <> struct AccType<true> { typedef double type; };
+
+template <int PHYS, bool STRICT, int VARIANT, bool A64>
 __global__ void __launch_bounds__(PW_WARPS * 32) k_pointwise(const __grid_constant__ PwArgs a) {
     constexpr int OD = Phys<PHYS>::OD, PD = Phys<PHYS>::PD;
+    typedef typename AccType<A64>::type acc_t;      // ACCUM = double: fp64 outputs (onb_set_accum)
     __shared__ float4 sA[PW_WARPS][128];
     __shared__ float4 sB[PW_WARPS][Phys<PHYS>::NF4 > 1 ? 128 : 1];
     __shared__ float  sC[PW_WARPS][Phys<PHYS>::F1 ? 128 : 1];
@@ -49,9 +53,9 @@ __global__ void __launch_bounds__(PW_WARPS * 32) k_pointwise(const __grid_consta
     Tgt tg; tg.x = a.tx[0][ti]; tg.y = a.tx[1][ti]; tg.z = PD > 2 ? a.tx[2][ti] : 0.f; tg.r2 = 0.f;
     if (Phys<PHYS>::TR) { const float r = a.tr[ti]; tg.r2 = __fmul_rn(r, r); }
     const float tpos[3] = { tg.x, tg.y, tg.z };
-    float acc[OD];
+    acc_t acc[OD];
     #pragma unroll
-    for (int d = 0; d < OD; ++d) acc[d] = valid ? a.tu[d][ti] : 0.f;
+    for (int d = 0; d < OD; ++d) acc[d] = valid ? (A64 ? (acc_t)a.tud[d][ti] : (acc_t)a.tu[d][ti]) : (acc_t)0;
     uint32_t n_leaf = 0, n_box = 0; unsigned long long pairs = 0;
 
     int sp = 0;
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32) k_pointwise(const __grid_consta
             if (mine) {
                 #pragma unroll 4
                 for (uint32_t j = 0; j < sn; ++j)
-                    pair<PHYS, STRICT>(sA[wib][j], Phys<PHYS>::NF4 > 1 ? sB[wib][j] : make_float4(0.f, 0.f, 0.f, 0.f), Phys<PHYS>::F1 ? sC[wib][j] : 0.f, tg, acc);
+                    pair_acc<PHYS, STRICT>(sA[wib][j], Phys<PHYS>::NF4 > 1 ? sB[wib][j] : make_float4(0.f, 0.f, 0.f, 0.f), Phys<PHYS>::F1 ? sC[wib][j] : 0.f, tg, acc);
                 ++n_leaf; pairs += sn;
             }
             __syncwarp();
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32) k_pointwise(const __grid_consta
                 if (accept) {
                     #pragma unroll 4
                     for (uint32_t j = 0; j < cnt; ++j)
-                        pair<PHYS, STRICT>(sA[wib][j], Phys<PHYS>::NF4 > 1 ? sB[wib][j] : make_float4(0.f, 0.f, 0.f, 0.f), Phys<PHYS>::F1 ? sC[wib][j] : 0.f, tg, acc);
+                        pair_acc<PHYS, STRICT>(sA[wib][j], Phys<PHYS>::NF4 > 1 ? sB[wib][j] : make_float4(0.f, 0.f, 0.f, 0.f), Phys<PHYS>::F1 ? sC[wib][j] : 0.f, tg, acc);
                     ++n_box; pairs += cnt;
                 }
                 __syncwarp();
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32) k_pointwise(const __grid_consta
                     p0 = make_float4(a.st.x[0][S], a.st.x[1][S], a.st.x[2][S], r2);
                     p1 = make_float4(a.st.s[0][S], a.st.s[1][S], a.st.s[2][S], 0.f);
                 } else p0 = make_float4(a.st.x[0][S], a.st.x[1][S], r2, a.st.s[0][S]);
-                pair<PHYS, STRICT>(p0, p1, p2, tg, acc);
+                pair_acc<PHYS, STRICT>(p0, p1, p2, tg, acc);
                 ++n_box; pairs += 1;
             }
         }
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(PW_WARPS * 32) k_pointwise(const __grid_consta
     }
     if (valid) {
         #pragma unroll
-        for (int d = 0; d < OD; ++d) a.tu[d][ti] = acc[d];
+        for (int d = 0; d < OD; ++d) { if (A64) a.tud[d][ti] = (double)acc[d]; else a.tu[d][ti] = (float)acc[d]; }
     }
     // counters: one atomic per warp
     unsigned long long v[3] = { n_leaf, n_box, pairs };
@@ -147,11 +151,15 @@ __global__ void __launch_bounds__(PW_WARPS * 32) k_pointwise(const __grid_consta
     }
 }
 
+template <int PHYS, bool A64>
+void launch_pw_t(onb_context* c, const PwArgs& a, uint32_t blocks, int variant) {
+    const bool st = c->arith == ONB_ARITH_STRICT;
+    if (variant == 2) { if (st) k_pointwise<PHYS, true, 2, A64><<<blocks, PW_WARPS * 32, 0, c->stream>>>(a); else k_pointwise<PHYS, false, 2, A64><<<blocks, PW_WARPS * 32, 0, c->stream>>>(a); }
+    else              { if (st) k_pointwise<PHYS, true, 1, A64><<<blocks, PW_WARPS * 32, 0, c->stream>>>(a); else k_pointwise<PHYS, false, 1, A64><<<blocks, PW_WARPS * 32, 0, c->stream>>>(a); }
+}
 template <int PHYS>
 void launch_pw(onb_context* c, const PwArgs& a, uint32_t blocks, int variant) {
-    const bool st = c->arith == ONB_ARITH_STRICT;
-    if (variant == 2) { if (st) k_pointwise<PHYS, true, 2><<<blocks, PW_WARPS * 32, 0, c->stream>>>(a); else k_pointwise<PHYS, false, 2><<<blocks, PW_WARPS * 32, 0, c->stream>>>(a); }
-    else              { if (st) k_pointwise<PHYS, true, 1><<<blocks, PW_WARPS * 32, 0, c->stream>>>(a); else k_pointwise<PHYS, false, 1><<<blocks, PW_WARPS * 32, 0, c->stream>>>(a); }
+    if (c->accum64) launch_pw_t<PHYS, true>(c, a, blocks, variant); else launch_pw_t<PHYS, false>(c, a, blocks, variant);
 }
 
 }  // namespace
@@ -166,7 +174,8 @@ int onb_run_treecode2(onb_context* c, float theta, int variant) {
     PwArgs a;
     for (int d = 0; d < 3; ++d) a.tx[d] = t.x[d];
     a.tr = t.r;
-    for (int d = 0; d < ONB_MAX_OD; ++d) a.tu[d] = t.u[d];
+    for (int d = 0; d < ONB_MAX_OD; ++d) { a.tu[d] = t.u[d]; a.tud[d] = t.ud[d]; }
+    if (c->accum64 && !t.ud[0]) { c->err = "ACCUM = double: set the targets after onb_set_accum"; return ONB_ERR_ARG; }
     a.st = view_of(c->trees[0]);
     a.s_pk0 = srcs.pk0; a.s_pk1 = srcs.pk1; a.s_pk2 = srcs.pk2;
     a.e_pk0 = eqs.pk0; a.e_pk1 = eqs.pk1; a.e_pk2 = eqs.pk2;

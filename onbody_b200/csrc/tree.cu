@@ -601,6 +601,7 @@ __global__ void k_leafrec_apply(const FinishArgs a, const float* __restrict__ re
 // ---------------------------------------------------------------------------------------------
 extern "C" int onb_get_build_stats(onb_context* c, uint64_t out[5]) {
     unsigned long long h[5];
+    ONB_CUDA(cudaSetDevice(c->device));
     ONB_CUDA(cudaStreamSynchronize(c->stream));
     ONB_CUDA(cudaMemcpy(h, c->d_build_stats, sizeof(h), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 5; ++i) out[i] = h[i];
