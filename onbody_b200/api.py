@@ -103,6 +103,8 @@ def load_library():
     L.onb_comm_destroy.argtypes = [C.c_void_p]
     L.onb_comm_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
     L.onb_set_memory_mode.argtypes = [C.c_void_p, C.c_int]
+    L.onb_set_accum.argtypes = [C.c_void_p, C.c_int]
+    L.onb_get_results_f64.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.onb_device_memory.argtypes = [C.c_void_p, _u64p, _u64p]
     L.onb_shard_range_for.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, _u64p, _u64p]
     L.onb_set_pivot_mode.argtypes = [C.c_int]
@@ -176,7 +178,7 @@ def shard_range_for(n, block, rank, nranks):
 class GpuSession:
     """One source set + one target set on one B200, phase by phase."""
 
-    def __init__(self, physics, nsrc=None, ntarg=None, block=128, order=4, arith=ARITH_FAST, device=0, **_ignored):
+    def __init__(self, physics, nsrc=None, ntarg=None, block=128, order=4, arith=ARITH_FAST, device=0, accum64=False, **_ignored):
         self.lib = load_library()
         self.physics = physics
         self.PD, self.SD, self.OD = _DIMS[physics]
@@ -187,6 +189,14 @@ class GpuSession:
         if not self.h:
             raise OnbodyError("onb_create failed: %s" % self.lib.onb_last_create_error().decode())
         self._chk(self.lib.onb_set_params(self.h, block, order, arith))
+        if accum64:            # the reference's ACCUM = double (ongrav3d.cpp:8): fp32 pair arithmetic, fp64 accumulation and outputs
+            self._chk(self.lib.onb_set_accum(self.h, 1))
+
+    def results_f64(self, which=1):
+        n = int(self.lib.onb_count(self.h, which))
+        u = np.zeros((self.OD, n), np.float64)
+        self._chk(self.lib.onb_get_results_f64(self.h, which, u.ctypes.data))
+        return u
 
     def _chk(self, rc):
         if rc != 0:

@@ -18,7 +18,13 @@
 #include <cstring>
 #include <vector>
 
-typedef Parts<STORE,ACCUM,OREF_PD,OREF_SD,OREF_OD> OrefParts;
+// OREF_ACCUM: the accumulator type the templates are instantiated with. The drivers fix it with "#define ACCUM float"
+// (ongrav3d.cpp:8); hooks_grav3d_a64.cpp asks for double here, which is the README's fp32-store / fp64-accumulate variant -
+// every reference function is a template on <S,A,...>, so no reference source needs touching.
+#ifndef OREF_ACCUM
+#define OREF_ACCUM ACCUM
+#endif
+typedef Parts<STORE,OREF_ACCUM,OREF_PD,OREF_SD,OREF_OD> OrefParts;
 typedef Tree<STORE,OREF_PD,OREF_SD> OrefTree;
 
 struct OrefSession {
@@ -157,9 +163,16 @@ OREF_API void oref_get_parts(void* h, int which, float* x, float* r, float* str,
     if (x) for (int d=0; d<OREF_PD; ++d) std::memcpy(x+d*n, p.x[d].data(), n*sizeof(float));
     if (r) std::memcpy(r, p.r.data(), n*sizeof(float));
     if (str && p.are_sources) for (int d=0; d<OREF_SD; ++d) std::memcpy(str+d*n, p.s[d].data(), n*sizeof(float));
-    if (u && !p.are_sources) for (int d=0; d<OREF_OD; ++d) std::memcpy(u+d*n, p.u[d].data(), n*sizeof(float));
+    if (u && !p.are_sources) for (int d=0; d<OREF_OD; ++d) for (size_t i=0; i<n; ++i) u[d*n+i] = (float)p.u[d][i];
     if (gidx && p.gidx.size() == n) for (size_t i=0; i<n; ++i) gidx[i] = p.gidx[i];
 }
+// outputs in the accumulator's own precision (which: 1 targets, 3 equivalent targets); u:[OD][n] doubles
+OREF_API void oref_get_u64(void* h, int which, double* u) {
+    OrefParts& p = oref_parts((OrefSession*)h, which);
+    const size_t n = p.n;
+    for (int d=0; d<OREF_OD; ++d) for (size_t i=0; i<n; ++i) u[d*n+i] = (double)p.u[d][i];
+}
+OREF_API int oref_accum_bytes(void) { return (int)sizeof(OREF_ACCUM); }
 
 OREF_API void oref_tree_shape(void* h, int which, int* levels, int* numnodes) {
     OrefTree& t = oref_tree((OrefSession*)h, which);

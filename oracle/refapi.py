@@ -61,8 +61,10 @@ class RefSession:
         L.oref_create.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
         return L.oref_create(nsrc, ntarg, block, eq_block, order)
 
-    def __init__(self, physics, nsrc, ntarg, block=128, order=4, eq_block=128, build="strict"):
-        self.rawlib = self._open(physics, build)
+    def __init__(self, physics, nsrc, ntarg, block=128, order=4, eq_block=128, build="strict", accum64=False):
+        # accum64: the reference templates instantiated with ACCUM = double (libref_<physics>_a64.so, grav3d and vort3d)
+        self.accum64 = accum64
+        self.rawlib = self._open(physics + ("_a64" if accum64 else ""), build)
         self.lib = _NS(self.rawlib, self._prefix)
         L = self.lib
         L.oref_destroy.argtypes = [C.c_void_p]
@@ -146,6 +148,14 @@ class RefSession:
         g = np.full(n, np.iinfo(np.uint64).max, np.uint64) if which == 1 else None
         self.lib.oref_get_parts(self.h, which, _fp(x), _fp(r), _fp(s), _fp(u), _up(g))
         return {"n": n, "x": x, "r": r, "s": s, "u": u, "gidx": g}
+
+    def results_f64(self, which=1):
+        """outputs in the accumulator's precision: [OD, n] float64 (which: 1 targets, 3 equivalent targets)"""
+        n = int(self.lib.oref_count(self.h, which))
+        u = np.zeros((self.OD, n), np.float64)
+        self.rawlib.oref_get_u64.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        self.rawlib.oref_get_u64(self.h, which, u.ctypes.data_as(C.POINTER(C.c_double)))
+        return u
 
     def tree(self, which):
         lev, nn = C.c_int(), C.c_int()

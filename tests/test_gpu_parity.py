@@ -530,3 +530,43 @@ def test_fast_arithmetic_deviation_at_1e6():
     df = rel_rms(g.parts(1, ("u",))["u"], uf)
     print("fast arithmetic vs strict reference at N=1e6: boxwise %.3e dual tree %.3e" % (d3, df))
     assert d3 < 1e-6 and df < 1e-6, (d3, df)
+
+
+@pytest.mark.parametrize("physics", ["grav3d", "vort3d"])
+def test_accum_double_matches_the_reference_built_with_accum_double(physics):
+    """the reference's compile-time ACCUM = double variant (ongrav3d.cpp:7-8, README.md:107-112: fp32 storage and
+    pair arithmetic, fp64 accumulation). onb_set_accum(1) against the reference templates instantiated with A = double
+    (oracle/_ref/strict/libref_<physics>_a64.so): every method bit-exact in the strict arithmetic - outputs compared as
+    fp64 -, the product arithmetic within 1e-6, and the dual tree at a tight theta below the float32 error floor."""
+    from onbody_b200.api import GpuSession, ARITH_STRICT, ARITH_FAST
+    from oracle.refapi import RefSession, ref_available
+    if not ref_available(physics + "_a64"):
+        pytest.skip("ACCUM = double build of the reference (oracle/_ref) not present")
+    n, theta = 20000, 1.3
+
+    def run(s):
+        out = {}
+        s.init_driver(); s.make_tree(0); s.upward(0); s.make_tree(1); s.refine(1); s.upward(1)
+        s.zero_vels(); s.naive(1); out["naive"] = s.results_f64(1)
+        for name in ("treecode1", "treecode2", "treecode3"):
+            s.zero_vels(); getattr(s, name)(theta); out[name] = s.results_f64(1)
+        s.zero_vels(); s.fastsumm(theta); out["fastsumm"] = s.results_f64(1); out["fastsumm.eq"] = s.results_f64(3)
+        s.zero_vels(); s.fastsumm(3.0); out["fastsumm.tight"] = s.results_f64(1)
+        return out
+    want = run(RefSession(physics, n, n, accum64=True))
+    strict = run(GpuSession(physics, n, n, arith=ARITH_STRICT, accum64=True))
+    for k, v in want.items():
+        assert bits_equal(v, strict[k]), k
+    g = GpuSession(physics, n, n, arith=ARITH_FAST, accum64=True)
+    fast = run(g)
+    for k, v in want.items():
+        assert rel_rms(fast[k], v) < 1e-6, (k, rel_rms(fast[k], v))
+    # the float view of the fp64 outputs is their correctly rounded copy
+    assert bits_equal(g.parts(1, ("u",))["u"], fast["fastsumm.tight"].astype(np.float32))
+    # README.md:107-112: fp64 accumulation takes the dual tree below the float32 floor (6e-6 at float, a few 1e-7 with ACCUM = double)
+    err64 = rel_rms(fast["fastsumm.tight"], want["naive"])
+    f32 = GpuSession(physics, n, n, arith=ARITH_FAST)
+    f32.init_driver(); f32.make_trees(); f32.prepare_eval(); f32.zero_vels(); f32.fastsumm(3.0)
+    err32 = rel_rms(f32.parts(1, ("u",))["u"], want["naive"])
+    print("%s dual tree at -t=3 vs fp64-accumulated direct sum: ACCUM=float %.2e, ACCUM=double %.2e" % (physics, err32, err64))
+    assert err64 < 0.5 * err32 and err64 < 1e-6
