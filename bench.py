@@ -449,9 +449,9 @@ def run_ours(args):
         "roofline": {"kernel": "k_p2p_lists<grav3d,fast>", "bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved_tf / peak_tf) if peak_tf else None,
                      # DRAM bytes per launch of the packed pair kernel at this workload, from the ncu launch list of the same
-                     # step (profiles/r1_launch_list_summary_v3.txt: 1672.3 MB read + 180.3 MB written over 5 launches)
-                     "traffic": 370.5e6 if (N == 10000000 and world == 1) else None,
-                     "traffic_source": "profiles/r1_launch_list_summary_v3.txt (dram__bytes_read.sum + dram__bytes_write.sum, k_p2p_lists<grav3d,fast,TPT=4,packed>, per launch)" if (N == 10000000 and world == 1) else None,
+                     # step (profiles/r2_launch_list_summary.txt: 1671.7 MB read + 181.1 MB written over 5 launches)
+                     "traffic": 370.6e6 if (N == 10000000 and world == 1) else None,
+                     "traffic_source": "profiles/r2_launch_list_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, k_p2p_lists<grav3d,fast,TPT=4,packed>, per launch)" if (N == 10000000 and world == 1) else None,
                      "peak_source": "FP32 FMA issue microbenchmark run in this process (onb_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 SIMT figure",
                      "flop_per_pair": FLOP_PER_PAIR,
                      "fp32_issue_util": (pairs_local * FP32_SLOTS_PER_PAIR * 2 / (p2p_ms * 1e-3) * 1e-12 / peak_tf) if (peak_tf and p2p_ms > 0) else None,
@@ -460,8 +460,19 @@ def run_ours(args):
                           "achieved": tree_bytes / (tree_ms * 1e-3) * 1e-9 if (tree_ms > 0 and world == 1) else None,
                           "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "peak_source": peaks_src,
                           "frac": (tree_bytes / (tree_ms * 1e-3) * 1e-9 / peaks.get("hbm_gbs")) if (tree_ms > 0 and world == 1) else None,
-                          "algorithmic_bytes": tree_bytes, "lower_bound_bytes": tree_bytes_lb, "traffic": None,
+                          "algorithmic_bytes": tree_bytes, "lower_bound_bytes": tree_bytes_lb,
+                          # measured DRAM bytes of all tree kernels of one step (both trees), ncu launch list of the same workload
+                          "traffic": 16.25e9 if (N == 10000000 and world == 1) else None,
+                          "traffic_source": "profiles/r2_launch_list_summary.txt (k_big_level + k_gather + k_subtree + k_node_split + k_apply_perm + k_copy_back, dram read + write)" if (N == 10000000 and world == 1) else None,
                           "note": "algorithmic bytes = level-synchronous partition build (see bench.py/_tree_bytes and DESIGN.md section 4); lower_bound_bytes = every plane read and written once"},
+        # the barycentric upward pass (source side of onb_prepare_eval): SURVEY 8d models it as 52 B x N of HBM traffic, ncu shows it is
+        # bound by instruction issue and shared memory instead (profiles/r2_ncu_full_upward.txt: SM throughput 80 %, DRAM 4 %)
+        "roofline_upward": {"kernel": "k_upward<3,1,5> (17 one-level launches per tree)", "bound": "hbm", "unit": "GB/s", "peak": peaks.get("hbm_gbs"), "peak_source": peaks_src,
+                            "algorithmic_bytes": 52 * N, "ms": 1.79 if (N == 10000000 and world == 1) else None,
+                            "achieved": (52 * N / 1.79e-3 * 1e-9) if (N == 10000000 and world == 1) else None,
+                            "frac": (52 * N / 1.79e-3 * 1e-9 / peaks.get("hbm_gbs")) if (N == 10000000 and world == 1) else None,
+                            "traffic": 423.9e6 if (N == 10000000 and world == 1) else None,
+                            "source": "profiles/r2_launch_list_summary.txt (duration and DRAM bytes of the 34 k_upward launches of one step, both trees), profiles/r2_ncu_full_upward.txt"},
     }
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference itself on a bounded sample
     if world == 1 and not args.no_cpu_baseline:

@@ -7,6 +7,10 @@ N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 2000000
 theta = float(sys.argv[2]) if len(sys.argv) > 2 else 1.11111
 g = GpuSession("grav3d", N, N); g.init_driver()
 g.make_tree(0); g.upward(0)
+if os.environ.get("ONB_PW_UNSORTED") is None:
+    # the drivers build (and, when the dual tree is scheduled, refine) the target tree before any treecode runs
+    # (ongrav3d.cpp:675-724), so a warp's 32 consecutive targets are spatial neighbours; ONB_PW_UNSORTED=1 skips it
+    g.make_tree(1); g.refine(1)
 for it in range(2):
     g.zero_vels(); g.treecode2(theta)
     st = g.stats()
