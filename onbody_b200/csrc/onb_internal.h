@@ -252,6 +252,7 @@ struct WorkList {
     uint32_t* entries = nullptr;
     uint64_t nentries = 0;         // allocated entries (reads are clamped to it)
     const uint32_t* ebase = nullptr;   // optional device-resident offset of the list inside `entries`
+    const uint32_t* order = nullptr;   // optional launch order of the items (longest list first, scan.cu onb_lpt_order)
 };
 int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tgt_which_box, bool accumulate, uint32_t nsplit = 1);
 void onb_free_worklist(onb_context* c, WorkList& wl);
@@ -271,3 +272,4 @@ cudaEvent_t onb_cached_event(onb_context* c, size_t i);
 int onb_memset_plane(onb_context* c, float* p, size_t count, cudaStream_t st);
 // scan.cu
 int onb_exclusive_scan_u32(onb_context* c, const uint32_t* in, uint32_t* out, uint32_t n, uint64_t* total);
+int onb_lpt_order(onb_context* c, const uint32_t* start, uint32_t n, uint32_t** order_out);

@@ -114,6 +114,7 @@ struct P2PArgs {
     const uint32_t* s_epnum;        // legacy equivalents: per source node count (null = num_eqps everywhere)
     float* partial;                 // nsplit > 1: [item][segment][OD][128] partial sums, reduced in segment order by k_p2p_reduce
     const uint32_t* ebase;          // device-resident offset of this work list inside `entries` (dual tree: the level's pool base), or null
+    const uint32_t* order;          // launch order of the work items (longest list first), or null = item index order
     uint32_t block, ebs, num_eqps, node_base, nentries, nsplit;
 };
 // [e0, e1) of work item w, clamped to the allocated entries (a dual-tree pass whose pool overflowed is discarded, not faulted)
@@ -145,7 +146,8 @@ __global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__
     const int tid = threadIdx.x;
     // nsplit > 1 (under-filled launches of the upper dual-tree levels, fast arithmetic only): the item's list is cut into
     // nsplit contiguous segments, one CTA each, partial sums go to a[].partial and are added in segment order afterwards
-    const uint32_t w = blockIdx.x / a.nsplit, seg = blockIdx.x - w * a.nsplit;
+    const uint32_t wl = blockIdx.x / a.nsplit, seg = blockIdx.x - wl * a.nsplit;
+    const uint32_t w = a.order ? a.order[wl] : wl;
     uint32_t e0, e1; item_range(a, w, e0, e1);   // never read past the allocated list
     if (e0 >= e1) return;
     if (a.nsplit > 1) {
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__
                 #pragma unroll
                 for (int d = 0; d < OD; ++d) { if (leaf) a.tu[d][ti] = acc[q][d]; else a.bu[d][ti] = acc[q][d]; }
             } else {
-                float* __restrict__ part = a.partial + ((size_t)blockIdx.x * OD) * 128u;
+                float* __restrict__ part = a.partial + (((size_t)w * a.nsplit + seg) * OD) * 128u;
                 #pragma unroll
                 for (int d = 0; d < OD; ++d) part[d * 128 + slot] = acc[q][d];
             }
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(128) k_p2p_lists_a64(const __grid_constant__ P
     constexpr int OD = Phys<PHYS>::OD;
     __shared__ TileSmem<PHYS> sm;
     const int tid = threadIdx.x;
-    const uint32_t w = blockIdx.x;
+    const uint32_t w = a.order ? a.order[blockIdx.x] : blockIdx.x;
     uint32_t e0, e1; item_range(a, w, e0, e1);
     if (e0 >= e1) return;
     const uint32_t T = a.item_node ? a.item_node[w] : a.node_base + w;
@@ -543,7 +545,7 @@ int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tg
     a.item_node = wl.tgt_node; a.start = wl.start; a.entries = wl.entries;
     a.block = c->block; a.ebs = c->ebs; a.num_eqps = c->num_eqps; a.node_base = wl.node_base; a.nentries = (uint32_t)wl.nentries;
     a.s_epnum = c->legacy ? c->d_epnum : nullptr;
-    a.nsplit = nsplit; a.partial = nullptr; a.ebase = wl.ebase;
+    a.nsplit = nsplit; a.partial = nullptr; a.ebase = wl.ebase; a.order = wl.order;
     for (int d = 0; d < ONB_MAX_OD; ++d) { a.tud[d] = tl.ud[d]; a.bud[d] = tb.ud[d]; }
     if (c->accum64) {
         if (!tl.ud[0] || (tgt_which_box != tgt_which_leaf && tb.n && !tb.ud[0])) { c->err = "ACCUM = double: set the targets (and build the equivalent target points) after onb_set_accum"; return ONB_ERR_ARG; }

@@ -3,6 +3,7 @@
  * per-block scan + block totals, recursive scan of the totals, add-back. HBM-bound, trivial share of a step.
  */
 #include "onb_internal.h"
+#include <algorithm>
 
 namespace {
 constexpr int SCAN_T = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_T * SCAN_ITEMS;
@@ -34,7 +35,52 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, const uint32_t* __restric
 __global__ void k_total(const uint32_t* __restrict__ in, const uint32_t* __restrict__ out, uint32_t n, unsigned long long* total) {
     *total = (unsigned long long)out[n - 1] + (unsigned long long)in[n - 1];
 }
+// ---- longest-list-first order of the work items of a pair-kernel launch --------------------------------------------
+// A launch ends when its longest list has been walked; with items in tree order the long lists are scattered and the tail of
+// every launch is a few CTAs finishing alone. A counting sort of the items by list length (256 bins of 4 entries, descending;
+// exact order inside a bin does not matter) lets the hardware scheduler hand out the long lists first. Per-item results do
+// not depend on which CTA runs when, so nothing changes but the time.
+constexpr int LPT_BINS = 256;
+__device__ __forceinline__ uint32_t lpt_bin(uint32_t len) { return (LPT_BINS - 1) - min((uint32_t)(LPT_BINS - 1), (len + 3u) >> 2); }   // len 0 -> last bin
+__global__ void __launch_bounds__(256) k_lpt_hist(const uint32_t* __restrict__ start, uint32_t n, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[LPT_BINS];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&sh[lpt_bin(start[i + 1] - start[i])], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void __launch_bounds__(LPT_BINS) k_lpt_offsets(uint32_t* hist) {      // exclusive scan of the 256 bins, in place
+    __shared__ uint32_t sh[LPT_BINS];
+    const uint32_t v = hist[threadIdx.x];
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < LPT_BINS; o <<= 1) { const uint32_t t = threadIdx.x >= (unsigned)o ? sh[threadIdx.x - o] : 0u; __syncthreads(); sh[threadIdx.x] += t; __syncthreads(); }
+    hist[threadIdx.x] = sh[threadIdx.x] - v;
+}
+__global__ void __launch_bounds__(256) k_lpt_scatter(const uint32_t* __restrict__ start, uint32_t n, uint32_t* __restrict__ offs, uint32_t* __restrict__ order) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    order[atomicAdd(&offs[lpt_bin(start[i + 1] - start[i])], 1u)] = i;
+}
 }  // namespace
+
+// order[k] = k-th work item in (binned) descending list length; start has n+1 entries. Enqueued on ONB_ST(c), no host sync.
+int onb_lpt_order(onb_context* c, const uint32_t* start, uint32_t n, uint32_t** order_out) {
+    *order_out = nullptr;
+    if (n < 2) return ONB_OK;
+    uint32_t *hist = nullptr, *order = nullptr;
+    ONB_CUDA(onb_dmalloc(c, (void**)&hist, LPT_BINS * 4));
+    ONB_CUDA(onb_dmalloc(c, (void**)&order, (size_t)n * 4));
+    ONB_CUDA(cudaMemsetAsync(hist, 0, LPT_BINS * 4, ONB_ST(c)));
+    const uint32_t blocks = std::min<uint32_t>((n + 255) / 256, 1024u);
+    k_lpt_hist<<<blocks, 256, 0, ONB_ST(c)>>>(start, n, hist); ONB_LAUNCH(c);
+    k_lpt_offsets<<<1, LPT_BINS, 0, ONB_ST(c)>>>(hist); ONB_LAUNCH(c);
+    k_lpt_scatter<<<(n + 255) / 256, 256, 0, ONB_ST(c)>>>(start, n, hist, order); ONB_LAUNCH(c);
+    ONB_CUDA(cudaGetLastError());
+    *order_out = order;
+    return ONB_OK;
+}
 
 // out[i] = sum of in[0..i); if total != null it receives the grand total (host value, synchronises the stream).
 // in and out may alias.

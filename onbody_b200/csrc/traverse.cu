@@ -291,6 +291,10 @@ int onb_lists_boxwise(onb_context* c, float theta, WorkList& wl) {
     a.entries = wl.entries;
     k_boxwise<true><<<(nl + TB - 1) / TB, TB, 0, c->stream>>>(a); ONB_LAUNCH(c);
     ONB_CUDA(cudaGetLastError());
+    { static const bool lpt = std::getenv("ONB_LPT") != nullptr;
+      uint32_t* order = nullptr;
+      if (lpt && nl >= 4096) { rc = onb_lpt_order(c, wl.start, nl, &order); if (rc) return rc; }
+      wl.order = order; }
     rc = fetch_stats(c, d_stats);
     onb_dfree(c, d_stats); onb_dfree(c, leaf_all);
     return rc;
@@ -378,6 +382,12 @@ static int fastsumm_pass(onb_context* c, float theta, bool* redo) {
         k_dtt<true><<<blocks, TB, 0, ONB_ST(c)>>>(a); ONB_LAUNCH(c);
         ONB_CUDA(cudaGetLastError());
         if (d_lvl) ONB_CUDA(cudaMemcpyAsync(d_lvl + lev, d_stats + 9, 8, cudaMemcpyDeviceToDevice, ONB_ST(c)));
+        // optional launch order of this level's pair kernel: longest list first (ONB_LPT=1; built on the list stream). Measured
+        // at N = 1e7: no gain on one GPU (79.2 vs 80.1 ms of pair kernels, within box-to-box noise) and none on a 1/8 shard - the
+        // items of a level have similar lengths, the loss of small launches is wave quantisation, not stragglers - so it is off.
+        uint32_t* order = nullptr;
+        static const bool lpt = std::getenv("ONB_LPT") != nullptr;
+        if (lpt && nn >= 4096) { if ((rc = onb_lpt_order(c, istart, nn, &order))) break; }
         ONB_CUDA(cudaEventRecord(ev(lev, 1), ONB_ST(c)));
         if (ahead) { c->cur_stream = nullptr; ONB_CUDA(cudaStreamWaitEvent(c->stream, ev(lev, 1), 0)); ONB_CUDA(cudaEventRecord(ev(lev, 4), c->stream)); }
         // node entry: zero + interpolate from the parent (ongrav3d.cpp:232-304)
@@ -385,7 +395,7 @@ static int fastsumm_pass(onb_context* c, float theta, bool* redo) {
         ONB_CUDA(cudaEventRecord(ev(lev, 2), c->stream));
         // then this level's interactions, in list order, on top of the interpolated values (:315-402)
         WorkList wl; wl.nitems = nn; wl.tgt_node = nullptr; wl.node_base = node0; wl.start = istart; wl.entries = c->dtt_pool; wl.nentries = c->dtt_pool_cap;
-        wl.ebase = d_bases + 2 * lev;
+        wl.ebase = d_bases + 2 * lev; wl.order = order;
         // Upper levels have too few target nodes to fill the machine with one warp per node. Cutting every list into nsplit
         // segments (ONB_P2P_SPLIT_TARGET=<CTAs per launch to aim for>) makes the pair kernel 4 % faster at N = 1e7 (79.5 ->
         // 76.1 ms), but it is OFF by default: adding the far-field partial sums in another order than the reference moves

@@ -570,3 +570,39 @@ def test_accum_double_matches_the_reference_built_with_accum_double(physics):
     err32 = rel_rms(f32.parts(1, ("u",))["u"], want["naive"])
     print("%s dual tree at -t=3 vs fp64-accumulated direct sum: ACCUM=float %.2e, ACCUM=double %.2e" % (physics, err32, err64))
     assert err64 < 0.5 * err32 and err64 < 1e-6
+
+
+def test_first_call_of_prepare_eval_at_full_size():
+    """on the very first onb_prepare_eval of a context the equivalent-target planes are allocated while the
+    target chain runs on the second stream; their zero fill must be ordered on THAT stream or it can land after k_upward has
+    written the points. N = 1e7 makes the source chain long enough to lose such a race; compare with the separate calls."""
+    n = 10000000
+    a = _gpu("grav3d", n); a.init_driver(); a.make_trees(); a.prepare_eval()          # first call, nothing allocated yet
+    ea = a.parts(3, ("x",))["x"]; a.zero_vels(); a.fastsumm(1.4); ua = a.parts(1, ("u",))["u"]; a.close()
+    b = _gpu("grav3d", n); b.init_driver(); b.make_trees(); b.upward(0); b.refine(1); b.upward(1)
+    eb = b.parts(3, ("x",))["x"]; b.zero_vels(); b.fastsumm(1.4); ub = b.parts(1, ("u",))["u"]; b.close()
+    assert np.isfinite(ua).all() and bits_equal(ea, eb) and bits_equal(ua, ub)
+
+
+@pytest.mark.parametrize("physics,n,tol", [("vort3d", 200000, 1e-6), ("vortgrad3d", 100000, 5e-6)])
+def test_other_physics_fast_arithmetic_at_larger_n(physics, n, tol):
+    """BASELINE configs[2]/[3] (onvort3d, onvortgrad3d): product arithmetic against the compiled strict reference beyond the
+    3e4 of the per-physics test - boxwise treecode for both, dual tree where the reference has one"""
+    from onbody_b200.api import ARITH_FAST
+    from oracle.refapi import RefSession, ref_available
+    if not ref_available(physics):
+        pytest.skip("compiled reference (oracle/_ref) not present")
+    o = RefSession(physics, n, n); o.init_driver()
+    o.make_tree(0); o.upward(0); o.make_tree(1); o.refine(1)
+    g = _gpu(physics, n, arith=ARITH_FAST); g.init_driver(); g.make_trees(); g.upward(0); g.refine(1)
+    o.zero_vels(); f_ref = o.treecode3(1.2); u3 = o.parts(1)["u"]
+    g.zero_vels(); f_gpu = g.treecode3(1.2)
+    assert f_gpu == f_ref                                                   # same interaction lists (flop checksum)
+    d3 = rel_rms(g.parts(1, ("u",))["u"], u3)
+    assert d3 < tol, d3
+    if o.has_fastsumm:
+        o.upward(1); g.upward(1)
+        o.zero_vels(); o.fastsumm(1.4); uf = o.parts(1)["u"]
+        g.zero_vels(); g.fastsumm(1.4)
+        df = rel_rms(g.parts(1, ("u",))["u"], uf)
+        assert df < tol, df
