@@ -106,6 +106,10 @@ int onb_dist_make_trees(onb_context* c, int which) {
     const bool both = which < 0;
     const bool do_src = both || which == 0, do_tgt = both || which == 1;
     int rc;
+    if (c->legacy) {      // refineTree(srcs) + calcEquivalents walk every source leaf in place: there is no sharded form of them here
+        c->err = "the legacy equivalents (-o omitted) are single-GPU only: attach the communicator to a context with a barycentric order";
+        return ONB_ERR_UNSUPPORTED;
+    }
     if (do_src && (rc = ensure_plan(c, 0))) return rc;
     if (do_tgt && (rc = ensure_plan(c, 1))) return rc;
     if (do_src && (rc = onb_alloc_tree(c, c->trees[0], c->parts[0].n, c->block))) return rc;

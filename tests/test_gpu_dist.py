@@ -163,3 +163,44 @@ def test_device_results_added_in_place():
     want = np.full((3, n), 2.0, np.float32); want[:, p["gidx"].astype(np.int64)] += p["u"]
     assert bits_equal(host, want) and bits_equal(dev.cpu().numpy(), want)
     g.close()
+
+
+@pytest.mark.timeout(600)
+def test_loopback_accum_double_and_refusals():
+    """ACCUM = double through the distributed path (fp64 outputs of each rank's shard equal the single-context run), and the
+    combinations the library refuses loudly: legacy equivalents with a communicator, ACCUM = double in the lean memory mode"""
+    from onbody_b200.api import GpuSession, OnbodyError, driver_inputs, comm_init_loopback, shard_range_for, MEM_LEAN
+    n, world, theta = 40000, 3, 1.3
+    inputs = driver_inputs("grav3d", n, True)
+    ref = GpuSession("grav3d", n, n, accum64=True)
+    ref.set_sources(*inputs); ref.set_targets(inputs[0], inputs[1]); ref.make_trees(); ref.prepare_eval()
+    ref.zero_vels(); ref.fastsumm(theta); want = ref.results_f64(1)
+    ref.zero_vels(); ref.treecode3(theta); want3 = ref.results_f64(1); ref.close()
+    sess = [GpuSession("grav3d", n, n, accum64=True) for _ in range(world)]
+    comm_init_loopback(sess)
+
+    def run(rank, g):
+        g.set_sources(*inputs); g.set_targets(inputs[0], inputs[1]); g.make_trees(); g.prepare_eval()
+        g.zero_vels(); g.fastsumm(theta); a = g.results_f64(1)
+        g.zero_vels(); g.treecode3(theta); b = g.results_f64(1)
+        return a, b
+    for rank, (a, b) in enumerate(_on_all(sess, run)):
+        lo, hi = shard_range_for(n, 128, rank, world)
+        assert bits_equal(a[:, lo:hi], want[:, lo:hi]) and bits_equal(b[:, lo:hi], want3[:, lo:hi]), rank
+    for s in sess:
+        s.close()
+    legacy = [GpuSession("grav3d", n, n, order=-1) for _ in range(2)]
+    comm_init_loopback(legacy)
+    legacy[0].set_sources(*inputs); legacy[0].set_targets(inputs[0], inputs[1])
+    with pytest.raises(OnbodyError):
+        legacy[0].make_tree(0)                       # refused before any collective is entered
+    for s in legacy:
+        s.close()
+    lean = [GpuSession("grav3d", n, n, accum64=True) for _ in range(2)]
+    for s in lean:
+        s.set_memory_mode(MEM_LEAN)
+    comm_init_loopback(lean)
+    with pytest.raises(OnbodyError):
+        lean[0].set_targets(inputs[0], inputs[1])
+    for s in lean:
+        s.close()

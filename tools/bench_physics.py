@@ -55,7 +55,29 @@ if world > 1:
     tot, ev, pp, pairs = mx[0].item(), mx[1].item(), mx[2].item(), sm[3].item()
 if rank == 0:
     peak = g.measure_fp32_peak()
-    print(json.dumps({"physics": physics, "method": method, "n": N, "theta": theta, "n_gpus": world, "ms_per_step": tot / steps, "ms_eval": ev / steps,
+    cpu = None
+    if world == 1 and os.environ.get("ONB_CPU_BASELINE"):
+        # the reference's own OpenMP path on the host cores, bounded sample of the same workload (checker code, timing only)
+        import ctypes
+        from oracle.refapi import RefSession, ref_available
+        if ref_available(physics, "fast"):
+            cores = os.cpu_count() or 1
+            os.environ["OMP_NUM_THREADS"] = str(cores)
+            try:
+                ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+            except OSError:
+                pass
+            n_cpu = int(float(os.environ["ONB_CPU_BASELINE"]))
+            o = RefSession(physics, n_cpu, n_cpu, build="fast"); o.init_driver()
+            t0 = time.perf_counter()
+            o.make_tree(0); o.upward(0); o.make_tree(1)
+            if method == "dualtree":
+                o.refine(1); o.upward(1); o.zero_vels(); o.fastsumm(theta, parallel=True)
+            else:
+                o.zero_vels(); o.treecode3(theta)
+            cpu = {"kind": "reference", "cores": cores, "n": n_cpu, "seconds": time.perf_counter() - t0,
+                   "sample": "N=%d of the same generator, whole step, %d OpenMP threads" % (n_cpu, cores)}
+    print(json.dumps({"cpu_baseline": cpu, "physics": physics, "method": method, "n": N, "theta": theta, "n_gpus": world, "ms_per_step": tot / steps, "ms_eval": ev / steps,
                       "ms_p2p_max_rank": pp / steps, "pairs": int(pairs), "Ginteractions_per_s": pairs / (tot / steps) * 1e-6,
                       "p2p_TFLOPs_per_gpu": (pairs / world) * FLOPS[physics] / (pp / steps) * 1e-9, "fp32_peak_TFLOPs": peak}))
 if world > 1:

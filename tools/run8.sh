@@ -16,6 +16,12 @@ run 8 bench.py --gpus 8 --particles 100000000 --steps 3 --warmup 2 --check-error
 TMO=900
 run 8 bench.py --gpus 8 --particles 1000000000 --steps 2 --warmup 1 > gpurun_out/r2_bench_8gpu_n1e9.json 2> gpurun_out/r2_bench_8gpu_n1e9.err; echo "8gpu 1e9 rc=$?"
 tail -4 gpurun_out/r2_bench_8gpu_n1e9.err
+TMO=240
+: > gpurun_out/r2_bench_8gpu_other_physics.jsonl
+run 8 tools/bench_physics.py vort3d dualtree 10000000 1.4 | grep "^{" >> gpurun_out/r2_bench_8gpu_other_physics.jsonl
+run 8 tools/bench_physics.py vort3d boxwise 10000000 1.4 | grep "^{" >> gpurun_out/r2_bench_8gpu_other_physics.jsonl
+run 8 tools/bench_physics.py vortgrad3d boxwise 10000000 1.4 | grep "^{" >> gpurun_out/r2_bench_8gpu_other_physics.jsonl
+cat gpurun_out/r2_bench_8gpu_other_physics.jsonl | cut -c1-400
 timeout 300 ./onbody_b200/bin/ongrav3d -g=8 -n=100000000 -t=1.4 -o=4 > gpurun_out/r2_driver_8gpu_n1e8.txt 2>&1; echo "driver rc=$?"; tail -8 gpurun_out/r2_driver_8gpu_n1e8.txt
 python - <<'PY'
 import json, glob
