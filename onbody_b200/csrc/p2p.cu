@@ -115,6 +115,8 @@ struct P2PArgs {
     float* partial;                 // nsplit > 1: [item][segment][OD][128] partial sums, reduced in segment order by k_p2p_reduce
     const uint32_t* ebase;          // device-resident offset of this work list inside `entries` (dual tree: the level's pool base), or null
     const uint32_t* order;          // launch order of the work items (longest list first), or null = item index order
+    uint32_t* work; uint32_t nwork; // persistent mode: atomic item counter (zeroed before the launch) and the number of items x nsplit
+    uint32_t* work_counter;         // host side: a zeroed counter the launcher may use for the persistent mode
     uint32_t block, ebs, num_eqps, node_base, nentries, nsplit;
 };
 // [e0, e1) of work item w, clamped to the allocated entries (a dual-tree pass whose pool overflowed is discarded, not faulted)
@@ -143,106 +145,132 @@ __global__ void __launch_bounds__(128 / TPT) k_p2p_lists(const __grid_constant__
     constexpr int G = PK ? TPT / 2 : 1;          // packed target pairs per thread
     static_assert(!PK || (TPT % 2 == 0 && !STRICT), "packed arithmetic needs an even TPT and the fast mode");
     __shared__ TileSmem<PHYS> sm;
+    __shared__ uint32_t s_next;
     const int tid = threadIdx.x;
-    // nsplit > 1 (under-filled launches of the upper dual-tree levels, fast arithmetic only): the item's list is cut into
-    // nsplit contiguous segments, one CTA each, partial sums go to a[].partial and are added in segment order afterwards
-    const uint32_t wl = blockIdx.x / a.nsplit, seg = blockIdx.x - wl * a.nsplit;
-    const uint32_t w = a.order ? a.order[wl] : wl;
-    uint32_t e0, e1; item_range(a, w, e0, e1);   // never read past the allocated list
-    if (e0 >= e1) return;
-    if (a.nsplit > 1) {
-        const uint32_t len = e1 - e0;
-        const uint32_t s0 = e0 + (uint32_t)((unsigned long long)len * seg / a.nsplit), s1 = e0 + (uint32_t)((unsigned long long)len * (seg + 1u) / a.nsplit);
-        e0 = s0; e1 = s1;
-    }
-    const uint32_t T = a.item_node ? a.item_node[w] : a.node_base + w;
-    const uint32_t tn = a.t_num[T];
-    const bool leaf = tn <= a.block;
-    const uint32_t toff = leaf ? a.t_ioffset[T] : T * a.ebs;
-    const uint32_t tcnt = leaf ? tn : a.num_eqps;
-    Tgt tg[TPT];
-    float acc[TPT][OD];
-    #pragma unroll
-    for (int q = 0; q < TPT; ++q) {
-        const uint32_t slot = (uint32_t)tid + (uint32_t)q * NT;
-        const bool valid = slot < tcnt;
-        const uint32_t ti = toff + (valid ? slot : 0);
-        tg[q].x = leaf ? a.tx[0][ti] : a.bx[0][ti];
-        tg[q].y = leaf ? a.tx[1][ti] : a.bx[1][ti];
-        tg[q].z = Phys<PHYS>::PD > 2 ? (leaf ? a.tx[2][ti] : a.bx[2][ti]) : 0.f;
-        tg[q].r2 = 0.f;
-        if (Phys<PHYS>::TR) { const float r = leaf ? a.tr[ti] : a.br[ti]; tg[q].r2 = __fmul_rn(r, r); }
-        #pragma unroll
-        for (int d = 0; d < OD; ++d) acc[q][d] = (valid && a.nsplit == 1) ? (leaf ? a.tu[d][ti] : a.bu[d][ti]) : 0.f;
-    }
-    Tgt2 tg2[G];
-    f2 acc2[G][OD];
-    if (PK) {
-        #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const Tgt& t0 = tg[2 * g]; const Tgt& t1 = tg[PK ? 2 * g + 1 : 0];
-            tg2[g].px = mk2(t0.x, t1.x); tg2[g].py = mk2(t0.y, t1.y); tg2[g].pz = mk2(t0.z, t1.z);
-            tg2[g].nx = mk2(-t0.x, -t1.x); tg2[g].ny = mk2(-t0.y, -t1.y); tg2[g].nz = mk2(-t0.z, -t1.z);
-            tg2[g].r2 = mk2(t0.r2, t1.r2);
-            #pragma unroll
-            for (int d = 0; d < OD; ++d) acc2[g][d] = mk2(acc[2 * g][d], acc[PK ? 2 * g + 1 : 0][d]);
-        }
-    }
-
     if (tid == 0) { ptx::mbar_init(&sm.bar[0], 1); ptx::mbar_init(&sm.bar[1], 1); ptx::fence_mbar_init(); }
     __syncthreads();
-    TileRef cur = decode_entry(a, a.entries[min(e0, a.nentries - 1u)]);
-    if (tid == 0 && e0 < e1) tile_issue<PHYS>(sm, 0, cur);
-    for (uint32_t e = e0; e < e1; ++e) {
-        const int buf = (e - e0) & 1;
-        const uint32_t par = ((e - e0) >> 1) & 1;
-        TileRef nxt = cur;
-        if (e + 1 < e1) {
-            nxt = decode_entry(a, a.entries[e + 1]);
-            if (tid == 0) tile_issue<PHYS>(sm, buf ^ 1, nxt);
+    uint32_t tiles_done = 0;      // tiles this CTA has consumed so far: ring slot and mbarrier phase continue across work items
+    // Two ways to hand out the work items (one item = one target block with its list):
+    //   a.work == null : CTA b takes item b (the hardware scheduler deals CTAs out as slots free up - fine for launches of many waves)
+    //   a.work != null : PERSISTENT CTAs pull items from an atomic counter. A launch that fits the machine in one wave is otherwise
+    //                    dealt out statically and ends when the most loaded SM sub-partition is done; pulling items balances it.
+    for (uint32_t round = 0;; ++round) {
+        uint32_t bid;
+        if (a.work) {
+            if (NT > 32) {
+                if (tid == 0) s_next = atomicAdd(a.work, 1u);
+                __syncthreads();
+                bid = s_next;
+                __syncthreads();
+            } else {
+                uint32_t v = 0;
+                if (tid == 0) v = atomicAdd(a.work, 1u);
+                bid = __shfl_sync(0xffffffffu, v, 0);
+            }
+            if (bid >= a.nwork) break;
+        } else {
+            if (round) break;
+            bid = blockIdx.x;
         }
-        ptx::mbar_wait(&sm.bar[buf], par);
-        {
-            const float4* __restrict__ A = sm.a[buf];
-            const float4* __restrict__ B = sm.b[buf];
-            const float*  __restrict__ C = sm.c[buf] + (Phys<PHYS>::F1 ? (cur.off & 3u) : 0u);
-            const int cnt = (int)cur.cnt;
-            #pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-                const float4 p0 = A[j];
-                const float4 p1 = Phys<PHYS>::NF4 > 1 ? B[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float p2 = Phys<PHYS>::F1 ? C[j] : 0.f;
-                if (PK) {
-                    #pragma unroll
-                    for (int g = 0; g < G; ++g) pair2<PHYS>(p0, p1, p2, tg2[g], acc2[g]);
-                } else {
-                    #pragma unroll
-                    for (int q = 0; q < TPT; ++q) pair<PHYS, STRICT>(p0, p1, p2, tg[q], acc[q]);
-                }
+        // nsplit > 1 (optional, fast arithmetic only): the item's list is cut into nsplit contiguous segments, one CTA each,
+        // partial sums go to a.partial and are added in segment order afterwards
+        const uint32_t wl = bid / a.nsplit, seg = bid - wl * a.nsplit;
+        const uint32_t w = a.order ? a.order[wl] : wl;
+        uint32_t e0, e1; item_range(a, w, e0, e1);   // never read past the allocated list
+        if (e0 >= e1) continue;
+        if (a.nsplit > 1) {
+            const uint32_t len = e1 - e0;
+            const uint32_t s0 = e0 + (uint32_t)((unsigned long long)len * seg / a.nsplit), s1 = e0 + (uint32_t)((unsigned long long)len * (seg + 1u) / a.nsplit);
+            e0 = s0; e1 = s1;
+            if (e0 >= e1) continue;
+        }
+        const uint32_t T = a.item_node ? a.item_node[w] : a.node_base + w;
+        const uint32_t tn = a.t_num[T];
+        const bool leaf = tn <= a.block;
+        const uint32_t toff = leaf ? a.t_ioffset[T] : T * a.ebs;
+        const uint32_t tcnt = leaf ? tn : a.num_eqps;
+        Tgt tg[TPT];
+        float acc[TPT][OD];
+        #pragma unroll
+        for (int q = 0; q < TPT; ++q) {
+            const uint32_t slot = (uint32_t)tid + (uint32_t)q * NT;
+            const bool valid = slot < tcnt;
+            const uint32_t ti = toff + (valid ? slot : 0);
+            tg[q].x = leaf ? a.tx[0][ti] : a.bx[0][ti];
+            tg[q].y = leaf ? a.tx[1][ti] : a.bx[1][ti];
+            tg[q].z = Phys<PHYS>::PD > 2 ? (leaf ? a.tx[2][ti] : a.bx[2][ti]) : 0.f;
+            tg[q].r2 = 0.f;
+            if (Phys<PHYS>::TR) { const float r = leaf ? a.tr[ti] : a.br[ti]; tg[q].r2 = __fmul_rn(r, r); }
+            #pragma unroll
+            for (int d = 0; d < OD; ++d) acc[q][d] = (valid && a.nsplit == 1) ? (leaf ? a.tu[d][ti] : a.bu[d][ti]) : 0.f;
+        }
+        Tgt2 tg2[G];
+        f2 acc2[G][OD];
+        if (PK) {
+            #pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const Tgt& t0 = tg[2 * g]; const Tgt& t1 = tg[PK ? 2 * g + 1 : 0];
+                tg2[g].px = mk2(t0.x, t1.x); tg2[g].py = mk2(t0.y, t1.y); tg2[g].pz = mk2(t0.z, t1.z);
+                tg2[g].nx = mk2(-t0.x, -t1.x); tg2[g].ny = mk2(-t0.y, -t1.y); tg2[g].nz = mk2(-t0.z, -t1.z);
+                tg2[g].r2 = mk2(t0.r2, t1.r2);
+                #pragma unroll
+                for (int d = 0; d < OD; ++d) acc2[g][d] = mk2(acc[2 * g][d], acc[PK ? 2 * g + 1 : 0][d]);
             }
         }
-        if (NT > 32) __syncthreads(); else __syncwarp();   // everyone is done with `buf` before it is refilled two iterations later
-        cur = nxt;
-    }
-    if (PK) {
-        #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            #pragma unroll
-            for (int d = 0; d < OD; ++d) { acc[2 * g][d] = lo2(acc2[g][d]); acc[PK ? 2 * g + 1 : 0][d] = hi2(acc2[g][d]); }
+
+        TileRef cur = decode_entry(a, a.entries[e0]);
+        if (tid == 0) tile_issue<PHYS>(sm, (int)(tiles_done & 1u), cur);
+        for (uint32_t e = e0; e < e1; ++e, ++tiles_done) {
+            const int buf = (int)(tiles_done & 1u);
+            const uint32_t par = (tiles_done >> 1) & 1u;
+            TileRef nxt = cur;
+            if (e + 1 < e1) {
+                nxt = decode_entry(a, a.entries[e + 1]);
+                if (tid == 0) tile_issue<PHYS>(sm, buf ^ 1, nxt);
+            }
+            ptx::mbar_wait(&sm.bar[buf], par);
+            {
+                const float4* __restrict__ A = sm.a[buf];
+                const float4* __restrict__ B = sm.b[buf];
+                const float*  __restrict__ C = sm.c[buf] + (Phys<PHYS>::F1 ? (cur.off & 3u) : 0u);
+                const int cnt = (int)cur.cnt;
+                #pragma unroll 4
+                for (int j = 0; j < cnt; ++j) {
+                    const float4 p0 = A[j];
+                    const float4 p1 = Phys<PHYS>::NF4 > 1 ? B[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float p2 = Phys<PHYS>::F1 ? C[j] : 0.f;
+                    if (PK) {
+                        #pragma unroll
+                        for (int g = 0; g < G; ++g) pair2<PHYS>(p0, p1, p2, tg2[g], acc2[g]);
+                    } else {
+                        #pragma unroll
+                        for (int q = 0; q < TPT; ++q) pair<PHYS, STRICT>(p0, p1, p2, tg[q], acc[q]);
+                    }
+                }
+            }
+            if (NT > 32) __syncthreads(); else __syncwarp();   // everyone is done with `buf` before it is refilled two iterations later
+            cur = nxt;
         }
-    }
-    #pragma unroll
-    for (int q = 0; q < TPT; ++q) {
-        const uint32_t slot = (uint32_t)tid + (uint32_t)q * NT;
-        if (slot < tcnt) {
-            const uint32_t ti = toff + slot;
-            if (a.nsplit == 1) {
+        if (PK) {
+            #pragma unroll
+            for (int g = 0; g < G; ++g) {
                 #pragma unroll
-                for (int d = 0; d < OD; ++d) { if (leaf) a.tu[d][ti] = acc[q][d]; else a.bu[d][ti] = acc[q][d]; }
-            } else {
-                float* __restrict__ part = a.partial + (((size_t)w * a.nsplit + seg) * OD) * 128u;
-                #pragma unroll
-                for (int d = 0; d < OD; ++d) part[d * 128 + slot] = acc[q][d];
+                for (int d = 0; d < OD; ++d) { acc[2 * g][d] = lo2(acc2[g][d]); acc[PK ? 2 * g + 1 : 0][d] = hi2(acc2[g][d]); }
+            }
+        }
+        #pragma unroll
+        for (int q = 0; q < TPT; ++q) {
+            const uint32_t slot = (uint32_t)tid + (uint32_t)q * NT;
+            if (slot < tcnt) {
+                const uint32_t ti = toff + slot;
+                if (a.nsplit == 1) {
+                    #pragma unroll
+                    for (int d = 0; d < OD; ++d) { if (leaf) a.tu[d][ti] = acc[q][d]; else a.bu[d][ti] = acc[q][d]; }
+                } else {
+                    float* __restrict__ part = a.partial + (((size_t)w * a.nsplit + seg) * OD) * 128u;
+                    #pragma unroll
+                    for (int d = 0; d < OD; ++d) part[d * 128 + slot] = acc[q][d];
+                }
             }
         }
     }
@@ -456,8 +484,21 @@ __global__ void k_fma_peak(float* out, int iters) {
 int g_p2p_tpt = 0;     // 0 = per-physics default; 1, 2 or 4 forces the register blocking; +16 = scalar instead of packed f32x2
 
 template <int PHYS, int TPT>
-void launch_lists_t(onb_context* c, const P2PArgs& a, uint32_t nitems, bool packed) {
-    const uint32_t grid = nitems * a.nsplit;
+void launch_lists_t(onb_context* c, P2PArgs a, uint32_t nitems, bool packed) {
+    uint32_t grid = nitems * a.nsplit;
+    // Optional persistent mode (ONB_PERSIST=1) for launches of few waves (the upper and middle dual-tree levels; every level of a
+    // multi-GPU shard): a fixed number of CTAs - ONB_PERSIST_WARPS warps per SM (default 16) - pull the items from an atomic
+    // counter. OFF by default: measured at N = 1e7 it changes nothing (pair kernels 79.9 vs 80.0 ms on one GPU, 13.5 vs 13.5 ms
+    // on a 1/8 shard) - ncu of such a launch (12 warps per SM resident): 53 % of the cycles have no eligible warp (short
+    // scoreboard + fixed-latency waits), i.e. these launches are bound by per-warp latency, not by how items are dealt out.
+    static const int persist_on = std::getenv("ONB_PERSIST") ? atoi(std::getenv("ONB_PERSIST")) : 0;
+    static const int persist_warps = std::getenv("ONB_PERSIST_WARPS") ? std::max(4, atoi(std::getenv("ONB_PERSIST_WARPS"))) : 16;
+    static const int persist_waves = std::getenv("ONB_PERSIST_WAVES") ? std::max(1, atoi(std::getenv("ONB_PERSIST_WAVES"))) : 8;
+    constexpr int warps_per_cta = (128 / TPT + 31) / 32;
+    const uint32_t slots = (uint32_t)c->sm_count * (uint32_t)std::min(32, 64 / warps_per_cta);      // resident CTAs of this shape
+    const uint32_t pgrid = (uint32_t)c->sm_count * (uint32_t)std::max(1, persist_warps / warps_per_cta);
+    a.work = nullptr; a.nwork = grid;
+    if (persist_on && a.work_counter && grid > pgrid && (unsigned long long)grid <= (unsigned long long)persist_waves * slots) { a.work = a.work_counter; grid = pgrid; }
     if (c->arith == ONB_ARITH_STRICT) k_p2p_lists<PHYS, true, TPT, false><<<grid, 128 / TPT, 0, c->stream>>>(a);
     else if (packed && TPT > 1)       k_p2p_lists<PHYS, false, TPT, (TPT > 1)><<<grid, 128 / TPT, 0, c->stream>>>(a);
     else                              k_p2p_lists<PHYS, false, TPT, false><<<grid, 128 / TPT, 0, c->stream>>>(a);
@@ -547,6 +588,11 @@ int onb_p2p_lists(onb_context* c, const WorkList& wl, int tgt_which_leaf, int tg
     a.s_epnum = c->legacy ? c->d_epnum : nullptr;
     a.nsplit = nsplit; a.partial = nullptr; a.ebase = wl.ebase; a.order = wl.order;
     for (int d = 0; d < ONB_MAX_OD; ++d) { a.tud[d] = tl.ud[d]; a.bud[d] = tb.ud[d]; }
+    a.work = nullptr; a.nwork = 0; a.work_counter = nullptr;
+    if (!c->accum64) {
+        ONB_CUDA(onb_dmalloc(c, (void**)&a.work_counter, 4));
+        ONB_CUDA(cudaMemsetAsync(a.work_counter, 0, 4, c->stream));
+    }
     if (c->accum64) {
         if (!tl.ud[0] || (tgt_which_box != tgt_which_leaf && tb.n && !tb.ud[0])) { c->err = "ACCUM = double: set the targets (and build the equivalent target points) after onb_set_accum"; return ONB_ERR_ARG; }
         a.nsplit = 1;
