@@ -7,10 +7,10 @@
  * context (onb_comm_init_all: the C++ drivers' -g=<n>). NCCL is loaded with dlopen at the first use, so single-GPU callers
  * neither link nor need it.
  *
- * Two collectives are all the hot path needs, both IN PLACE on buffers that have the same layout on every rank:
+ * ONE collective is all the hot path needs, IN PLACE on buffers that have the same layout on every rank:
  *   all-gather : rank r owns bytes [r*chunk, (r+1)*chunk) of every listed buffer  -> one ncclAllGather per buffer, grouped
- *   broadcasts : a list of (pointer, bytes, owner) ranges                         -> one ncclBroadcast per range, grouped
- * Both are enqueued on the communicator's own stream; the callers order them against the build / upward streams with events,
+ * (leaf records, source planes, sliced inputs as they lie; the equivalent strengths after packing them per rank, dist.cu).
+ * It is enqueued on the communicator's own stream; the callers order them against the build / upward streams with events,
  * so that they overlap with the tree build of the other particle set and with the local part of the upward pass.
  *
  * A third transport, "loopback", joins contexts of ONE process (any devices, also all on the same one) with plain device
@@ -38,7 +38,6 @@ struct Nccl {
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GetVersion)(int*) = nullptr;
     void* handle = nullptr;
     std::string err;
@@ -57,7 +56,7 @@ bool nccl_load(std::string& err) {
     struct { const char* name; void** fn; } syms[] = {
         {"ncclGetUniqueId", (void**)&g_nccl.GetUniqueId}, {"ncclCommInitRank", (void**)&g_nccl.CommInitRank}, {"ncclCommInitAll", (void**)&g_nccl.CommInitAll},
         {"ncclCommDestroy", (void**)&g_nccl.CommDestroy}, {"ncclGetErrorString", (void**)&g_nccl.GetErrorString}, {"ncclGroupStart", (void**)&g_nccl.GroupStart},
-        {"ncclGroupEnd", (void**)&g_nccl.GroupEnd}, {"ncclAllGather", (void**)&g_nccl.AllGather}, {"ncclBroadcast", (void**)&g_nccl.Broadcast},
+        {"ncclGroupEnd", (void**)&g_nccl.GroupEnd}, {"ncclAllGather", (void**)&g_nccl.AllGather},
         {"ncclGetVersion", (void**)&g_nccl.GetVersion} };
     for (auto& s : syms) { *s.fn = dlsym(h, s.name); if (!*s.fn) { err = std::string("NCCL symbol missing: ") + s.name; return false; } }
     g_nccl.handle = h;
@@ -124,31 +123,6 @@ int onb_comm_allgather(onb_context* c, const std::vector<void*>& bufs, const std
     g->barrier();
     for (int q = 0; q < cm->nranks; ++q) if (q != cm->rank) ONB_CUDA(cudaStreamWaitEvent(cm->stream, g->done[q], 0));   // my buffers stay untouched until every peer has read them
     g->barrier();                                                                                                       // (and the events are not re-recorded before every peer has enqueued its waits)
-    return ONB_OK;
-}
-
-// grouped in-place broadcasts: range k (ptrs[k], bytes[k]) is valid on rank owner[k] and wanted everywhere
-int onb_comm_bcast_ranges(onb_context* c, const std::vector<void*>& ptrs, const std::vector<size_t>& bytes, const std::vector<int>& owner) {
-    OnbComm* cm = c->comm;
-    if (!cm || cm->nranks == 1 || ptrs.empty()) return ONB_OK;
-    if (cm->nccl) {
-        ONB_NCCL(g_nccl.GroupStart());
-        for (size_t k = 0; k < ptrs.size(); ++k)
-            if (bytes[k]) ONB_NCCL(g_nccl.Broadcast(ptrs[k], ptrs[k], bytes[k], NCCL_CHAR, owner[k], cm->nccl, cm->stream));
-        ONB_NCCL(g_nccl.GroupEnd());
-        return ONB_OK;
-    }
-    LoopGroup* g = cm->loop;
-    ONB_CUDA(cudaEventRecord(g->ready[cm->rank], cm->stream));
-    g->ptrs[cm->rank] = ptrs;
-    g->barrier();
-    for (int q = 0; q < cm->nranks; ++q) if (q != cm->rank) ONB_CUDA(cudaStreamWaitEvent(cm->stream, g->ready[q], 0));
-    for (size_t k = 0; k < ptrs.size(); ++k)
-        if (owner[k] != cm->rank && bytes[k]) ONB_CUDA(cudaMemcpyAsync(ptrs[k], g->ptrs[owner[k]][k], bytes[k], cudaMemcpyDefault, cm->stream));
-    ONB_CUDA(cudaEventRecord(g->done[cm->rank], cm->stream));
-    g->barrier();
-    for (int q = 0; q < cm->nranks; ++q) if (q != cm->rank) ONB_CUDA(cudaStreamWaitEvent(cm->stream, g->done[q], 0));
-    g->barrier();
     return ONB_OK;
 }
 

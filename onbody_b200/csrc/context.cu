@@ -181,6 +181,7 @@ void onb_destroy(onb_context* c) {
     onb_comm_destroy(c);
     for (int k = 0; k < 2; ++k) { if (c->d_shared[k]) cudaFree(c->d_shared[k]); if (c->rec_buf[k]) cudaFree(c->rec_buf[k]); }
     if (c->ev_src_planes) cudaEventDestroy(c->ev_src_planes);
+    if (c->eq_stage) cudaFree(c->eq_stage);
     if (c->d_epnum) cudaFree(c->d_epnum);
     if (c->dtt_pool) cudaFree(c->dtt_pool);
     for (auto& e : c->ev_cache) if (e) cudaEventDestroy(e);
@@ -246,6 +247,7 @@ int onb_set_memory_mode(onb_context* c, int mode) {
 static int set_parts(onb_context* c, int which, uint64_t n, const float* const* xs, const float* r, const float* const* ss) {
     if (n == 0 || n >= 0xfffff000ull) { c->err = "particle count out of range for one GPU"; return ONB_ERR_ARG; }
     ONB_CUDA(cudaSetDevice(c->device));
+    if (which == 0) { int jrc = onb_dist_join_source_planes(c, c->stream); if (jrc) return jrc; }     // a plane gather of the previous step may still be in flight
     DParts& p = c->parts[which];
     const uint64_t want_key = (which == 1 && c->mem_mode == ONB_MEM_LEAN && c->shard_n > 1) ? c->plan_key_for(n) : 0ull;
     if (p.n != n || p.unpacked_released || p.sparse_key != want_key || (which == 1 && (p.ud[0] != nullptr) != c->accum64)) { onb_free_parts(c, p); int rc = onb_alloc_parts(c, p, (uint32_t)n, which == 0); if (rc) return rc; }

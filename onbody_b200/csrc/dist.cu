@@ -5,8 +5,8 @@
  * What crosses NVLink, per step (N particles, R ranks, L tree levels):
  *   leaf records   13 floats per leaf of both trees, one in-place all-gather each (0.4 B per particle)   tree.cu k_leafrec_*
  *   source planes  x[PD], r, s[SD]: each rank's tree-ordered range, one grouped in-place all-gather       (20 B per particle)
- *   eq. strengths  s[SD] of the equivalent sources every rank anterpolated for the nodes inside its range,
- *                  grouped in-place broadcasts, one per (level, owner)                                    (4 B per particle)
+ *   eq. strengths  s[SD] of the equivalent sources every rank anterpolated for the nodes inside its range, packed into one
+ *                  chunk per rank, one in-place all-gather, scattered back                                (4 B per particle)
  * Target particles are NOT exchanged: a rank sorts, refines and evaluates only its own leaves, and the node arrays of the
  * whole target tree (the ancestors' centres enter the dual-tree MAC, ongrav3d.cpp:338) follow from the leaf records alone.
  *
@@ -22,7 +22,6 @@
 #include <cstdlib>
 
 int onb_comm_allgather(onb_context* c, const std::vector<void*>& bufs, const std::vector<size_t>& chunk_bytes);
-int onb_comm_bcast_ranges(onb_context* c, const std::vector<void*>& ptrs, const std::vector<size_t>& bytes, const std::vector<int>& owner);
 cudaStream_t onb_comm_stream(const onb_context* c);
 
 static int ensure_plan(onb_context* c, int which) {
@@ -42,8 +41,29 @@ int onb_plan_upload_shared(onb_context* c, int which) {
         if (P.shared[l].size() > (size_t)P.nranks) { c->err = "plan: more straddling nodes than ranks on one level"; return ONB_ERR_UNSUPPORTED; }
         for (size_t k = 0; k < P.shared[l].size(); ++k) h[(size_t)l * P.nranks + k] = P.shared[l][k];
     }
+    // ... followed by the table of the strength exchange: for every rank q and level l the first node it owns and the number of
+    // blocks it owns on the levels above (tab[(q*(L+1) + l)*2 + {0,1}]); tab[..L..][1] = all blocks of rank q
+    const int L = P.levels;
+    std::vector<uint32_t> tab((size_t)P.nranks * (L + 1) * 2, 0u);
+    uint32_t most = 0;
+    for (int q = 0; q < P.nranks; ++q) {
+        uint32_t pre = 0;
+        for (int l = 0; l <= L; ++l) {
+            tab[((size_t)q * (L + 1) + l) * 2 + 1] = pre;
+            if (l < L) {
+                const uint32_t a = P.all_own_lo[(size_t)l * P.nranks + q], b = P.all_own_hi[(size_t)l * P.nranks + q];
+                tab[((size_t)q * (L + 1) + l) * 2] = a;
+                if (l + 1 < L && b > a) pre += b - a;          // the last level holds only leaves: no equivalent particles there
+            }
+        }
+        most = std::max(most, pre);
+    }
+    c->eq_chunk_blocks[which] = most;
+    const size_t shared_words = h.size();
+    h.insert(h.end(), tab.begin(), tab.end());
     ONB_CUDA(cudaMalloc((void**)&c->d_shared[which], h.size() * 4 + 4));
     ONB_CUDA(cudaMemcpy(c->d_shared[which], h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    c->d_eqtab[which] = c->d_shared[which] + shared_words;
     c->shared_key[which] = key;
     return ONB_OK;
 }
@@ -193,6 +213,33 @@ int onb_dist_join_source_planes(onb_context* c, cudaStream_t st) {
     return ONB_OK;
 }
 
+namespace {
+// The strengths of the equivalent sources a rank anterpolated for its own nodes sit in one node interval PER LEVEL. Sending them
+// as they lie would take one broadcast per (level, owner) - 184 small collectives on 8 GPUs, 1.2 ms at N = 1e7 -, so they are
+// packed into one contiguous chunk per rank (blocks in level order), exchanged with ONE in-place all-gather and scattered back.
+struct EqXArgs { float* s[ONB_MAX_SD]; float* stage; const uint32_t* tab; uint32_t chunk_blocks, ebs; int SD, L, me, nranks; };
+__device__ __forceinline__ uint32_t eqx_node(const EqXArgs& a, int q, uint32_t k) {
+    const uint32_t* t = a.tab + (size_t)q * (a.L + 1) * 2;
+    int l = 0;
+    while (l + 1 < a.L && t[(l + 1) * 2 + 1] <= k) ++l;          // levels are few (<= 32): a linear walk
+    return t[l * 2] + (k - t[l * 2 + 1]);
+}
+__global__ void __launch_bounds__(128) k_eqx_pack(const EqXArgs a) {
+    const uint32_t k = blockIdx.x;
+    const uint32_t node = eqx_node(a, a.me, k);
+    float* out = a.stage + ((size_t)a.me * a.chunk_blocks + k) * a.SD * a.ebs;
+    for (int d = 0; d < a.SD; ++d) out[d * a.ebs + threadIdx.x] = a.s[d][(size_t)node * a.ebs + threadIdx.x];
+}
+__global__ void __launch_bounds__(128) k_eqx_unpack(const EqXArgs a) {
+    const int q = (int)(blockIdx.x / a.chunk_blocks);
+    const uint32_t k = blockIdx.x - (uint32_t)q * a.chunk_blocks;
+    if (q == a.me || k >= a.tab[((size_t)q * (a.L + 1) + a.L) * 2 + 1]) return;
+    const uint32_t node = eqx_node(a, q, k);
+    const float* in = a.stage + ((size_t)q * a.chunk_blocks + k) * a.SD * a.ebs;
+    for (int d = 0; d < a.SD; ++d) a.s[d][(size_t)node * a.ebs + threadIdx.x] = in[d * a.ebs + threadIdx.x];
+}
+}  // namespace
+
 // barycentric upward pass of the source tree, on c->stream: own nodes -> exchange of their strengths (comm stream) while the
 // replicated positions pass and the packing of the real sources run -> the few nodes that straddle rank boundaries -> packing
 int onb_dist_upward_sources(onb_context* c) {
@@ -201,23 +248,34 @@ int onb_dist_upward_sources(onb_context* c) {
     const ShardPlan& P = c->plan[0];
     cudaStream_t s1 = c->stream, sc = onb_comm_stream(c);
     rc = onb_bary_upward_mode(c, p, ep, t, ONB_UP_OWN); if (rc) return rc;
+    rc = onb_plan_upload_shared(c, 0); if (rc) return rc;
+    EqXArgs xa; xa.stage = nullptr;
+    for (int d = 0; d < ONB_MAX_SD; ++d) xa.s[d] = ep.s[d];
+    xa.tab = c->d_eqtab[0]; xa.chunk_blocks = c->eq_chunk_blocks[0]; xa.ebs = (uint32_t)c->ebs; xa.SD = c->SD; xa.L = P.levels; xa.me = P.rank; xa.nranks = P.nranks;
+    const size_t chunk_bytes = (size_t)xa.chunk_blocks * c->SD * c->ebs * sizeof(float);
+    if (xa.chunk_blocks) {
+        if (c->eq_stage_cap < chunk_bytes * (size_t)P.nranks) {
+            if (c->eq_stage) cudaFree(c->eq_stage);
+            c->eq_stage = nullptr; c->eq_stage_cap = 0;
+            ONB_CUDA(cudaMalloc((void**)&c->eq_stage, chunk_bytes * (size_t)P.nranks));
+            c->eq_stage_cap = chunk_bytes * (size_t)P.nranks;
+        }
+        xa.stage = c->eq_stage;
+        uint32_t mine = 0;
+        for (int l = 0; l + 1 < P.levels; ++l) mine += P.own_hi[l] - P.own_lo[l];
+        if (mine) { k_eqx_pack<<<mine, 128, 0, s1>>>(xa); ONB_LAUNCH(c); ONB_CUDA(cudaGetLastError()); }
+    }
     ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_UP), s1));
     ONB_CUDA(cudaStreamWaitEvent(sc, onb_cached_event(c, EV_UP), 0));
-    std::vector<void*> ptrs; std::vector<size_t> bytes; std::vector<int> owner;
-    for (int l = 0; l + 1 < P.levels; ++l)
-        for (int r = 0; r < P.nranks; ++r) {
-            const uint32_t a = P.all_own_lo[(size_t)l * P.nranks + r], b = P.all_own_hi[(size_t)l * P.nranks + r];
-            if (b <= a) continue;
-            for (int d = 0; d < c->SD; ++d) { ptrs.push_back(ep.s[d] + (size_t)a * c->ebs); bytes.push_back((size_t)(b - a) * c->ebs * sizeof(float)); owner.push_back(r); }
-        }
     ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_EQ0), sc));
-    rc = onb_comm_bcast_ranges(c, ptrs, bytes, owner); if (rc) return rc;
+    if (xa.chunk_blocks) { rc = onb_comm_allgather(c, {(void*)c->eq_stage}, {chunk_bytes}); if (rc) return rc; }
     ONB_CUDA(cudaEventRecord(onb_cached_event(c, EV_EQ), sc));
     c->eq_timed = true;
     rc = onb_dist_join_source_planes(c, s1); if (rc) return rc;
     rc = onb_bary_upward_mode(c, p, ep, t, ONB_UP_POS); if (rc) return rc;          // needs r of every node's first particle: after the plane gather
     if (!p.packed_valid) { rc = onb_pack_sources(c, p); if (rc) return rc; }
     ONB_CUDA(cudaStreamWaitEvent(s1, onb_cached_event(c, EV_EQ), 0));
+    if (xa.chunk_blocks) { k_eqx_unpack<<<xa.chunk_blocks * (uint32_t)P.nranks, 128, 0, s1>>>(xa); ONB_LAUNCH(c); ONB_CUDA(cudaGetLastError()); }
     rc = onb_bary_upward_mode(c, p, ep, t, ONB_UP_SHARED); if (rc) return rc;
     return onb_pack_sources(c, ep);
 }
@@ -231,8 +289,8 @@ void onb_dist_record_exchange_times(onb_context* c) {
         c->phase_ms["ag_src_planes_bytes"] = (double)c->plan[0].chunk * c->shard_n * sizeof(float) * (c->PD + 1 + c->SD);
     }
     if (c->eq_timed && cudaEventElapsedTime(&ms, onb_cached_event(c, EV_EQ0), onb_cached_event(c, EV_EQ)) == cudaSuccess) {
-        c->phase_ms["bcast_eq_strengths"] = ms;
-        c->phase_ms["bcast_eq_strengths_bytes"] = (double)c->parts[2].n * sizeof(float) * c->SD;
+        c->phase_ms["bcast_eq_strengths"] = ms;          // (name kept from the broadcast form: now one all-gather of packed chunks)
+        c->phase_ms["bcast_eq_strengths_bytes"] = (double)c->eq_chunk_blocks[0] * c->shard_n * c->ebs * sizeof(float) * c->SD;
     }
     cudaGetLastError();
     c->ag_timed = c->eq_timed = false;

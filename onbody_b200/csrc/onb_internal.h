@@ -148,6 +148,8 @@ struct onb_context {
     ShardPlan plan[2];
     uint32_t* d_shared[2] = {nullptr, nullptr};   // device copy of plan[which].shared, [levels * nranks]
     uint64_t shared_key[2] = {0, 0};
+    const uint32_t* d_eqtab[2] = {nullptr, nullptr}; uint32_t eq_chunk_blocks[2] = {0, 0};   // packed exchange of the equivalent strengths (dist.cu)
+    float* eq_stage = nullptr; size_t eq_stage_cap = 0;
     // identifies the partition a sparse allocation / an uploaded plan belongs to (never 0)
     uint64_t plan_key(int which) const { return plan_key_for(parts[which].n); }
     uint64_t plan_key_for(uint64_t n) const { return ((n * 131u + (uint64_t)block) * 131u + (uint64_t)shard_n) * 131u + (uint64_t)shard_rank + 1u; }

@@ -1,6 +1,6 @@
 """CPU tests of the multi-GPU host logic (no GPU needed): the partition arithmetic of csrc/plan.cu against a brute-force
 restatement, and - with gloo at world size 2 and 3 - the data movement the C++ communicator performs with NCCL (in-place
-all-gather of equal leaf-aligned chunks, owner broadcasts of the per-level node intervals), driven by the plan the library
+all-gather of equal leaf-aligned chunks; packed exchange of the per-level node intervals), driven by the plan the library
 computes, on host tensors."""
 import ctypes as C
 import os
@@ -121,7 +121,9 @@ def _worker(rank, world, port, n, block, q):
         parts = [plane[r * chunk:(r + 1) * chunk] for r in range(world)]
         dist.all_gather(parts, plane[rank * chunk:(rank + 1) * chunk].clone())
         ok = bool(torch.equal(plane[:n], truth[:n]))
-        # (2) equivalent strengths: owner broadcasts of the per-level own intervals, then the straddling nodes locally
+        # (2) equivalent strengths (dist.cu k_eqx_pack / k_eqx_unpack): every rank packs the blocks of the nodes it owns, level by
+        #     level, into ITS chunk of a staging buffer, one in-place all-gather of equal chunks, every rank scatters the others'
+        #     chunks back by walking the same per-level intervals; then the straddling nodes locally
         ebs = 4
         levels, nodes = _tree_shape(n, block)
         numnodes = 1 << levels
@@ -131,18 +133,22 @@ def _worker(rank, world, port, n, block, q):
                 want[i * ebs:(i + 1) * ebs] = float(i)
         eq = torch.zeros(numnodes * ebs)
         plans = [_plan(n, block, world, r) for r in range(world)]
+        owned = [[i for l in range(levels - 1) for i in range(int(plans[r][1][l]), int(plans[r][2][l]))] for r in range(world)]
         _, own_lo, own_hi, _, _, shared = plans[rank]
-        for l in range(levels):
-            for i in range(own_lo[l], own_hi[l]):
-                if nodes[i][1] > block:
-                    eq[i * ebs:(i + 1) * ebs] = float(i)
-        for l in range(levels):
-            for r in range(world):
-                a, b = int(plans[r][1][l]), int(plans[r][2][l])
-                if b > a:
-                    seg = eq[a * ebs:b * ebs].clone()
-                    dist.broadcast(seg, src=r)
-                    eq[a * ebs:b * ebs] = seg
+        for i in owned[rank]:
+            if nodes[i][1] > block:
+                eq[i * ebs:(i + 1) * ebs] = float(i)
+        chunk_blocks = max(len(o) for o in owned)
+        stage = torch.full((world * chunk_blocks * ebs,), -7.0)
+        for k, i in enumerate(owned[rank]):
+            stage[(rank * chunk_blocks + k) * ebs:(rank * chunk_blocks + k + 1) * ebs] = eq[i * ebs:(i + 1) * ebs]
+        if chunk_blocks:
+            parts = [stage[r * chunk_blocks * ebs:(r + 1) * chunk_blocks * ebs] for r in range(world)]
+            dist.all_gather(parts, stage[rank * chunk_blocks * ebs:(rank + 1) * chunk_blocks * ebs].clone())
+        for r in range(world):
+            if r != rank:
+                for k, i in enumerate(owned[r]):
+                    eq[i * ebs:(i + 1) * ebs] = stage[(r * chunk_blocks + k) * ebs:(r * chunk_blocks + k + 1) * ebs]
         for l in range(levels):
             for i in shared[l]:
                 eq[i * ebs:(i + 1) * ebs] = float(i)
