@@ -132,6 +132,7 @@ def test_loopback_separate_calls_and_second_step():
 
     def run(rank, g):
         outs = []
+        g.set_sliced_inputs(True)        # every context pulls only its 1/world slice of the inputs; the library all-gathers them
         for inp in steps:
             g.set_sources(*inp); g.set_targets(inp[0], inp[1])
             g.make_tree(0); g.upward(0); g.make_tree(1); g.refine(1); g.upward(1)
