@@ -13,6 +13,11 @@ the dual-tree lists contain (the same lists as the reference's, proven bit-for-b
 value : inputs already resident in HBM when the timed region starts (CUDA events on the library's stream).
 e2e   : the same step through the C ABI with HOST buffers: pinned host -> device copies of sources and targets and
         the device -> host read of the target outputs are inside the timed region.
+N > 1 : one process per GPU; the communicator is the C++ library's own (csrc/comm.cu, NCCL); torch.distributed only ships the
+        128-byte NCCL id, reduces the timings (max over ranks) and sums the work. The hot path is the same three C-ABI calls.
+Also in the record: cold_ms_per_step (a step on never-seen particles), accuracy (rms error against the direct sum on a target
+sample, the drivers' own metric), exchange (device times of the NVLink collectives), device_memory_peak_bytes_per_gpu.
+--particles 1000000000 --gpus 8 is BASELINE configs[4] (lean memory mode is selected automatically).
 The last line printed by rank 0 is the JSON record.
 """
 import argparse
@@ -515,7 +520,9 @@ def main():
     ap.add_argument("--n-ref", type=int, default=0, help="sample size of the CPU reference leg (default: sized to a few minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="lean memory mode (automatic above 4.5e8 particles)")
-    ap.add_argument("--check-error", action="store_true", help="also report the rms error against the direct sum on a target sample")
+    ap.add_argument("--no-check-error", dest="check_error", action="store_false",
+                    help="skip the accuracy leg (rms error against the direct sum on ~2048 sample targets, after the timed regions)")
+    ap.add_argument("--check-error", dest="check_error", action="store_true", default=True, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

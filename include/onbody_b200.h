@@ -23,6 +23,10 @@
  * separate shim libraries (same symbol names, different arity - exactly as in the reference):
  * include/onbody_bh2dvort.h and include/onbody_bh3dvortgrads.h.
  *
+ * Beyond the reference's single-device, float-accumulating drivers the same ABI carries: the multi-GPU communicator
+ * (onb_comm_*: with it attached the phase calls above run distributed and return the same bits), the lean memory mode for
+ * N ~ 1e9 (onb_set_memory_mode), and the reference's ACCUM = double build option (onb_set_accum, ongrav3d.cpp:7-8).
+ *
  * "which" arguments: 0 = sources, 1 = targets, 2 = equivalent sources, 3 = equivalent targets.
  * All array arguments are HOST pointers; planar layout: x is [PD][n], s is [SD][n], u is [OD][n].
  */
