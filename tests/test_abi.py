@@ -86,3 +86,30 @@ def test_bench_reference_arm_runs():
     import json
     rec = json.loads(out)
     assert rec["impl"] == "reference" and rec["value"] > 0 and rec["cpu_baseline"]["kind"] == "reference"
+
+
+@pytest.mark.parametrize("headers", [("onbody_b200.h", "onbody_bh2dvort.h"), ("onbody_b200.h", "onbody_bh3dvortgrads.h")])
+def test_headers_are_plain_c(headers, tmp_path):
+    """the boundary is a C ABI: the headers must compile as C99 (no C++ types, no default arguments) - what a cgo / Fortran /
+    ctypes binding generator would consume. (The two shim headers declare the same names with different arities, exactly as
+    the reference's two libraries do, so they are checked separately.)"""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text("".join('#include "%s"\n' % h for h in headers) + "int main(void) { return 0; }\n")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-fsyntax-only", str(src)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+
+
+def test_communicator_entry_points_without_a_gpu():
+    """host-only parts of the multi-GPU ABI work (and fail loudly) without a device: the partition arithmetic answers, the
+    communicator refuses null contexts instead of crashing"""
+    import ctypes as C
+    lib = ctypes.CDLL(_built())
+    lib.onb_shard_chunk_for.restype = C.c_uint64
+    lib.onb_shard_chunk_for.argtypes = [C.c_uint64, C.c_int, C.c_int]
+    assert lib.onb_shard_chunk_for(10 ** 9, 128, 8) == 976563 * 128          # ceil(7812500 leaves / 8) leaves per rank
+    lib.onb_comm_init_all.argtypes = [C.c_void_p, C.c_int]
+    assert lib.onb_comm_init_all(None, 2) != 0
+    lib.onb_comm_init_loopback.argtypes = [C.c_void_p, C.c_int]
+    assert lib.onb_comm_init_loopback(None, 2) != 0
