@@ -207,3 +207,29 @@ def test_loopback_accum_double_and_refusals():
         lean[0].set_targets(inputs[0], inputs[1])
     for s in lean:
         s.close()
+
+
+@pytest.mark.timeout(600)
+def test_loopback_other_block_size_order_and_unequal_clouds():
+    """the distributed path away from the defaults: block size 64, order 3, different source and target clouds of unequal size"""
+    from onbody_b200.api import GpuSession, driver_inputs, comm_init_loopback, shard_range_for
+    ns, nt, world, theta, block, order = 45000, 31000, 3, 1.3, 64, 3
+    xs, rs, ss = driver_inputs("grav3d", ns, True)
+    rng = np.random.RandomState(11)
+    xt = np.ascontiguousarray(rng.uniform(-1, 1, (3, nt)).astype(np.float32)); rt = np.full(nt, nt ** (-1.0 / 3), np.float32)
+
+    def run(g):
+        g.set_sources(xs, rs, ss); g.set_targets(xt, rt); g.make_trees(); g.prepare_eval()
+        g.zero_vels(); g.fastsumm(theta); a = g.parts(1, ("u", "gidx"))
+        g.zero_vels(); g.treecode3(theta); b = g.parts(1, ("u",))["u"]
+        return a, b, g.parts(2, ("s",))["s"]
+    ref = GpuSession("grav3d", ns, nt, block=block, order=order)
+    want = run(ref); ref.close()
+    sess = [GpuSession("grav3d", ns, nt, block=block, order=order) for _ in range(world)]
+    comm_init_loopback(sess)
+    for rank, (a, b, eq) in enumerate(_on_all(sess, lambda r, g: run(g))):
+        lo, hi = shard_range_for(nt, block, rank, world)
+        assert bits_equal(a["u"][:, lo:hi], want[0]["u"][:, lo:hi]) and bits_equal(a["gidx"][lo:hi], want[0]["gidx"][lo:hi]), rank
+        assert bits_equal(b[:, lo:hi], want[1][:, lo:hi]) and bits_equal(eq, want[2]), rank
+    for s_ in sess:
+        s_.close()
